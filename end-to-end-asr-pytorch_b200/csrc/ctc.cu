@@ -1,0 +1,364 @@
+// K9 (log-softmax half) + K10: CTC loss forward (alpha) and backward (beta, gradient) in one call.
+//
+//   log_softmax_fwd_kernel : one warp per row, online max/sum, writes log-probs (+ lse, argmax)
+//   log_softmax_bwd_kernel : dlogits = g - exp(lp) * sum_c g
+//   ctc_alpha_beta_kernel  : grid (B,2): CTA y=0 runs the alpha recursion, CTA y=1 the beta
+//                            recursion of the same utterance concurrently (they are independent);
+//                            one thread per extended-label position, lattice rows stream to HBM
+//   ctc_grad_kernel        : grid (T-chunks, B): per (b,t) row combines alpha+beta per class with a
+//                            deterministic occurrence-chain sum and streams the V-wide gradient row
+//
+// Semantics restated from the reference call site bin/train_asr.py:49,123-124
+// (torch.nn.CTCLoss(blank=0, zero_infinity=False) -> ATen _ctc_loss/_ctc_loss_backward; Graves 2006
+// eq. 6-8, 10-11, 16) incl. the ATen convention that the returned "log_probs" gradient is
+// exp(lp) - exp(log sum(alpha*beta) + nll - lp)  (SURVEY.md F9).
+#include "common.cuh"
+#include "../../include/b200asr.h"
+
+namespace b200asr {
+
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) log_softmax_fwd_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                             float* __restrict__ lse, long long* __restrict__ amax,
+                                                             long long N, int V) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= N) return;
+    const float* xr = x + row * V;
+    float m = NEG_INF, s = 0.f;
+    int mi = 0x7fffffff;
+    for (int c = lane; c < V; c += 32) {
+        const float v = xr[c];
+        if (v > m) {
+            s = s * expf(m - v) + 1.f;  // m=-inf: s=0 -> 0*exp(-inf)=0
+            m = v;
+            mi = c;
+        } else {
+            s += expf(v - m);
+        }
+    }
+    // warp combine (first index wins ties)
+    float M = m;
+    int MI = mi;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, M, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, MI, o);
+        if (om > M || (om == M && oi < MI)) {
+            M = om;
+            MI = oi;
+        }
+    }
+    const float part = (m == NEG_INF) ? 0.f : s * expf(m - M);
+    const float S = warp_sum(part);
+    const float L = M + logf(S);
+    for (int c = lane; c < V; c += 32) y[row * V + c] = xr[c] - L;
+    if (lane == 0) {
+        if (lse) lse[row] = L;
+        if (amax) amax[row] = MI;
+    }
+}
+
+__global__ void __launch_bounds__(256) log_softmax_bwd_kernel(const float* __restrict__ lp, const float* __restrict__ g,
+                                                             float* __restrict__ dx, long long N, int V) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= N) return;
+    const float* gr = g + row * V;
+    const float* lr = lp + row * V;
+    float s = 0.f;
+    for (int c = lane; c < V; c += 32) s += gr[c];
+    s = warp_sum(s);
+    for (int c = lane; c < V; c += 32) dx[row * V + c] = gr[c] - expf(lr[c]) * s;
+}
+
+// ------------------------------------------------------------------------------------------
+struct CtcParams {
+    const float* lp;     // log-probs, element (b,t,c) at lp[b*sb + t*st + c]
+    long long sb, st;
+    const long long* targets;  // [B, L_max]
+    const long long* in_len;   // [B]
+    const long long* tgt_len;  // [B]
+    int B, T, V, L_max, S_max, blank;
+    float* nll;          // [B]
+    const float* scale;  // [B] or null
+    float* grad;         // same strides as lp, or null
+    float* alpha;        // [B,T,S_max]
+    float* beta;         // [B,T,S_max]
+    int* prev_same;      // [B,S_max]
+    int* is_last;        // [B,S_max]
+};
+
+__device__ __forceinline__ float lse3(float a, float b, float c) {
+    float m = fmaxf(a, fmaxf(b, c));
+    if (m == NEG_INF) return NEG_INF;
+    return logf(expf(a - m) + expf(b - m) + expf(c - m)) + m;
+}
+
+__global__ void __launch_bounds__(1024) ctc_alpha_beta_kernel(CtcParams p) {
+    extern __shared__ float s_dyn[];
+    const int S_max = p.S_max;
+    float* buf0 = s_dyn;
+    float* buf1 = s_dyn + S_max;
+    int* lab = reinterpret_cast<int*>(s_dyn + 2 * S_max);
+    int* skip = lab + S_max;
+
+    const int b = blockIdx.x;
+    const bool is_beta = blockIdx.y == 1;
+    long long Tb64 = p.in_len[b];
+    long long Lb64 = p.tgt_len[b];
+    const int Tb = (int)(Tb64 < 0 ? 0 : (Tb64 > p.T ? p.T : Tb64));
+    const int Lb = (int)(Lb64 < 0 ? 0 : (Lb64 > p.L_max ? p.L_max : Lb64));
+    const int Sb = 2 * Lb + 1;
+    const float* lpb = p.lp + (long long)b * p.sb;
+    float* lat = (is_beta ? p.beta : p.alpha) + (long long)b * p.T * S_max;
+
+    for (int s = threadIdx.x; s < S_max; s += blockDim.x) {
+        int l = -1;
+        if (s < Sb) l = (s & 1) ? (int)p.targets[(long long)b * p.L_max + (s >> 1)] : p.blank;
+        lab[s] = l;
+    }
+    __syncthreads();
+    for (int s = threadIdx.x; s < S_max; s += blockDim.x) {
+        int sk = 0;
+        if (!is_beta) {
+            if (s >= 2 && s < Sb && lab[s] != p.blank && lab[s] != lab[s - 2]) sk = 1;
+        } else {
+            if (s + 2 < Sb && lab[s + 2] != p.blank && lab[s + 2] != lab[s]) sk = 1;
+        }
+        skip[s] = sk;
+        if (!is_beta) {
+            // occurrence chains of equal labels (consumed by ctc_grad_kernel)
+            int prev = -1, last = 0;
+            if ((s & 1) && s < Sb) {
+                const int l = lab[s];
+                for (int q = s - 2; q >= 1; q -= 2)
+                    if (lab[q] == l) { prev = q; break; }
+                last = 1;
+                for (int q = s + 2; q < Sb; q += 2)
+                    if (lab[q] == l) { last = 0; break; }
+            }
+            p.prev_same[(long long)b * S_max + s] = prev;
+            p.is_last[(long long)b * S_max + s] = last;
+        }
+    }
+    __syncthreads();
+
+    if (Tb == 0) {
+        if (!is_beta && threadIdx.x == 0) p.nll[b] = (Lb == 0) ? 0.f : INFINITY;
+        return;
+    }
+
+    float* prev = buf0;
+    float* cur = buf1;
+    const int t0 = is_beta ? Tb - 1 : 0;
+    const int dt = is_beta ? -1 : 1;
+    // boundary row
+    {
+        const float* lpt = lpb + (long long)t0 * p.st;
+        for (int s = threadIdx.x; s < S_max; s += blockDim.x) {
+            float a = NEG_INF;
+            if (!is_beta) {
+                if (s == 0) a = lpt[p.blank];
+                else if (s == 1 && Sb > 1) a = lpt[lab[1]];
+            } else {
+                if (s == Sb - 1) a = lpt[p.blank];
+                else if (s == Sb - 2 && Sb > 1) a = lpt[lab[Sb - 2]];
+            }
+            prev[s] = a;
+            lat[(long long)t0 * S_max + s] = a;
+        }
+    }
+    for (int step = 1; step < Tb; ++step) {
+        const int t = t0 + dt * step;
+        const float* lpt = lpb + (long long)t * p.st;
+        __syncthreads();  // prev fully written
+        for (int s = threadIdx.x; s < S_max; s += blockDim.x) {
+            float v = NEG_INF;
+            if (s < Sb) {
+                const float e = lpt[lab[s]];
+                float a0 = prev[s], a1, a2;
+                if (!is_beta) {
+                    a1 = (s > 0) ? prev[s - 1] : NEG_INF;
+                    a2 = skip[s] ? prev[s - 2] : NEG_INF;
+                } else {
+                    a1 = (s + 1 < Sb) ? prev[s + 1] : NEG_INF;
+                    a2 = skip[s] ? prev[s + 2] : NEG_INF;
+                }
+                v = lse3(a0, a1, a2) + e;
+            }
+            cur[s] = v;
+            lat[(long long)t * S_max + s] = v;
+        }
+        float* tmp = prev; prev = cur; cur = tmp;
+    }
+    if (!is_beta) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const float l1 = prev[Sb - 1];
+            const float l2 = (Sb > 1) ? prev[Sb - 2] : NEG_INF;
+            const float m = fmaxf(l1, l2);
+            const float ll = (m == NEG_INF) ? NEG_INF : logf(expf(l1 - m) + expf(l2 - m)) + m;
+            p.nll[b] = -ll;
+        }
+    }
+}
+
+constexpr int CTC_GRAD_THREADS = 256;
+constexpr int CTC_GRAD_TCHUNK = 8;
+
+__global__ void __launch_bounds__(CTC_GRAD_THREADS) ctc_grad_kernel(CtcParams p) {
+    extern __shared__ float s_dyn[];
+    __shared__ float s_scratch[32];
+    const int S_max = p.S_max, V = p.V;
+    float* acc = s_dyn;             // [V]
+    float* e = s_dyn + V;           // [S_max]
+    int* lab = reinterpret_cast<int*>(e + S_max);
+    int* prev_same = lab + S_max;
+    int* is_last = prev_same + S_max;
+
+    const int b = blockIdx.y;
+    long long Tb64 = p.in_len[b];
+    long long Lb64 = p.tgt_len[b];
+    const int Tb = (int)(Tb64 < 0 ? 0 : (Tb64 > p.T ? p.T : Tb64));
+    const int Lb = (int)(Lb64 < 0 ? 0 : (Lb64 > p.L_max ? p.L_max : Lb64));
+    const int Sb = 2 * Lb + 1;
+    const float nll = p.nll[b];
+    const float scale = p.scale ? p.scale[b] : 1.f;
+
+    for (int c = threadIdx.x; c < V; c += blockDim.x) acc[c] = 0.f;
+    for (int s = threadIdx.x; s < S_max; s += blockDim.x) {
+        int l = -1;
+        if (s < Sb) l = (s & 1) ? (int)p.targets[(long long)b * p.L_max + (s >> 1)] : p.blank;
+        lab[s] = l;
+        prev_same[s] = p.prev_same[(long long)b * S_max + s];
+        is_last[s] = p.is_last[(long long)b * S_max + s];
+    }
+    __syncthreads();
+
+    const int t_begin = blockIdx.x * CTC_GRAD_TCHUNK;
+    const int t_end = min(p.T, t_begin + CTC_GRAD_TCHUNK);
+    for (int t = t_begin; t < t_end; ++t) {
+        float* gt = p.grad + (long long)b * p.sb + (long long)t * p.st;
+        if (t >= Tb) {
+            for (int c = threadIdx.x; c < V; c += blockDim.x) gt[c] = 0.f;
+            continue;
+        }
+        const float* lpt = p.lp + (long long)b * p.sb + (long long)t * p.st;
+        const float* al = p.alpha + ((long long)b * p.T + t) * S_max;
+        const float* be = p.beta + ((long long)b * p.T + t) * S_max;
+        // 1. alpha+beta, row max
+        float mx = NEG_INF;
+        for (int s = threadIdx.x; s < Sb; s += blockDim.x) {
+            const float v = al[s] + be[s];
+            e[s] = v;
+            mx = fmaxf(mx, v);
+        }
+        const float m = block_max(mx, s_scratch);  // includes __syncthreads
+        for (int s = threadIdx.x; s < Sb; s += blockDim.x) {
+            const float v = e[s];
+            e[s] = (v == NEG_INF) ? 0.f : expf(v - m);
+        }
+        __syncthreads();
+        // 2a. blank (even s): fixed-order per-thread partials + fixed tree
+        float part = 0.f;
+        for (int s = 2 * threadIdx.x; s < Sb; s += 2 * blockDim.x) part += e[s];
+        const float tot_blank = block_sum(part, s_scratch);
+        if (threadIdx.x == 0)
+            acc[p.blank] = (tot_blank > 0.f) ? expf(logf(tot_blank) + m + nll - lpt[p.blank]) : 0.f;
+        // 2b. labels (odd s): the thread owning the last occurrence walks the chain backwards
+        for (int s = 2 * threadIdx.x + 1; s < Sb; s += 2 * blockDim.x) {
+            if (is_last[s]) {
+                float tot = 0.f;
+                for (int q = s; q >= 0; q = prev_same[q]) tot += e[q];
+                const int l = lab[s];
+                if (l != p.blank) acc[l] = (tot > 0.f) ? expf(logf(tot) + m + nll - lpt[l]) : 0.f;
+            }
+        }
+        __syncthreads();
+        // 3. stream the gradient row
+        for (int c = threadIdx.x; c < V; c += blockDim.x) gt[c] = (expf(lpt[c]) - acc[c]) * scale;
+        __syncthreads();
+        // 4. reset touched accumulators
+        if (threadIdx.x == 0) acc[p.blank] = 0.f;
+        for (int s = 2 * threadIdx.x + 1; s < Sb; s += 2 * blockDim.x) acc[lab[s]] = 0.f;
+        __syncthreads();
+    }
+}
+
+}  // namespace b200asr
+
+using namespace b200asr;
+
+extern "C" int b200asr_log_softmax_fwd(const float* logits, float* log_probs, float* lse, long long* argmax,
+                                       long long n_rows, int V, b200asr_stream stream) {
+    B200_REQUIRE(logits && log_probs, "log_softmax_fwd: null pointer");
+    B200_REQUIRE(n_rows >= 0 && V > 0, "log_softmax_fwd: bad sizes");
+    if (n_rows == 0) return B200_OK;
+    const int wpb = 8;
+    const long long blocks = (n_rows + wpb - 1) / wpb;
+    log_softmax_fwd_kernel<<<(unsigned)blocks, wpb * 32, 0, (cudaStream_t)stream>>>(logits, log_probs, lse, argmax,
+                                                                                   n_rows, V);
+    B200_LAUNCH_CHECK("log_softmax_fwd_kernel");
+    return B200_OK;
+}
+
+extern "C" int b200asr_log_softmax_bwd(const float* log_probs, const float* grad_out, float* grad_in,
+                                       long long n_rows, int V, b200asr_stream stream) {
+    B200_REQUIRE(log_probs && grad_out && grad_in, "log_softmax_bwd: null pointer");
+    B200_REQUIRE(n_rows >= 0 && V > 0, "log_softmax_bwd: bad sizes");
+    if (n_rows == 0) return B200_OK;
+    const int wpb = 8;
+    const long long blocks = (n_rows + wpb - 1) / wpb;
+    log_softmax_bwd_kernel<<<(unsigned)blocks, wpb * 32, 0, (cudaStream_t)stream>>>(log_probs, grad_out, grad_in,
+                                                                                   n_rows, V);
+    B200_LAUNCH_CHECK("log_softmax_bwd_kernel");
+    return B200_OK;
+}
+
+extern "C" size_t b200asr_ctc_workspace_bytes(int B, int T, int L_max) {
+    const size_t S = 2 * (size_t)L_max + 1;
+    return 2 * (size_t)B * T * S * sizeof(float) + 2 * (size_t)B * S * sizeof(int);
+}
+
+extern "C" int b200asr_ctc_fwd_bwd(const float* log_probs, long long stride_b, long long stride_t,
+                                   const long long* targets, const long long* input_lengths,
+                                   const long long* target_lengths, int B, int T, int V, int L_max, int blank,
+                                   float* nll, const float* grad_scale, float* grad, void* workspace,
+                                   size_t workspace_bytes, b200asr_stream stream) {
+    B200_REQUIRE(log_probs && targets && input_lengths && target_lengths && nll && workspace,
+                 "ctc_fwd_bwd: null pointer");
+    B200_REQUIRE(B > 0 && T > 0 && V > 0 && L_max >= 0, "ctc_fwd_bwd: bad sizes B=%d T=%d V=%d L=%d", B, T, V, L_max);
+    B200_REQUIRE(blank >= 0 && blank < V, "ctc_fwd_bwd: blank %d outside [0,%d)", blank, V);
+    B200_REQUIRE(workspace_bytes >= b200asr_ctc_workspace_bytes(B, T, L_max), "ctc_fwd_bwd: workspace too small");
+    CtcParams p;
+    p.lp = log_probs; p.sb = stride_b; p.st = stride_t; p.targets = targets; p.in_len = input_lengths;
+    p.tgt_len = target_lengths; p.B = B; p.T = T; p.V = V; p.L_max = L_max; p.S_max = 2 * L_max + 1; p.blank = blank;
+    p.nll = nll; p.scale = grad_scale; p.grad = grad;
+    const size_t S = (size_t)p.S_max;
+    float* ws = reinterpret_cast<float*>(workspace);
+    p.alpha = ws;
+    p.beta = ws + (size_t)B * T * S;
+    p.prev_same = reinterpret_cast<int*>(ws + 2 * (size_t)B * T * S);
+    p.is_last = p.prev_same + (size_t)B * S;
+
+    int threads = (p.S_max + 31) / 32 * 32;
+    if (threads > 1024) threads = 1024;
+    const size_t smem_ab = S * (2 * sizeof(float) + 2 * sizeof(int));
+    B200_REQUIRE(smem_ab <= (size_t)max_optin_smem(), "ctc_fwd_bwd: target too long for shared memory (L=%d)", L_max);
+    if (smem_ab > 48 * 1024)
+        B200_CUDA(cudaFuncSetAttribute(ctc_alpha_beta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem_ab));
+    ctc_alpha_beta_kernel<<<dim3(B, 2), threads, smem_ab, (cudaStream_t)stream>>>(p);
+    B200_LAUNCH_CHECK("ctc_alpha_beta_kernel");
+    if (grad) {
+        const size_t smem_g = (size_t)V * sizeof(float) + S * (sizeof(float) + 3 * sizeof(int));
+        B200_REQUIRE(smem_g <= (size_t)max_optin_smem(), "ctc_fwd_bwd: vocabulary %d too large for shared memory", V);
+        if (smem_g > 48 * 1024)
+            B200_CUDA(cudaFuncSetAttribute(ctc_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+        dim3 grid((T + CTC_GRAD_TCHUNK - 1) / CTC_GRAD_TCHUNK, B);
+        ctc_grad_kernel<<<grid, CTC_GRAD_THREADS, smem_g, (cudaStream_t)stream>>>(p);
+        B200_LAUNCH_CHECK("ctc_grad_kernel");
+    }
+    return B200_OK;
+}

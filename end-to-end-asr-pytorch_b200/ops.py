@@ -1,0 +1,263 @@
+"""torch.autograd wrappers around the C-ABI kernels (host-side plumbing; the arithmetic is in csrc/)."""
+import ctypes
+
+import torch
+from torch.autograd import Function
+
+from . import lib as L
+
+
+def _f32c(t):
+    if t.dtype != torch.float32:
+        raise L.B200AsrError("b200asr kernels compute in fp32 (got %s)" % t.dtype)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _gemm_exact():
+    """Plain library GEMMs (cuBLAS through torch) must run in true fp32 for the 1e-4 parity budget."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+
+_gemm_exact()
+
+_perm_cache = {}
+
+
+def gate_perm(H, device):
+    """Row permutation from PyTorch's gate-major [i|f|g|o] layout to the kernels' unit-major layout:
+    new row j*4+g  <-  old row g*H+j."""
+    key = (H, str(device))
+    p = _perm_cache.get(key)
+    if p is None:
+        p = torch.arange(4 * H, device=device).view(4, H).t().reshape(-1).contiguous()
+        _perm_cache[key] = p
+    return p
+
+
+# ----------------------------------------------------------------------------------------------------------
+class BiLSTMFn(Function):
+    """One (bi)directional LSTM layer over zero-padded frames, zero initial state (src/module.py:129-132).
+
+    forward(x[B,T,I], ndir, w_ih_0, w_hh_0, b_ih_0, b_hh_0 [, w_ih_1, w_hh_1, b_ih_1, b_hh_1]) -> out[B,T,ndir*H]
+    The input projection and the weight-gradient contractions are cuBLAS GEMMs; the recurrence (forward and
+    BPTT) is the persistent kernel pair b200asr_bilstm_fwd / b200asr_bilstm_bwd.
+    """
+
+    @staticmethod
+    def forward(ctx, x, ndir, *params):
+        lib = L.load()
+        assert len(params) == 4 * ndir
+        x = _f32c(x)
+        B, T, I = x.shape
+        H = params[1].shape[1]
+        dev = x.device
+        perm = gate_perm(H, dev)
+        x2 = x.view(B * T, I)
+        gates = torch.empty((ndir, B, T, H, 4), device=dev, dtype=torch.float32)
+        w_ih_p = []
+        for d in range(ndir):
+            w_ih, w_hh, b_ih, b_hh = params[4 * d:4 * d + 4]
+            wp = w_ih.detach().index_select(0, perm)
+            bp = (b_ih.detach() + b_hh.detach()).index_select(0, perm)
+            torch.addmm(bp, x2, wp.t(), out=gates[d].view(B * T, 4 * H))
+            w_ih_p.append(wp)
+        w_hh = torch.stack([_f32c(params[4 * d + 1].detach()) for d in range(ndir)]).contiguous()
+        cst = torch.empty((ndir, B, T, H), device=dev, dtype=torch.float32)
+        out = torch.empty((B, T, ndir * H), device=dev, dtype=torch.float32)
+        ws_bytes = lib.b200asr_bilstm_workspace_bytes(B, T, H, ndir)
+        if ws_bytes == 0:
+            raise L.B200AsrError("bilstm: no feasible decomposition for B=%d H=%d (H must be a multiple of 16)" % (B, H))
+        ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+        L.check(lib.b200asr_bilstm_fwd(L.ptr(gates), L.ptr(w_hh), L.ptr(cst), L.ptr(out), B, T, H, ndir, L.ptr(ws),
+                                       ws_bytes, L.stream()), "bilstm_fwd")
+        ctx.ndir = ndir
+        ctx.dims = (B, T, I, H)
+        ctx.consumed = False
+        ctx.save_for_backward(x, gates, cst, out, w_hh, *w_ih_p)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = L.load()
+        if ctx.consumed:
+            raise L.B200AsrError("BiLSTMFn.backward ran twice: the gate stash is overwritten in place")
+        ctx.consumed = True
+        ndir = ctx.ndir
+        B, T, I, H = ctx.dims
+        x, gates, cst, out, w_hh = ctx.saved_tensors[:5]
+        w_ih_p = ctx.saved_tensors[5:]
+        dev = x.device
+        dout = _f32c(dout)
+        ws_bytes = lib.b200asr_bilstm_workspace_bytes(B, T, H, ndir)
+        ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+        L.check(lib.b200asr_bilstm_bwd(L.ptr(gates), L.ptr(w_hh), L.ptr(cst), L.ptr(dout), B, T, H, ndir, L.ptr(ws),
+                                       ws_bytes, L.stream()), "bilstm_bwd")
+        perm = gate_perm(H, dev)
+        x2 = x.view(B * T, I)
+        dx2 = None
+        grads = []
+        for d in range(ndir):
+            dG = gates[d].view(B * T, 4 * H)  # d(loss)/d(pre-activation), unit-major columns
+            dx2 = torch.mm(dG, w_ih_p[d]) if dx2 is None else torch.addmm(dx2, dG, w_ih_p[d])
+            dw_ih = torch.empty((4 * H, I), device=dev, dtype=torch.float32)
+            dw_ih.index_copy_(0, perm, torch.mm(dG.t(), x2))
+            db = torch.empty((4 * H,), device=dev, dtype=torch.float32)
+            db.index_copy_(0, perm, dG.sum(0))
+            dG3 = gates[d].view(B, T, 4 * H)
+            hd = out[:, :, d * H:(d + 1) * H]
+            if T > 1:
+                if d == 0:   # h_{t-1} = out[:, t-1]
+                    dw = torch.bmm(dG3[:, 1:].transpose(1, 2), hd[:, :-1]).sum(0)
+                else:        # reverse direction: the previous step is t+1
+                    dw = torch.bmm(dG3[:, :-1].transpose(1, 2), hd[:, 1:]).sum(0)
+            else:
+                dw = torch.zeros((4 * H, H), device=dev, dtype=torch.float32)
+            dw_hh = torch.empty((4 * H, H), device=dev, dtype=torch.float32)
+            dw_hh.index_copy_(0, perm, dw)
+            grads += [dw_ih, dw_hh, db, db.clone()]
+        return (dx2.view(B, T, I), None, *grads)
+
+
+def bilstm(x, lstm_params, ndir):
+    return BiLSTMFn.apply(x, ndir, *lstm_params)
+
+
+# ----------------------------------------------------------------------------------------------------------
+class LogSoftmaxFn(Function):
+    """log_softmax over the last dim (src/asr.py:96) + greedy argmax ids as a by-product."""
+
+    @staticmethod
+    def forward(ctx, logits):
+        lib = L.load()
+        x = _f32c(logits)
+        V = x.shape[-1]
+        n = x.numel() // V
+        y = torch.empty_like(x)
+        am = torch.empty(x.shape[:-1], device=x.device, dtype=torch.int64)
+        L.check(lib.b200asr_log_softmax_fwd(L.ptr(x), L.ptr(y), None, L.ptr(am), n, V, L.stream()), "log_softmax_fwd")
+        ctx.save_for_backward(y)
+        ctx.mark_non_differentiable(am)
+        return y, am
+
+    @staticmethod
+    def backward(ctx, g, _gam):
+        lib = L.load()
+        (y,) = ctx.saved_tensors
+        g = _f32c(g)
+        V = y.shape[-1]
+        n = y.numel() // V
+        dx = torch.empty_like(y)
+        L.check(lib.b200asr_log_softmax_bwd(L.ptr(y), L.ptr(g), L.ptr(dx), n, V, L.stream()), "log_softmax_bwd")
+        return dx
+
+
+def log_softmax(logits):
+    return LogSoftmaxFn.apply(logits)
+
+
+class CTCLossFn(Function):
+    """sum_b weight_b * nll_b with the gradient produced in the same kernel call (forward + backward fused).
+
+    log_probs: [T,B,V] view of [B,T,V] memory (or any layout with unit class stride), like the reference passes
+    `ctc_output.transpose(0,1)` (bin/train_asr.py:123-124).
+    """
+
+    @staticmethod
+    def forward(ctx, log_probs, targets, input_lengths, target_lengths, blank, weights):
+        lib = L.load()
+        if log_probs.dtype != torch.float32 or log_probs.stride(2) != 1:
+            log_probs = log_probs.float().contiguous()
+        T, B, V = log_probs.shape
+        dev = log_probs.device
+        targets = targets.to(device=dev, dtype=torch.int64).contiguous()
+        if targets.dim() != 2:
+            raise L.B200AsrError("CTC targets must be a padded [B, L] tensor (cudnn-style 1-D targets unsupported)")
+        Lmax = targets.shape[1]
+        il = torch.as_tensor(input_lengths, dtype=torch.int64).to(dev).contiguous()
+        tl = torch.as_tensor(target_lengths, dtype=torch.int64).to(dev).contiguous()
+        w = _f32c(weights.to(dev))
+        nll = torch.empty(B, device=dev, dtype=torch.float32)
+        # gradient buffer laid out like log_probs' memory
+        grad = torch.empty_strided(log_probs.shape, log_probs.stride(), device=dev, dtype=torch.float32)
+        ws_bytes = lib.b200asr_ctc_workspace_bytes(B, T, Lmax)
+        ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+        L.check(lib.b200asr_ctc_fwd_bwd(L.ptr(log_probs), log_probs.stride(1), log_probs.stride(0), L.ptr(targets),
+                                        L.ptr(il), L.ptr(tl), B, T, V, Lmax, blank, L.ptr(nll), L.ptr(w), L.ptr(grad),
+                                        L.ptr(ws), ws_bytes, L.stream()), "ctc_fwd_bwd")
+        ctx.save_for_backward(grad)
+        ctx.mark_non_differentiable(nll)
+        loss = (nll * w).sum()
+        return loss, nll
+
+    @staticmethod
+    def backward(ctx, gloss, _gnll):
+        (grad,) = ctx.saved_tensors
+        return grad.mul_(gloss), None, None, None, None, None   # stash consumed in place
+
+
+class CTCLoss(torch.nn.Module):
+    """Drop-in for torch.nn.CTCLoss(blank, reduction, zero_infinity=False) at bin/train_asr.py:49.
+
+    `global_batch` lets a data-parallel rank normalise by the global batch size."""
+
+    def __init__(self, blank=0, reduction="mean", zero_infinity=False):
+        super().__init__()
+        if zero_infinity:
+            raise NotImplementedError("zero_infinity=True is not part of the reference path")
+        self.blank = blank
+        self.reduction = reduction
+        self.global_batch = None
+
+    def forward(self, log_probs, targets, input_lengths, target_lengths):
+        B = log_probs.shape[1]
+        dev = log_probs.device
+        tl = torch.as_tensor(target_lengths, dtype=torch.int64).to(dev)
+        if self.reduction == "mean":
+            denom = float(self.global_batch or B)
+            w = 1.0 / (tl.clamp_min(1).to(torch.float32) * denom)
+        elif self.reduction == "sum":
+            w = torch.ones(B, device=dev, dtype=torch.float32)
+        else:
+            raise NotImplementedError("reduction=%s" % self.reduction)
+        loss, nll = CTCLossFn.apply(log_probs, targets, input_lengths, tl, self.blank, w)
+        self.last_nll = nll
+        return loss
+
+
+# ----------------------------------------------------------------------------------------------------------
+class LSTMCellFn(Function):
+    """Pointwise part of one LSTM step (decoder, src/asr.py:214-221): pre[B,4H] (i,f,g,o) , c_prev -> h, c."""
+
+    @staticmethod
+    def forward(ctx, pre, c_prev):
+        lib = L.load()
+        pre = _f32c(pre)
+        c_prev = _f32c(c_prev)
+        B, H4 = pre.shape
+        H = H4 // 4
+        gates = torch.empty_like(pre)
+        c = torch.empty_like(c_prev)
+        h = torch.empty_like(c_prev)
+        L.check(lib.b200asr_lstm_cell_fwd(L.ptr(pre), L.ptr(c_prev), L.ptr(gates), L.ptr(c), L.ptr(h), B, H,
+                                          L.stream()), "lstm_cell_fwd")
+        ctx.save_for_backward(gates, c_prev, c)
+        return h, c
+
+    @staticmethod
+    def backward(ctx, dh, dc):
+        lib = L.load()
+        gates, c_prev, c = ctx.saved_tensors
+        B, H4 = gates.shape
+        H = H4 // 4
+        dh = _f32c(dh) if dh is not None else torch.zeros_like(c)
+        dcn = _f32c(dc) if dc is not None else None
+        dpre = torch.empty_like(gates)
+        dcp = torch.empty_like(c)
+        L.check(lib.b200asr_lstm_cell_bwd(L.ptr(gates), L.ptr(c_prev), L.ptr(c), L.ptr(dh), L.ptr(dcn), L.ptr(dpre),
+                                          L.ptr(dcp), B, H, L.stream()), "lstm_cell_bwd")
+        return dpre, dcp
+
+
+def lstm_cell(pre, c_prev):
+    return LSTMCellFn.apply(pre, c_prev)

@@ -1,0 +1,123 @@
+/* libb200asr.so - C ABI of the B200-native ASR train-step kernels (sm_100a).
+ *
+ * The reference (Alexander-H-Liu/End-to-end-ASR-Pytorch) is 100% Python and has no FFI of its own: every
+ * "kernel" is a stock torch / torchaudio call.  Each entry point below therefore cites the reference CALL SITE
+ * (file:line under /root/reference, or kaldi.py = torchaudio/compliance/kaldi.py) whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless stated otherwise; tensors are contiguous row-major fp32,
+ *     indices / lengths are int64 ("long long") where the reference passes LongTensors, int32 otherwise;
+ *   - the library never allocates, frees or retains device memory: the caller owns inputs, outputs and the
+ *     workspaces whose sizes the *_workspace_bytes() helpers return;
+ *   - all work is enqueued on `stream` (a cudaStream_t) and the call returns without synchronising;
+ *   - return value: 0 = ok, <0 = error (-1 invalid argument, -2 CUDA failure); the message is available
+ *     from b200asr_last_error() (thread local).  There is no CPU fallback.
+ */
+#ifndef B200ASR_H
+#define B200ASR_H
+
+#include <stddef.h>
+
+#define B200ASR_VERSION 100
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define B200ASR_API __attribute__((visibility("default")))
+#else
+#define B200ASR_API
+#endif
+
+typedef void* b200asr_stream; /* cudaStream_t */
+
+B200ASR_API int b200asr_version(void);
+B200ASR_API const char* b200asr_last_error(void);
+/* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
+B200ASR_API unsigned long long b200asr_launch_count(void);
+B200ASR_API void b200asr_launch_count_reset(void);
+B200ASR_API int b200asr_device_sm_count(void);
+
+/* ---- K1: fused STFT + mel + log -----------------------------------------------------------------------
+ * replaces src/audio.py:104-108 -> kaldi.py:514-646 (fbank), :44-83 (framing), :154-217 (dc / pre-emphasis /
+ * window).  wave [B, n_max] (zero padded), wave_len [B] samples.  window [win_size] and the sparse mel
+ * filters (filter i covers FFT bins mel_start[i] .. +mel_count[i], weights at mel_w[mel_off[i] ..]) are
+ * caller-built tables.  fbank [B, t_max, n_mel] (frames >= n_frames[b] are zeroed), n_frames [B] (int32 out)
+ * = 1 + (len - win_size) / win_shift (snip_edges=True).  n_fft must be 512.                               */
+B200ASR_API int b200asr_fbank_fwd(const float* wave, const int* wave_len, int B, int n_max, int win_size, int win_shift,
+                      int n_fft, float preemph, int remove_dc, const float* window, int n_mel,
+                      const int* mel_start, const int* mel_count, const int* mel_off, const float* mel_w,
+                      int mel_w_total, int use_log, float log_floor, float* fbank, int t_max, int* n_frames,
+                      b200asr_stream stream);
+
+/* ---- K2+K3: delta / delta-delta + per-utterance CMVN + channel-major interleave ---------------------------
+ * replaces src/audio.py:51-54,57-77 (Delta), :25-27 (CMVN, unbiased std, eps added to std), :85-89
+ * (Postprocess).  feat [B, t_max, n_mel*(delta_order+1)], rows >= n_frames[b] are zero (pad_sequence,
+ * src/data.py:39).                                                                                          */
+B200ASR_API int b200asr_delta_cmvn_fwd(const float* fbank, const int* n_frames, int B, int t_max, int n_mel,
+                           int delta_order, int delta_window, int apply_cmvn, float cmvn_eps, float* feat,
+                           b200asr_stream stream);
+
+/* ---- K9: log-softmax over the vocabulary (src/asr.py:96) -------------------------------------------------
+ * log_probs may alias logits.  lse [n_rows] and argmax [n_rows] (int64; util.py:117-118 / test_asr.py:116-118)
+ * are optional (NULL).                                                                                      */
+B200ASR_API int b200asr_log_softmax_fwd(const float* logits, float* log_probs, float* lse, long long* argmax,
+                            long long n_rows, int V, b200asr_stream stream);
+B200ASR_API int b200asr_log_softmax_bwd(const float* log_probs, const float* grad_out, float* grad_in, long long n_rows,
+                            int V, b200asr_stream stream);
+
+/* ---- K10: CTC loss forward + backward in one call ---------------------------------------------------------
+ * replaces torch.nn.CTCLoss(blank=0, zero_infinity=False) at bin/train_asr.py:49,123-124 (ATen _ctc_loss +
+ * _ctc_loss_backward).  log_probs element (b,t,c) lives at log_probs[b*stride_b + t*stride_t + c]; targets
+ * [B, L_max] zero padded int64; input_lengths / target_lengths [B] int64.  nll [B] out (per-utterance negative
+ * log likelihood, +inf when infeasible).  If grad != NULL it receives, with the same strides as log_probs,
+ * grad_scale[b] * (exp(lp) - exp(log sum_{s: l'_s = c} alpha_t(s) beta_t(s) + nll - lp)) for t < input_length
+ * and 0 after it - ATen's convention.  grad_scale may be NULL (= 1).                         */
+B200ASR_API size_t b200asr_ctc_workspace_bytes(int B, int T, int L_max);
+B200ASR_API int b200asr_ctc_fwd_bwd(const float* log_probs, long long stride_b, long long stride_t, const long long* targets,
+                        const long long* input_lengths, const long long* target_lengths, int B, int T, int V,
+                        int L_max, int blank, float* nll, const float* grad_scale, float* grad, void* workspace,
+                        size_t workspace_bytes, b200asr_stream stream);
+
+/* ---- K7/K8: persistent (Bi)LSTM recurrence -----------------------------------------------------------------
+ * replaces the time loop inside torch.nn.LSTM as used by src/module.py:112-113,129-132 (one layer,
+ * batch_first, zero initial state, run over the padded frames).  ndir = 1 or 2 (direction 1 = reverse time).
+ *   gates  [ndir, B, T, H, 4]  in : input projection x.W_ih^T + b_ih + b_hh, gate-interleaved (i,f,g,o minor)
+ *                              out: the activated gates (stash for the backward pass)
+ *   w_hh   [ndir, 4H, H]       PyTorch layout (weight_hh_l0 [, weight_hh_l0_reverse])
+ *   cstate [ndir, B, T, H]     out: cell state after every step (stash)
+ *   out    [B, T, ndir*H]      out: hidden states (the layer output)
+ * backward: gates in = stash, out = d(loss)/d(pre-activation) in the same layout; dout [B, T, ndir*H].
+ * H must be a multiple of 16; the (unit-block, batch-block) decomposition must fit the SM count
+ * (b200asr_bilstm_plan reports it).  Launched cooperatively: all CTAs are co-resident.                       */
+B200ASR_API size_t b200asr_bilstm_workspace_bytes(int B, int T, int H, int ndir);
+B200ASR_API int b200asr_bilstm_plan(int B, int H, int ndir, int* unit_block, int* batch_block, int* n_ctas);
+B200ASR_API int b200asr_bilstm_fwd(float* gates, const float* w_hh, float* cstate, float* out, int B, int T, int H, int ndir,
+                       void* workspace, size_t workspace_bytes, b200asr_stream stream);
+B200ASR_API int b200asr_bilstm_bwd(float* gates, const float* w_hh, const float* cstate, const float* dout, int B, int T,
+                       int H, int ndir, void* workspace, size_t workspace_bytes, b200asr_stream stream);
+
+/* ---- K13: one LSTM cell step (decoder, src/asr.py:214-221) -------------------------------------------------
+ * preact [B, 4H] gate-major (i,f,g,o) = x.W_ih^T + h.W_hh^T + biases; gates [B,4H] activated (stash).        */
+B200ASR_API int b200asr_lstm_cell_fwd(const float* preact, const float* c_prev, float* gates, float* c, float* h, int B,
+                          int H, b200asr_stream stream);
+B200ASR_API int b200asr_lstm_cell_bwd(const float* gates, const float* c_prev, const float* c, const float* dh,
+                          const float* dc_next /* may be NULL */, float* dpreact, float* dc_prev, int B, int H,
+                          b200asr_stream stream);
+
+/* ---- K16: gradient norm, clip and optimizer update on flat buffers (src/solver.py:84-89, src/optim.py) ----
+ * grad_norm (device scalar) may be NULL (no clipping, no NaN skip); max_norm <= 0 disables clipping.          */
+B200ASR_API size_t b200asr_grad_norm_scratch_bytes(void);
+B200ASR_API int b200asr_grad_norm(const float* grad, long long n, float* norm_out, void* scratch, b200asr_stream stream);
+B200ASR_API int b200asr_adadelta_step(float* param, const float* grad, float* square_avg, float* acc_delta, long long n,
+                          float lr, float rho, float eps, float weight_decay, const float* grad_norm,
+                          float max_norm, b200asr_stream stream);
+B200ASR_API int b200asr_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                      float beta1, float beta2, float eps, float weight_decay, int step, const float* grad_norm,
+                      float max_norm, b200asr_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200ASR_H */

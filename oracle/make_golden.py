@@ -1,0 +1,189 @@
+"""Generate tests/golden/*.npz by RUNNING the unmodified reference (CPU) in the build container.
+
+    python -m oracle.make_golden            # from the repo root; needs /root/reference
+
+The vectors pin the oracle (oracle_np.py, ref_port.py) and are the committed authority the GPU parity tests compare
+against on the GPU box, where /root/reference does not exist.  Everything is seeded; sizes are tiny on purpose.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+from . import ref_shim
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+AUDIO_CFG = dict(feat_type="fbank", feat_dim=40, frame_length=25, frame_shift=10, dither=0, apply_cmvn=True,
+                 delta_order=2, delta_window_size=2)
+
+
+def tiny_model_cfg(kind):
+    enc = dict(prenet="", module="LSTM", bidirection=True, dim=[32, 32], dropout=[0, 0], layer_norm=[False, False],
+               proj=[False, False], sample_rate=[1, 2], sample_style="concat")
+    att = dict(mode="loc", dim=16, num_head=1, v_proj=False, temperature=0.5, loc_kernel_size=5, loc_kernel_num=4)
+    dec = dict(module="LSTM", dim=32, layer=1, dropout=0)
+    if kind == "ctc":
+        return dict(ctc_weight=1.0, encoder=enc, attention=att, decoder=dec)
+    if kind == "hybrid":
+        return dict(ctc_weight=0.3, encoder=enc, attention=att, decoder=dec)
+    if kind == "cnn":
+        enc = dict(prenet="cnn", module="LSTM", bidirection=True, dim=[48, 48], dropout=[0, 0],
+                   layer_norm=[False, False], proj=[True, True], sample_rate=[1, 1], sample_style="drop")
+        return dict(ctc_weight=0.3, encoder=enc, attention=att, decoder=dec)
+    if kind == "att":
+        enc = dict(enc, sample_rate=[1, 1], proj=[True, False], sample_style="drop")
+        dec = dict(dec, layer=2)
+        return dict(ctc_weight=0.0, encoder=enc, attention=att, decoder=dec)
+    raise KeyError(kind)
+
+
+def synth_batch(seed, B, T, D, V, Lmax, ragged=True):
+    g = torch.Generator().manual_seed(seed)
+    feat_len = torch.full((B,), T, dtype=torch.long)
+    if ragged:
+        feat_len = torch.sort(torch.randint(max(T // 2, 8), T + 1, (B,), generator=g), descending=True)[0]
+        feat_len[0] = T
+    feat = torch.randn(B, T, D, generator=g)
+    for b in range(B):
+        feat[b, feat_len[b]:] = 0
+    txt = torch.zeros(B, Lmax, dtype=torch.long)
+    for b in range(B):
+        L = int(torch.randint(2, Lmax, (1,), generator=g))
+        ids = torch.randint(3, V, (L,), generator=g)
+        if L > 3:
+            ids[2] = ids[1]                      # force a repeated label (CTC needs the blank between them)
+        txt[b, :L] = ids
+        txt[b, L] = 1                            # <eos>
+    return feat, feat_len, txt
+
+
+def golden_frontend():
+    from src.audio import create_transform                                    # the reference's
+    from scipy.io import wavfile
+    wav = os.path.join(ref_shim.REF_ROOT, "tests", "sample_data", "3830-12529-0005.wav")
+    sr, pcm = wavfile.read(wav)
+    out = {"sample_pcm": pcm.astype(np.int16), "sample_rate": np.int64(sr)}
+    for order in (0, 1, 2):
+        cfg = dict(AUDIO_CFG, delta_order=order)
+        tr, dim = create_transform(cfg.copy())
+        y = tr(wav)
+        out["sample_feat_d%d" % order] = y.numpy().astype(np.float32)
+    cfg = dict(AUDIO_CFG, delta_order=0, apply_cmvn=False)
+    tr, _ = create_transform(cfg.copy())
+    out["sample_fbank_raw"] = tr(wav).numpy().astype(np.float32)
+    # synthetic, different lengths (incl. one exactly one frame long and one with a remainder)
+    import torchaudio
+    g = torch.Generator().manual_seed(1234)
+    real_load = torchaudio.load
+    for i, n in enumerate([400, 4000, 7013, 16000]):
+        w = torch.clamp(0.05 * torch.randn(1, n, generator=g) + 0.02 * torch.sin(torch.arange(n) * 0.05 * (i + 1)),
+                        -1, 1)
+        torchaudio.load = lambda path, _w=w: (_w, 16000)
+        tr, _ = create_transform(dict(AUDIO_CFG).copy())
+        raw, _ = create_transform(dict(AUDIO_CFG, delta_order=0, apply_cmvn=False).copy())
+        out["syn%d_wave" % i] = w[0].numpy()
+        out["syn%d_raw" % i] = raw("x").numpy().astype(np.float32)
+        if n > 400:
+            out["syn%d_feat" % i] = tr("x").numpy().astype(np.float32)
+    torchaudio.load = real_load
+    np.savez_compressed(os.path.join(OUT, "frontend.npz"), **out)
+    print("frontend.npz", {k: v.shape for k, v in out.items() if hasattr(v, "shape")})
+
+
+def golden_model(kind, seed, B, T, D, V, Lmax):
+    from src.asr import ASR                                                   # the reference's
+    cfg = tiny_model_cfg(kind)
+    torch.manual_seed(seed)
+    model = ASR(D, V, True, **cfg)
+    model.train()
+    feat, feat_len, txt = synth_batch(seed + 1, B, T, D, V, Lmax)
+    txt_len = (txt != 0).sum(-1)
+    ctc_out, enc_len, att_out, att_seq, _ = model(feat, feat_len, int(txt_len.max()), tf_rate=1.0, teacher=txt)
+    out = {"feat": feat.numpy(), "feat_len": feat_len.numpy(), "txt": txt.numpy(), "encode_len": enc_len.numpy()}
+    total = 0
+    if ctc_out is not None:
+        ctc = torch.nn.CTCLoss(blank=0, zero_infinity=False)(ctc_out.transpose(0, 1), txt, enc_len, txt_len)
+        total = total + ctc * model.ctc_weight
+        out["ctc_output"] = ctc_out.detach().numpy()
+        out["ctc_loss"] = ctc.detach().numpy()
+        out["ctc_argmax"] = ctc_out.argmax(-1).numpy()
+    if att_out is not None:
+        b, t, _ = att_out.shape
+        ce = torch.nn.CrossEntropyLoss(ignore_index=0)(att_out.view(b * t, -1), txt[:, :t].reshape(-1))
+        total = total + ce * (1 - model.ctc_weight)
+        out["att_output"] = att_out.detach().numpy()
+        out["att_seq"] = att_seq.detach().numpy()
+        out["att_loss"] = ce.detach().numpy()
+        out["att_argmax"] = att_out.argmax(-1).numpy()
+    total.backward()
+    out["total_loss"] = total.detach().numpy()
+    gn = torch.nn.utils.clip_grad_norm_(model.parameters(), 5.0)
+    out["grad_norm"] = np.float32(gn)
+    for k, v in model.state_dict().items():
+        out["sd." + k] = v.numpy()
+    for k, p in model.named_parameters():
+        if p.grad is not None:
+            # clip_grad_norm_ scaled the grads in place: undo so the vectors hold the raw gradients
+            coef = min(1.0, 5.0 / (float(gn) + 1e-6))
+            out["grad." + k] = (p.grad / coef).numpy()
+    # greedy inference outputs as well (teacher=None, argmax feedback), src/asr.py:137-142
+    if att_out is not None:
+        model.eval()
+        with torch.no_grad():
+            _, _, g_out, g_seq, _ = model(feat, feat_len, int(txt_len.max()) + 2)
+        out["greedy_argmax"] = g_out.argmax(-1).numpy()
+        out["greedy_output"] = g_out.numpy()
+    np.savez_compressed(os.path.join(OUT, "model_%s.npz" % kind), **out)
+    print("model_%s.npz" % kind, "loss", float(total), "grad_norm", float(gn))
+
+
+def golden_ctc():
+    """torch.nn.functional.ctc_loss + torch._ctc_loss (log_alpha) on adversarial small cases."""
+    g = torch.Generator().manual_seed(7)
+    cases = []
+    # (T, V, targets, input_len)
+    specs = [
+        (12, 6, [1, 2, 2, 3], 12),       # repeated label
+        (10, 5, [], 10),                 # empty target
+        (7, 5, [1, 1, 1, 1], 7),         # exactly feasible (needs 4 + 3 blanks = 7)
+        (6, 5, [1, 1, 1, 1], 6),         # infeasible -> inf
+        (15, 8, [3, 4, 5, 3, 4, 5, 6], 9),   # input shorter than T
+        (1, 4, [2], 1),                  # single frame
+    ]
+    out = {}
+    for i, (T, V, tgt, il) in enumerate(specs):
+        lp = torch.randn(T, 1, V, generator=g).log_softmax(-1).requires_grad_(True)
+        t = torch.tensor([tgt + [0]], dtype=torch.long) if tgt else torch.zeros(1, 1, dtype=torch.long)
+        tl = torch.tensor([len(tgt)])
+        ilt = torch.tensor([il])
+        nll, log_alpha = torch._ctc_loss(lp, t, ilt, tl, 0, False)
+        loss = torch.nn.functional.ctc_loss(lp, t, ilt, tl, blank=0, reduction="sum", zero_infinity=False)
+        loss.backward()
+        out["c%d_lp" % i] = lp.detach()[:, 0].numpy()
+        out["c%d_tgt" % i] = t[0].numpy()
+        out["c%d_tl" % i] = tl.numpy()
+        out["c%d_il" % i] = ilt.numpy()
+        out["c%d_nll" % i] = nll.detach().numpy()
+        out["c%d_alpha" % i] = log_alpha.detach()[0].numpy()
+        out["c%d_grad" % i] = lp.grad[:, 0].numpy()
+    out["n_cases"] = np.int64(len(specs))
+    np.savez_compressed(os.path.join(OUT, "ctc_cases.npz"), **out)
+    print("ctc_cases.npz", len(specs), "cases")
+
+
+def main():
+    ref_shim.install()
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(1)
+    golden_frontend()
+    golden_ctc()
+    golden_model("ctc", 11, 3, 24, 8, 12, 5)
+    golden_model("hybrid", 21, 3, 24, 8, 12, 5)
+    golden_model("cnn", 31, 2, 40, 8, 12, 5)
+    golden_model("att", 41, 3, 16, 8, 12, 6)
+
+
+if __name__ == "__main__":
+    main()
