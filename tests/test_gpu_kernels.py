@@ -1,0 +1,271 @@
+"""Parity of every CUDA kernel (through the C ABI) against the CPU oracle / committed golden vectors.
+Run on the B200 box: python -m pytest tests -m gpu."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import load_golden, rel_err
+from oracle import oracle_np as onp
+from oracle import ref_port
+from oracle.make_golden import AUDIO_CFG
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+# ------------------------------------------------------------------------------------------- front end
+def _frontend(pkg, **over):
+    cfg = dict(AUDIO_CFG)
+    cfg.update(over)
+    tr, dim = pkg.create_transform(cfg, device=DEV)
+    return tr, dim
+
+
+def test_fbank_sample_wav_vs_reference_golden(pkg):
+    g = load_golden("frontend.npz")
+    wave = torch.from_numpy(g["sample_pcm"].astype(np.float32) / 32768.0)[None].to(DEV)
+    tr, _ = _frontend(pkg, delta_order=0, apply_cmvn=False)
+    fb, n = tr.batch(wave, [wave.shape[1]])
+    assert int(n[0]) == 392 and fb.shape == (1, 392, 40)
+    assert rel_err(fb[0].cpu().numpy(), g["sample_fbank_raw"], floor=1.0) < 1e-4
+    for order in (0, 1, 2):
+        tr, dim = _frontend(pkg, delta_order=order)
+        y, n = tr.batch(wave, [wave.shape[1]])
+        assert dim == 40 * (order + 1) and y.shape == (1, 392, dim)
+        assert float(np.max(np.abs(y[0].cpu().numpy() - g["sample_feat_d%d" % order]))) < 1e-3
+
+
+def test_fbank_ragged_batch_vs_reference_golden(pkg):
+    g = load_golden("frontend.npz")
+    waves = [g["syn%d_wave" % i] for i in (3, 2, 1, 0)]           # 16000, 7013, 4000, 400 samples
+    lens = [len(w) for w in waves]
+    batch = torch.zeros(len(waves), max(lens))
+    for i, w in enumerate(waves):
+        batch[i, :len(w)] = torch.from_numpy(w)
+    tr, _ = _frontend(pkg)
+    raw, _ = _frontend(pkg, delta_order=0, apply_cmvn=False)
+    fb, n = raw.batch(batch.to(DEV), lens)
+    feat, n2 = tr.batch(batch.to(DEV), lens)
+    assert n.tolist() == [98, 42, 23, 1] == n2.tolist()
+    for row, i in enumerate((3, 2, 1, 0)):
+        m = int(n[row])
+        assert rel_err(fb[row, :m].cpu().numpy(), g["syn%d_raw" % i], floor=1.0) < 1e-4
+        assert float(fb[row, m:].abs().max() if m < fb.shape[1] else 0) == 0
+        if i > 0:
+            assert float(np.max(np.abs(feat[row, :m].cpu().numpy() - g["syn%d_feat" % i]))) < 2e-3
+            assert float(feat[row, m:].abs().max() if m < feat.shape[1] else 0) == 0   # pad_sequence zeros
+    # a single-frame utterance has an undefined unbiased std: NaN like torch.std
+    assert torch.isnan(feat[3, 0]).all()
+
+
+def test_fbank_filepath_transform_contract(pkg, tmp_path):
+    from scipy.io import wavfile
+    g = load_golden("frontend.npz")
+    p = str(tmp_path / "s.wav")
+    wavfile.write(p, 16000, g["sample_pcm"])
+    tr, dim = _frontend(pkg)
+    y = tr(p)
+    assert y.shape == (392, 120) and dim == 120 and y.device.type == "cpu"
+    assert float(np.max(np.abs(y.numpy() - g["sample_feat_d2"]))) < 1e-3
+    # properties the reference's own tests pin (tests/test_audio.py:87,103)
+    assert torch.allclose(y.mean(0), torch.zeros(120), atol=5e-5)
+    assert torch.allclose(y.std(0), torch.ones(120), atol=1e-5)
+
+
+def test_fbank_long_batch_linearity_property(pkg):
+    """Full-size property (12 s utterances): log-mel of a*x equals log-mel of x + 2*log(a) wherever the floor is
+    inactive; CMVN output is invariant to that gain."""
+    torch.manual_seed(0)
+    B, N = 8, 192000
+    x = torch.clamp(0.05 * torch.randn(B, N), -1, 1).to(DEV)
+    raw, _ = _frontend(pkg, delta_order=0, apply_cmvn=False)
+    full, _ = _frontend(pkg)
+    fb1, n = raw.batch(x, [N] * B)
+    fb2, _ = raw.batch(0.5 * x, [N] * B)
+    assert n.tolist() == [1198] * B
+    assert float((fb2 - fb1 - 2 * np.log(0.5)).abs().max()) < 1e-3
+    f1, _ = full.batch(x, [N] * B)
+    f2, _ = full.batch(0.5 * x, [N] * B)
+    assert float((f1 - f2).abs().max()) < 5e-3
+
+
+# ------------------------------------------------------------------------------------------- log-softmax / CTC
+@pytest.mark.parametrize("shape", [(7, 31), (3, 5, 1000), (2, 4, 5000)])
+def test_log_softmax_fwd_bwd(pkg, shape):
+    torch.manual_seed(1)
+    x = (3 * torch.randn(*shape)).to(DEV).requires_grad_(True)
+    y, am = pkg.ops.log_softmax(x)
+    xr = x.detach().cpu().double().requires_grad_(True)
+    yr = F.log_softmax(xr, -1)
+    assert rel_err(y.detach().cpu().numpy(), yr.detach().numpy()) < 1e-5
+    assert torch.equal(am.cpu(), yr.argmax(-1))
+    g = torch.randn(*shape)
+    y.backward(g.to(DEV))
+    yr.backward(g.double())
+    assert rel_err(x.grad.cpu().numpy(), xr.grad.numpy(), floor=1e-4) < 1e-4
+
+
+def test_ctc_golden_cases(pkg):
+    g = load_golden("ctc_cases.npz")
+    for i in range(int(g["n_cases"])):
+        lp = torch.from_numpy(g["c%d_lp" % i])[:, None, :].to(DEV).requires_grad_(True)     # [T,1,V]
+        tgt = torch.from_numpy(g["c%d_tgt" % i])[None].to(DEV)
+        tl = torch.from_numpy(g["c%d_tl" % i])
+        il = torch.from_numpy(g["c%d_il" % i])
+        crit = pkg.CTCLoss(blank=0, reduction="sum")
+        loss = crit(lp, tgt, il, tl)
+        ref = float(g["c%d_nll" % i][0])
+        if np.isinf(ref):
+            assert torch.isinf(loss).item() and loss.item() > 0        # infeasible -> +inf (zero_infinity=False)
+            continue
+        assert abs(loss.item() - ref) < 1e-4 * max(1.0, abs(ref))
+        loss.backward()
+        assert np.max(np.abs(lp.grad[:, 0].cpu().numpy() - g["c%d_grad" % i])) < 1e-5
+
+
+@pytest.mark.parametrize("B,T,V,Lmax", [(4, 50, 31, 20), (3, 37, 500, 9), (6, 149, 5000, 40), (2, 300, 31, 141)])
+def test_ctc_random_vs_aten_cpu(pkg, B, T, V, Lmax):
+    gen = torch.Generator().manual_seed(B * 1000 + T)
+    logits = torch.randn(B, T, V, generator=gen)
+    tl = torch.randint(1, Lmax, (B,), generator=gen)
+    tl[0] = Lmax - 1
+    il = torch.randint(T // 2 + Lmax, T + 1, (B,), generator=gen).clamp(max=T)
+    il[0] = T
+    txt = torch.zeros(B, Lmax, dtype=torch.long)
+    for b in range(B):
+        txt[b, :tl[b]] = torch.randint(1, V, (int(tl[b]),), generator=gen)
+        if tl[b] > 2:
+            txt[b, 1] = txt[b, 0]
+    x = logits.to(DEV).requires_grad_(True)
+    lp, _ = pkg.ops.log_softmax(x)
+    loss = pkg.CTCLoss(blank=0)(lp.transpose(0, 1), txt.to(DEV), il.to(DEV), tl.to(DEV))
+    loss.backward()
+    xr = logits.clone().requires_grad_(True)
+    lpr = F.log_softmax(xr, -1)
+    ref = F.ctc_loss(lpr.transpose(0, 1), txt, il, tl, blank=0, reduction="mean", zero_infinity=False)
+    ref.backward()
+    assert abs(loss.item() - ref.item()) < 1e-4 * abs(ref.item())
+    assert rel_err(x.grad.cpu().numpy(), xr.grad.numpy(), floor=1e-5) < 1e-3
+    # greedy path ids are bit exact
+    assert torch.equal(lp.argmax(-1).cpu(), lpr.argmax(-1))
+
+
+# ------------------------------------------------------------------------------------------- LSTM
+def _torch_lstm(I, H, bidir, seed):
+    torch.manual_seed(seed)
+    return torch.nn.LSTM(I, H, bidirectional=bidir, num_layers=1, batch_first=True)
+
+
+@pytest.mark.parametrize("B,T,I,H,bidir", [
+    (3, 7, 8, 16, True),        # UB=1 scalar scatter path, partial batch block
+    (5, 9, 12, 32, False),      # unidirectional
+    (4, 1, 8, 32, True),        # single step
+    (9, 6, 10, 48, True),       # two batch groups, tail rows
+    (8, 13, 40, 320, True),     # UB % 4 == 0 path with several unit blocks
+    (32, 11, 24, 640, True),    # cfg-D shape: UB = 10
+    (64, 10, 120, 512, True),   # cfg-B/C shape: UB = 16, Bc = 32, 128 CTAs
+])
+def test_bilstm_fwd_bwd_vs_aten_cpu(pkg, B, T, I, H, bidir):
+    ref = _torch_lstm(I, H, bidir, 3)
+    torch.manual_seed(4)
+    x = torch.randn(B, T, I)
+    xr = x.clone().requires_grad_(True)
+    yr, _ = ref(xr)
+    gy = torch.randn_like(yr)
+    yr.backward(gy)
+    ndir = 2 if bidir else 1
+    params = [p.detach().clone().to(DEV).requires_grad_(True) for p in ref.parameters()]
+    xg = x.to(DEV).requires_grad_(True)
+    y = pkg.ops.bilstm(xg, params, ndir)
+    assert y.shape == yr.shape
+    assert rel_err(y.detach().cpu().numpy(), yr.detach().numpy()) < 1e-4
+    y.backward(gy.to(DEV))
+    assert rel_err(xg.grad.cpu().numpy(), xr.grad.numpy(), floor=1e-4) < 1e-3
+    for p, q, (name, _) in zip(params, ref.parameters(), ref.named_parameters()):
+        scale = float(q.grad.abs().max())
+        assert float((p.grad.cpu() - q.grad).abs().max()) < 1e-4 * max(scale, 1e-3), name
+
+
+def test_bilstm_pad_through_semantics(pkg):
+    """The recurrence runs over padded frames: appending zero frames changes the reverse direction."""
+    ref = _torch_lstm(8, 16, True, 5)
+    torch.manual_seed(6)
+    x = torch.randn(2, 6, 8)
+    xp = torch.cat([x, torch.zeros(2, 3, 8)], 1)
+    params = [p.detach().to(DEV) for p in ref.parameters()]
+    y = pkg.ops.bilstm(xp.to(DEV), params, 2).cpu()
+    yr, _ = ref(xp)
+    assert rel_err(y.numpy(), yr.detach().numpy()) < 1e-4
+    y_short = pkg.ops.bilstm(x.to(DEV), params, 2).cpu()
+    assert float((y[:, :6, :16] - y_short[:, :, :16]).abs().max()) < 1e-6      # forward direction unchanged
+    assert float((y[:, :6, 16:] - y_short[:, :, 16:]).abs().max()) > 1e-4      # reverse direction saw the padding
+
+
+def test_bilstm_rejects_bad_hidden_size(pkg):
+    ref = _torch_lstm(8, 20, True, 1)
+    params = [p.detach().to(DEV) for p in ref.parameters()]
+    with pytest.raises(pkg.B200AsrError):
+        pkg.ops.bilstm(torch.randn(2, 3, 8, device=DEV), params, 2)
+
+
+def test_no_cpu_fallback(pkg):
+    with pytest.raises(pkg.B200AsrError):
+        pkg.ops.log_softmax(torch.randn(2, 5))
+
+
+def test_lstm_cell(pkg):
+    torch.manual_seed(0)
+    B, H = 6, 32
+    pre = torch.randn(B, 4 * H)
+    c0 = torch.randn(B, H)
+    a = pre.to(DEV).requires_grad_(True)
+    c = c0.to(DEV).requires_grad_(True)
+    h1, c1 = pkg.ops.lstm_cell(a, c)
+    hr, cr = onp.lstm_cell(pre.double().numpy(), c0.double().numpy())
+    assert rel_err(h1.detach().cpu().numpy(), hr) < 1e-5 and rel_err(c1.detach().cpu().numpy(), cr) < 1e-5
+    gh, gc = torch.randn(B, H), torch.randn(B, H)
+    (h1 * gh.to(DEV)).sum().add((c1 * gc.to(DEV)).sum()).backward()
+    ar = pre.double().requires_grad_(True)
+    c0r = c0.double().requires_grad_(True)
+    i, f, g_, o = ar[:, :H].sigmoid(), ar[:, H:2 * H].sigmoid(), ar[:, 2 * H:3 * H].tanh(), ar[:, 3 * H:].sigmoid()
+    cn = f * c0r + i * g_
+    hn = o * cn.tanh()
+    ((hn * gh.double()).sum() + (cn * gc.double()).sum()).backward()
+    assert rel_err(a.grad.cpu().numpy(), ar.grad.numpy(), floor=1e-4) < 1e-4
+    assert rel_err(c.grad.cpu().numpy(), c0r.grad.numpy(), floor=1e-4) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------- optimizer
+def test_grad_norm_and_adadelta_vs_torch(pkg):
+    from ctypes import c_void_p
+    L = pkg.lib
+    lib = L.load()
+    torch.manual_seed(2)
+    n = 100003
+    p0 = torch.randn(n)
+    g0 = torch.randn(n) * 3
+    p = p0.clone().to(DEV)
+    g = g0.clone().to(DEV)
+    sq = torch.zeros(n, device=DEV)
+    acc = torch.zeros(n, device=DEV)
+    norm = torch.zeros(1, device=DEV)
+    scratch = torch.empty(lib.b200asr_grad_norm_scratch_bytes(), dtype=torch.uint8, device=DEV)
+    pr = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adadelta([pr], lr=1.0, eps=1e-8)
+    for it in range(3):
+        L.check(lib.b200asr_grad_norm(L.ptr(g), n, L.ptr(norm), L.ptr(scratch), L.stream()))
+        L.check(lib.b200asr_adadelta_step(L.ptr(p), L.ptr(g), L.ptr(sq), L.ptr(acc), n, 1.0, 0.9, 1e-8, 0.0,
+                                          L.ptr(norm), 5.0, L.stream()))
+        pr.grad = g0.clone()
+        tn = torch.nn.utils.clip_grad_norm_([pr], 5.0)
+        opt.step()
+        assert abs(norm.item() - tn.item()) < 1e-5 * tn.item()
+        assert rel_err(p.cpu().numpy(), pr.detach().numpy(), floor=1e-3) < 1e-5
+    # NaN norm -> the update is skipped (src/solver.py:86-89)
+    before = p.clone()
+    g[5] = float("nan")
+    L.check(lib.b200asr_grad_norm(L.ptr(g), n, L.ptr(norm), L.ptr(scratch), L.stream()))
+    L.check(lib.b200asr_adadelta_step(L.ptr(p), L.ptr(g), L.ptr(sq), L.ptr(acc), n, 1.0, 0.9, 1e-8, 0.0,
+                                      L.ptr(norm), 5.0, L.stream()))
+    assert torch.isnan(norm).item() and torch.equal(p, before)
