@@ -40,3 +40,10 @@ def rel_err(a, b, floor=1e-3):
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)
     return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor))) if a.size else 0.0
+
+
+def scaled_err(a, b):
+    """max |a-b| / max |b|: error relative to the tensor's scale (for gradients with near-zero elements)."""
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return float(np.max(np.abs(a - b)) / max(float(np.max(np.abs(b))), 1e-30)) if a.size else 0.0

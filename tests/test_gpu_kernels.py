@@ -5,7 +5,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from conftest import load_golden, rel_err
+from conftest import load_golden, rel_err, scaled_err
 from oracle import oracle_np as onp
 from oracle import ref_port
 from oracle.make_golden import AUDIO_CFG
@@ -75,7 +75,8 @@ def test_fbank_filepath_transform_contract(pkg, tmp_path):
 
 def test_fbank_long_batch_linearity_property(pkg):
     """Full-size property (12 s utterances): log-mel of a*x equals log-mel of x + 2*log(a) wherever the floor is
-    inactive; CMVN output is invariant to that gain."""
+    inactive; the CMVN output is invariant to that gain except in the 4 edge frames on either side, where the deltas
+    see the reference's ZERO padding (src/audio.py:51-54), which does not shift with the gain."""
     torch.manual_seed(0)
     B, N = 8, 192000
     x = torch.clamp(0.05 * torch.randn(B, N), -1, 1).to(DEV)
@@ -87,7 +88,9 @@ def test_fbank_long_batch_linearity_property(pkg):
     assert float((fb2 - fb1 - 2 * np.log(0.5)).abs().max()) < 1e-3
     f1, _ = full.batch(x, [N] * B)
     f2, _ = full.batch(0.5 * x, [N] * B)
-    assert float((f1 - f2).abs().max()) < 5e-3
+    assert float((f1 - f2)[:, 4:-4].abs().max()) < 1e-3
+    assert float((f1 - f2)[:, :, :40].abs().max()) < 1e-3          # static channel: all frames
+    assert float((f1 - f2)[:, :4, 40:].abs().max()) > 0.1           # the edge effect is really there
 
 
 # ------------------------------------------------------------------------------------------- log-softmax / CTC
@@ -103,7 +106,7 @@ def test_log_softmax_fwd_bwd(pkg, shape):
     g = torch.randn(*shape)
     y.backward(g.to(DEV))
     yr.backward(g.double())
-    assert rel_err(x.grad.cpu().numpy(), xr.grad.numpy(), floor=1e-4) < 1e-4
+    assert scaled_err(x.grad.cpu().numpy(), xr.grad.numpy()) < 1e-5
 
 
 def test_ctc_golden_cases(pkg):
@@ -146,7 +149,7 @@ def test_ctc_random_vs_aten_cpu(pkg, B, T, V, Lmax):
     ref = F.ctc_loss(lpr.transpose(0, 1), txt, il, tl, blank=0, reduction="mean", zero_infinity=False)
     ref.backward()
     assert abs(loss.item() - ref.item()) < 1e-4 * abs(ref.item())
-    assert rel_err(x.grad.cpu().numpy(), xr.grad.numpy(), floor=1e-5) < 1e-3
+    assert scaled_err(x.grad.cpu().numpy(), xr.grad.numpy()) < 1e-4
     # greedy path ids are bit exact
     assert torch.equal(lp.argmax(-1).cpu(), lpr.argmax(-1))
 
@@ -181,7 +184,7 @@ def test_bilstm_fwd_bwd_vs_aten_cpu(pkg, B, T, I, H, bidir):
     assert y.shape == yr.shape
     assert rel_err(y.detach().cpu().numpy(), yr.detach().numpy()) < 1e-4
     y.backward(gy.to(DEV))
-    assert rel_err(xg.grad.cpu().numpy(), xr.grad.numpy(), floor=1e-4) < 1e-3
+    assert scaled_err(xg.grad.cpu().numpy(), xr.grad.numpy()) < 1e-4
     for p, q, (name, _) in zip(params, ref.parameters(), ref.named_parameters()):
         scale = float(q.grad.abs().max())
         assert float((p.grad.cpu() - q.grad).abs().max()) < 1e-4 * max(scale, 1e-3), name
@@ -223,7 +226,7 @@ def test_lstm_cell(pkg):
     c = c0.to(DEV).requires_grad_(True)
     h1, c1 = pkg.ops.lstm_cell(a, c)
     hr, cr = onp.lstm_cell(pre.double().numpy(), c0.double().numpy())
-    assert rel_err(h1.detach().cpu().numpy(), hr) < 1e-5 and rel_err(c1.detach().cpu().numpy(), cr) < 1e-5
+    assert scaled_err(h1.detach().cpu().numpy(), hr) < 1e-6 and scaled_err(c1.detach().cpu().numpy(), cr) < 1e-6
     gh, gc = torch.randn(B, H), torch.randn(B, H)
     (h1 * gh.to(DEV)).sum().add((c1 * gc.to(DEV)).sum()).backward()
     ar = pre.double().requires_grad_(True)
@@ -232,8 +235,8 @@ def test_lstm_cell(pkg):
     cn = f * c0r + i * g_
     hn = o * cn.tanh()
     ((hn * gh.double()).sum() + (cn * gc.double()).sum()).backward()
-    assert rel_err(a.grad.cpu().numpy(), ar.grad.numpy(), floor=1e-4) < 1e-4
-    assert rel_err(c.grad.cpu().numpy(), c0r.grad.numpy(), floor=1e-4) < 1e-4
+    assert scaled_err(a.grad.cpu().numpy(), ar.grad.numpy()) < 1e-6
+    assert scaled_err(c.grad.cpu().numpy(), c0r.grad.numpy()) < 1e-6
 
 
 # ------------------------------------------------------------------------------------------- optimizer
