@@ -1,0 +1,289 @@
+#!/usr/bin/env python
+"""Benchmark of the ASR train-step hot path (BASELINE.json metric: utterances/sec, ~12 s @ 16 kHz synthetic).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfgB|cfgC|cfgD] [--impl b200|reference]
+
+One "step" = one full train step over one synthetic batch: fused front end (STFT+mel+log, delta, CMVN) -> encoder ->
+CTC (+ attention decoder + CE) -> backward -> [NCCL grad all-reduce] -> grad-norm / clip / Adadelta.
+  value : whole-job utt/s with the waveforms already resident in HBM (device-timed, CUDA events, max over ranks);
+  e2e   : the same step driven from pinned HOST buffers: H2D of the waveforms + targets and D2H of the loss inside
+          the timed region, through the package's public TrainStep API;
+  roofline     : the dominant hand-written kernel (by device time inside the timed region, CUDA events on the
+                 launching stream), algorithmic bytes per SURVEY.md 8(d) over its mean launch duration, against
+                 the measured HBM peak of MEASURED_PEAKS.json;
+  cpu_baseline : the reference's CPU path (oracle/ref_port.py = the same ATen/torchaudio CPU kernels the reference
+                 calls) on a bounded sample of the same workload, on this box's host cores.
+--impl reference prints the CPU arm alone (rank 0 only under torchrun).
+"""
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+PKG = "end-to-end-asr-pytorch_b200"
+METRIC = "utterances/sec (train step, ~12s@16kHz synthetic)"
+UNIT = "utt/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfgB", choices=["cfgB", "cfgC", "cfgD"])
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's)")
+    ap.add_argument("--n-samples", type=int, default=192000)
+    ap.add_argument("--cpu-batch", type=int, default=0, help="utterances per CPU-baseline step (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_cpu_reference(cfg, vocab, seed=0):
+    """Parameter dict initialised like the reference (init_adadelta) for the CPU arm."""
+    pkg = importlib.import_module(PKG)
+    torch.manual_seed(seed)
+    audio = cfg["data"]["audio"]
+    feat_dim = audio["feat_dim"] * (audio.get("delta_order", 0) + 1)
+    model = pkg.ASR(feat_dim, vocab, True, **cfg["model"])        # parameters only; never run on the CPU
+    return {k: v.detach().clone() for k, v in model.state_dict().items()}
+
+
+def cpu_arm(cfg, vocab, n_samples, batch, steps, warmup):
+    """Time the reference's CPU path (oracle port) for `steps` steps of `batch` utterances."""
+    from oracle import ref_port
+    pkg = importlib.import_module(PKG)
+    torch.set_num_threads(os.cpu_count() or 1)
+    P = build_cpu_reference(cfg, vocab)
+    trainer = ref_port.CpuTrainer(P, cfg["model"], cfg["data"]["audio"], lr=cfg["hparas"]["lr"],
+                                  eps=cfg["hparas"]["eps"])
+    waves, lens, txt = pkg.synthetic.make_batch(vocab, batch, n_samples, seed=1000)
+    wl = [waves[b:b + 1, :int(lens[b])] for b in range(batch)]
+    tl = [[int(v) for v in txt[b] if int(v) != 0] for b in range(batch)]
+    times = []
+    loss = None
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        loss, _ = trainer.step(wl, tl)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    total = sum(times)
+    return {"value": batch * len(times) / total, "ms_per_step": 1000.0 * total / len(times), "batch": batch,
+            "cores": torch.get_num_threads(), "loss": loss}
+
+
+def main():
+    args = parse_args()
+    pkg = importlib.import_module(PKG)
+    cfg = pkg.synthetic.load_config(args.workload)
+    vocab = cfg["data"]["corpus"]["vocab_size"]
+    per_gpu = args.batch or cfg["data"]["corpus"]["batch_size"]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    config = {"workload": "%s: %s" % (args.workload, pkg.synthetic.WORKLOADS[args.workload]),
+              "global_batch": per_gpu * world, "per_gpu_batch": per_gpu, "n_samples": args.n_samples,
+              "frames": 1 + (args.n_samples - 400) // 160, "vocab": vocab,
+              "parallelism": "dp%d (utterance shards + 1 NCCL grad all-reduce)" % world,
+              "l2": "inputs+activations per step (>1 GB) exceed the 126 MB L2; no explicit flush",
+              "gemm": "cuBLAS fp32 (TF32 off) for the plain input-projection / weight-grad GEMMs"}
+
+    # ------------------------------------------------------------------------------- reference (CPU) arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        nsteps = args.steps + args.warmup
+        cb = args.cpu_batch or (8 if nsteps <= 25 else (4 if nsteps <= 60 else 2))
+        r = cpu_arm(cfg, vocab, args.n_samples, cb, args.steps, args.warmup)
+        sample = "%d-utterance steps of the same workload (reference CPU path via oracle/ref_port.py)" % cb
+        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": dict(config, cpu_batch=cb),
+                "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                                 "sample": sample},
+                "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------------------- B200 arm
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    dp = pkg.dist.DataParallel()
+    local = dp.local_rank if dp.enabled else 0
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    lib = pkg.load_library()
+    step_fn = pkg.trainer.TrainStep(cfg, vocab, device=dev, dp=dp, seed=0)
+    # identical initial weights on every rank
+    if dp.enabled:
+        torch.distributed.broadcast(step_fn.optimizer.buf.flat, 0)
+    waves, lens, txt = pkg.synthetic.make_batch(vocab, per_gpu, args.n_samples, seed=1000 + rank)
+    gb = per_gpu * world
+    ntok = None
+    if dp.enabled:
+        ntok = dp.all_reduce_scalar(float((txt != 0).sum()), dev)
+        # pad targets to the global max length so every rank decodes the same number of steps
+        t = torch.tensor([txt.shape[1]], device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        if int(t) > txt.shape[1]:
+            txt = torch.nn.functional.pad(txt, (0, int(t) - txt.shape[1]))
+    waves_pin, txt_pin = waves.pin_memory(), txt.pin_memory()
+    wave_dev = waves.to(dev)
+    txt_dev = txt.to(dev)
+    lens_dev = lens.to(dev)
+    loss_pin = torch.zeros(1).pin_memory()
+    gbatch = gb if dp.enabled else None
+
+    def step_resident():
+        return step_fn(wave_dev, lens_dev, txt_dev, global_batch=gbatch, global_tokens=ntok)
+
+    def step_e2e():
+        wave_dev.copy_(waves_pin, non_blocking=True)
+        txt_dev.copy_(txt_pin, non_blocking=True)
+        loss = step_fn(wave_dev, lens_dev, txt_dev, global_batch=gbatch, global_tokens=ntok)
+        loss_pin.copy_(loss.reshape(1), non_blocking=True)
+        return loss
+
+    def timed(fn, steps, profile=False):
+        dp.barrier()
+        torch.cuda.synchronize()
+        pkg.lib.TIMER.reset()
+        pkg.lib.TIMER.enabled = profile
+        pkg.lib.launch_count_reset()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            loss = fn()
+        b.record()
+        torch.cuda.synchronize()
+        dp.barrier()
+        pkg.lib.TIMER.enabled = False
+        ms = dp.max_time(a.elapsed_time(b), dev)
+        return ms, float(loss), pkg.lib.launch_count()
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms, loss, launches = timed(step_resident, args.steps, profile=True)
+    clocks = sampler.stop() if rank == 0 else None
+    summary = pkg.lib.TIMER.summary()
+    value = gb * args.steps / (ms / 1000.0)
+    e2e = None
+    if not args.no_e2e:
+        step_e2e()
+        ems, _, _ = timed(step_e2e, args.steps)
+        e2e = {"value": gb * args.steps / (ems / 1000.0), "unit": UNIT,
+               "h2d_bytes_per_step": int(waves_pin.numel() * 4 + txt_pin.numel() * 8) * world,
+               "d2h_bytes_per_step": 4 * world, "ms_per_step": ems / args.steps}
+
+    if rank != 0:
+        return 0
+    peak, peak_src = peaks()
+    kernels = {}
+    top, top_ms = None, -1.0
+    for name, d in summary.items():
+        per_launch_ms = d["ms"] / d["launches"]
+        gbs = (d["bytes"] / d["launches"]) / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
+        kernels[name] = {"ms_per_step": d["ms"] / args.steps, "launches_per_step": d["launches"] / args.steps,
+                         "algorithmic_gbs": gbs, "frac_hbm": gbs / peak}
+        if d["ms"] > top_ms:
+            top, top_ms = name, d["ms"]
+    own_ms = sum(d["ms"] for d in summary.values()) / args.steps
+    roofline = None
+    if top is not None:
+        k = kernels[top]
+        roofline = {"kernel": top, "bound": "hbm", "achieved": k["algorithmic_gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": k["frac_hbm"], "traffic": None, "peak_source": peak_src,
+                    "note": "binding bound for the LSTM step kernels is fp32 FMA issue + per-step cross-SM sync, "
+                            "not HBM (SURVEY.md 7); frac is the algorithmic-bytes fraction the north star asks for"}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "loss": loss, "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roofline,
+            "kernels": kernels, "own_kernel_ms_per_step": own_ms,
+            "library_ms_per_step": ms / args.steps - own_ms}
+    if world == 1 and not args.no_cpu_baseline:
+        cb = args.cpu_batch or 8
+        r = cpu_arm(cfg, vocab, args.n_samples, cb, 2, 1)
+        line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                                "sample": "1 warm-up + 2 timed steps of %d utterances of the same workload "
+                                          "(reference CPU path: kaldi.fbank per utterance + ATen LSTM/CTC + "
+                                          "clip + Adadelta, oracle/ref_port.py)" % cb,
+                                "ms_per_step": r["ms_per_step"]}
+    print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -14,6 +14,9 @@ from .lib import B200AsrError, load as load_library
 from .audio import create_transform, FbankFrontEnd
 from .asr import ASR, Encoder, Decoder, Attention
 from .ops import CTCLoss
+from . import audio, module, asr, optim, dist, synthetic, trainer, util
+from .optim import Optimizer
+from .trainer import TrainStep
 
 __all__ = ["lib", "B200AsrError", "load_library", "create_transform", "FbankFrontEnd", "ASR", "Encoder", "Decoder",
            "Attention", "CTCLoss"]

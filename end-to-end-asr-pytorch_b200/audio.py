@@ -148,18 +148,21 @@ class FbankFrontEnd(torch.nn.Module):
             t_max = self.num_frames(N)
         fb = torch.empty((B, t_max, self.num_mel), device=wave.device, dtype=torch.float32)
         nfr = torch.empty(B, device=wave.device, dtype=torch.int32)
-        L.check(lib.b200asr_fbank_fwd(L.ptr(wave), L.ptr(wl), B, N, self.win_size, self.win_shift, self.n_fft,
-                                      self.preemph, int(self.remove_dc), L.ptr(self.window), self.num_mel,
-                                      L.ptr(self.mel_start), L.ptr(self.mel_count), L.ptr(self.mel_off),
-                                      L.ptr(self.mel_w), int(self.mel_w.numel()), int(self.use_log), _FLT_EPS,
-                                      L.ptr(fb), t_max, L.ptr(nfr), L.stream()), "fbank_fwd")
+        # algorithmic bytes: read the waveform once, write the mel features once
+        with L.timed("fbank_fwd", 4 * int(wave.numel()) + 4 * B * t_max * self.num_mel):
+            L.check(lib.b200asr_fbank_fwd(
+                L.ptr(wave), L.ptr(wl), B, N, self.win_size, self.win_shift, self.n_fft, self.preemph,
+                int(self.remove_dc), L.ptr(self.window), self.num_mel, L.ptr(self.mel_start), L.ptr(self.mel_count),
+                L.ptr(self.mel_off), L.ptr(self.mel_w), int(self.mel_w.numel()), int(self.use_log), _FLT_EPS,
+                L.ptr(fb), t_max, L.ptr(nfr), L.stream()), "fbank_fwd")
         if self.delta_order == 0 and not self.apply_cmvn:
             feat = fb
         else:
             feat = torch.empty((B, t_max, self.feat_dim), device=wave.device, dtype=torch.float32)
-            L.check(lib.b200asr_delta_cmvn_fwd(L.ptr(fb), L.ptr(nfr), B, t_max, self.num_mel, self.delta_order,
-                                               self.delta_window, int(self.apply_cmvn), 1e-10, L.ptr(feat),
-                                               L.stream()), "delta_cmvn_fwd")
+            with L.timed("delta_cmvn_fwd", 4 * B * t_max * (self.num_mel + self.feat_dim)):
+                L.check(lib.b200asr_delta_cmvn_fwd(
+                    L.ptr(fb), L.ptr(nfr), B, t_max, self.num_mel, self.delta_order, self.delta_window,
+                    int(self.apply_cmvn), 1e-10, L.ptr(feat), L.stream()), "delta_cmvn_fwd")
         if return_fbank:
             return feat, nfr.to(torch.int64), fb
         return feat, nfr.to(torch.int64)

@@ -1,0 +1,77 @@
+"""Data parallelism over the 8 GPUs of one box: one process per GPU (torchrun), utterances of the GLOBALLY sorted and
+GLOBALLY padded batch sharded across ranks, ONE NCCL all-reduce(sum) of the flat fp32 gradient buffer per step.
+
+The reference has no distributed code at all; the rules that keep a DP step identical to the
+reference's single-process step are:
+  * pad to the global T_max / decode to the global max(txt_len) - the encoder runs through the padding (F5);
+  * CTC 'mean': each rank back-props sum_b nll_b / len_b / B_global; CE: sum over its tokens / N_tok_global;
+  * all-reduce = SUM, then every rank computes the identical global grad-norm, clip and update.
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+class DataParallel:
+    def __init__(self, backend=None):
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.enabled = self.world > 1
+        self.backend = backend
+        if self.enabled and not dist.is_initialized():
+            if backend is None:
+                backend = "nccl" if torch.cuda.is_available() else "gloo"
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ.setdefault("MASTER_PORT", "29500")
+            if backend == "nccl":
+                torch.cuda.set_device(self.local_rank)
+            dist.init_process_group(backend=backend, rank=self.rank, world_size=self.world)
+            self.backend = backend
+
+    def shard(self, *tensors):
+        """Rank r takes rows r::world of each [B_global, ...] tensor (lengths sorted desc => equal work)."""
+        if not self.enabled:
+            return tensors if len(tensors) > 1 else tensors[0]
+        out = tuple(t[self.rank::self.world].contiguous() for t in tensors)
+        return out if len(out) > 1 else out[0]
+
+    def all_reduce_(self, flat, n_buckets=1):
+        """In-place SUM of the flat gradient buffer (bucketed so later buckets overlap earlier ones' epilogue)."""
+        if not self.enabled:
+            return flat
+        if n_buckets <= 1:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+            return flat
+        n = flat.numel()
+        step = (n + n_buckets - 1) // n_buckets
+        works = [dist.all_reduce(flat[i:i + step], op=dist.ReduceOp.SUM, async_op=True) for i in range(0, n, step)]
+        for w in works:
+            w.wait()
+        return flat
+
+    def all_reduce_scalar(self, value, device):
+        if not self.enabled:
+            return value
+        t = torch.tensor([float(value)], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def max_time(self, ms, device):
+        """Max over ranks of a per-rank duration (multi-GPU numbers are the slowest rank's)."""
+        if not self.enabled:
+            return ms
+        t = torch.tensor([float(ms)], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def barrier(self):
+        if self.enabled:
+            dist.barrier()
+
+    def attach(self, optimizer, n_buckets=1):
+        """Make `optimizer.step()` all-reduce the flat gradient before the norm/clip/update."""
+        if self.enabled:
+            optimizer.pre_reduce = lambda flat: self.all_reduce_(flat, n_buckets)
+        return optimizer

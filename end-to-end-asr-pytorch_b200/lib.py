@@ -36,6 +36,7 @@ SIGNATURES = {
     "b200asr_bilstm_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
     "b200asr_lstm_cell_fwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, _P]),
     "b200asr_lstm_cell_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, _P]),
+    "b200asr_ce_fwd_bwd": (c_int, [_P, _P, c_longlong, c_longlong, c_int, _P, _P, _P, _P]),
     "b200asr_grad_norm_scratch_bytes": (c_size_t, []),
     "b200asr_grad_norm": (c_int, [_P, c_longlong, _P, _P, _P]),
     "b200asr_adadelta_step": (c_int, [_P, _P, _P, _P, c_longlong, c_float, c_float, c_float, c_float, _P, c_float, _P]),
@@ -98,3 +99,46 @@ def launch_count():
 
 def launch_count_reset():
     load().b200asr_launch_count_reset()
+
+
+# ---- optional per-kernel CUDA-event timing (bench.py's roofline numbers) -----------------------------------
+class KernelTimer:
+    """When enabled, every C-ABI kernel call is bracketed by CUDA events on the launching stream and tagged with
+    its algorithmic byte count; durations are read after the timed region, never inside it."""
+
+    def __init__(self):
+        self.enabled = False
+        self.records = []        # (name, start_event, end_event, algorithmic_bytes)
+
+    def reset(self):
+        self.records = []
+
+    def summary(self):
+        out = {}
+        for name, a, b, nbytes in self.records:
+            d = out.setdefault(name, {"launches": 0, "ms": 0.0, "bytes": 0})
+            d["launches"] += 1
+            d["ms"] += a.elapsed_time(b)
+            d["bytes"] += nbytes
+        return out
+
+
+TIMER = KernelTimer()
+
+
+class timed:
+    def __init__(self, name, nbytes=0):
+        self.name, self.nbytes = name, nbytes
+
+    def __enter__(self):
+        if TIMER.enabled:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if TIMER.enabled:
+            self.b.record()
+            TIMER.records.append((self.name, self.a, self.b, self.nbytes))
+        return False

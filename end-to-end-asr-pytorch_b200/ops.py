@@ -69,8 +69,10 @@ class BiLSTMFn(Function):
         if ws_bytes == 0:
             raise L.B200AsrError("bilstm: no feasible decomposition for B=%d H=%d (H must be a multiple of 16)" % (B, H))
         ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
-        L.check(lib.b200asr_bilstm_fwd(L.ptr(gates), L.ptr(w_hh), L.ptr(cst), L.ptr(out), B, T, H, ndir, L.ptr(ws),
-                                       ws_bytes, L.stream()), "bilstm_fwd")
+        # algorithmic bytes: per step and direction read Gx[t] (16BH) + write h,c (8BH); W_hh once
+        with L.timed("bilstm_fwd", ndir * (24 * B * H * T + 16 * H * H)):
+            L.check(lib.b200asr_bilstm_fwd(L.ptr(gates), L.ptr(w_hh), L.ptr(cst), L.ptr(out), B, T, H, ndir,
+                                           L.ptr(ws), ws_bytes, L.stream()), "bilstm_fwd")
         ctx.ndir = ndir
         ctx.dims = (B, T, I, H)
         ctx.consumed = False
@@ -91,8 +93,9 @@ class BiLSTMFn(Function):
         dout = _f32c(dout)
         ws_bytes = lib.b200asr_bilstm_workspace_bytes(B, T, H, ndir)
         ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
-        L.check(lib.b200asr_bilstm_bwd(L.ptr(gates), L.ptr(w_hh), L.ptr(cst), L.ptr(dout), B, T, H, ndir, L.ptr(ws),
-                                       ws_bytes, L.stream()), "bilstm_bwd")
+        with L.timed("bilstm_bwd", 2 * ndir * (24 * B * H * T + 16 * H * H)):
+            L.check(lib.b200asr_bilstm_bwd(L.ptr(gates), L.ptr(w_hh), L.ptr(cst), L.ptr(dout), B, T, H, ndir,
+                                           L.ptr(ws), ws_bytes, L.stream()), "bilstm_bwd")
         perm = gate_perm(H, dev)
         x2 = x.view(B * T, I)
         dx2 = None
@@ -135,7 +138,9 @@ class LogSoftmaxFn(Function):
         n = x.numel() // V
         y = torch.empty_like(x)
         am = torch.empty(x.shape[:-1], device=x.device, dtype=torch.int64)
-        L.check(lib.b200asr_log_softmax_fwd(L.ptr(x), L.ptr(y), None, L.ptr(am), n, V, L.stream()), "log_softmax_fwd")
+        with L.timed("log_softmax_fwd", 8 * n * V):
+            L.check(lib.b200asr_log_softmax_fwd(L.ptr(x), L.ptr(y), None, L.ptr(am), n, V, L.stream()),
+                    "log_softmax_fwd")
         ctx.save_for_backward(y)
         ctx.mark_non_differentiable(am)
         return y, am
@@ -148,7 +153,8 @@ class LogSoftmaxFn(Function):
         V = y.shape[-1]
         n = y.numel() // V
         dx = torch.empty_like(y)
-        L.check(lib.b200asr_log_softmax_bwd(L.ptr(y), L.ptr(g), L.ptr(dx), n, V, L.stream()), "log_softmax_bwd")
+        with L.timed("log_softmax_bwd", 12 * n * V):
+            L.check(lib.b200asr_log_softmax_bwd(L.ptr(y), L.ptr(g), L.ptr(dx), n, V, L.stream()), "log_softmax_bwd")
         return dx
 
 
@@ -182,9 +188,11 @@ class CTCLossFn(Function):
         grad = torch.empty_strided(log_probs.shape, log_probs.stride(), device=dev, dtype=torch.float32)
         ws_bytes = lib.b200asr_ctc_workspace_bytes(B, T, Lmax)
         ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
-        L.check(lib.b200asr_ctc_fwd_bwd(L.ptr(log_probs), log_probs.stride(1), log_probs.stride(0), L.ptr(targets),
-                                        L.ptr(il), L.ptr(tl), B, T, V, Lmax, blank, L.ptr(nll), L.ptr(w), L.ptr(grad),
-                                        L.ptr(ws), ws_bytes, L.stream()), "ctc_fwd_bwd")
+        # algorithmic bytes: read the log-probs and write the gradient once each (+ nll)
+        with L.timed("ctc_fwd_bwd", 8 * T * V * B + 4 * B):
+            L.check(lib.b200asr_ctc_fwd_bwd(L.ptr(log_probs), log_probs.stride(1), log_probs.stride(0),
+                                            L.ptr(targets), L.ptr(il), L.ptr(tl), B, T, V, Lmax, blank, L.ptr(nll),
+                                            L.ptr(w), L.ptr(grad), L.ptr(ws), ws_bytes, L.stream()), "ctc_fwd_bwd")
         ctx.save_for_backward(grad)
         ctx.mark_non_differentiable(nll)
         loss = (nll * w).sum()
@@ -261,3 +269,38 @@ class LSTMCellFn(Function):
 
 def lstm_cell(pre, c_prev):
     return LSTMCellFn.apply(pre, c_prev)
+
+
+# ----------------------------------------------------------------------------------------------------------
+class CrossEntropyFn(Function):
+    """CrossEntropyLoss(ignore_index) with the logit gradient produced by the same launch."""
+
+    @staticmethod
+    def forward(ctx, logits, target, ignore_index, reduction):
+        lib = L.load()
+        x = _f32c(logits)
+        N, V = x.shape
+        target = target.to(device=x.device, dtype=torch.int64).contiguous()
+        if reduction == "mean":
+            scale = 1.0 / (target != ignore_index).sum().to(torch.float32)
+        elif reduction == "sum":
+            scale = torch.ones((), device=x.device, dtype=torch.float32)
+        else:
+            raise NotImplementedError("reduction=%s" % reduction)
+        scale = scale.reshape(1).contiguous()
+        row = torch.empty(N, device=x.device, dtype=torch.float32)
+        grad = torch.empty_like(x)
+        with L.timed("ce_fwd_bwd", 8 * N * V):
+            L.check(lib.b200asr_ce_fwd_bwd(L.ptr(x), L.ptr(target), ignore_index, N, V, L.ptr(scale), L.ptr(row),
+                                           L.ptr(grad), L.stream()), "ce_fwd_bwd")
+        ctx.save_for_backward(grad)
+        return row.sum() * scale[0]
+
+    @staticmethod
+    def backward(ctx, gloss):
+        (grad,) = ctx.saved_tensors
+        return grad.mul_(gloss), None, None, None
+
+
+def cross_entropy(logits, target, ignore_index=0, reduction="mean"):
+    return CrossEntropyFn.apply(logits, target, ignore_index, reduction)

@@ -1,0 +1,61 @@
+"""The train step (the hot path) as one object: waveforms -> fused front end -> ASR.forward -> CTC (+CE) ->
+backward -> [grad all-reduce] -> fused norm/clip/update.  Used by the Solver mirror (train_asr.py) and bench.py.
+Mirrors bin/train_asr.py:95-137 + src/solver.py:76-91 of the reference."""
+import torch
+import torch.nn.functional as F
+
+from . import ops
+from .asr import ASR
+from .audio import create_transform
+from .dist import DataParallel
+from .optim import Optimizer
+
+
+class TrainStep:
+    def __init__(self, config, vocab_size, device="cuda", dp=None, seed=0):
+        self.device = torch.device(device)
+        self.dp = dp or DataParallel()
+        self.config = config
+        torch.manual_seed(seed)
+        self.transform, self.feat_dim = create_transform(dict(config["data"]["audio"]), device=self.device)
+        init_adadelta = config["hparas"]["optimizer"] == "Adadelta"
+        self.model = ASR(self.feat_dim, vocab_size, init_adadelta, **config["model"]).to(self.device)
+        self.model.train()
+        self.ctc_loss = ops.CTCLoss(blank=0, zero_infinity=False)
+        self.optimizer = Optimizer([{"params": self.model.parameters()}], **config["hparas"])
+        self.dp.attach(self.optimizer)
+        self.step_id = 0
+        self.last = {}
+
+    def front_end(self, wave, wave_len):
+        return self.transform.batch(wave, wave_len)
+
+    def __call__(self, wave, wave_len, txt, global_batch=None, global_tokens=None):
+        """wave [B,N] fp32 (device), wave_len [B], txt [B,L] int64 (device); returns the total loss (device scalar).
+        Under data parallelism `wave`/`txt` are this rank's shard, padded to the GLOBAL maxima."""
+        model = self.model
+        tf_rate = self.optimizer.pre_step(self.step_id)
+        feat, feat_len = self.front_end(wave, wave_len)
+        txt_len = torch.sum(txt != 0, dim=-1)
+        max_len = txt.shape[1] if global_batch is not None else int(txt_len.max())
+        ctc_output, encode_len, att_output, att_align, _ = model(feat, feat_len, max_len, tf_rate=tf_rate, teacher=txt)
+        total = 0
+        ctc = att = None
+        if ctc_output is not None:
+            self.ctc_loss.global_batch = global_batch
+            ctc = self.ctc_loss(ctc_output.transpose(0, 1), txt, encode_len, txt_len)
+            total = total + ctc * model.ctc_weight
+        if att_output is not None:
+            b, t, _ = att_output.shape
+            tgt = txt[:, :t].reshape(-1)
+            if global_tokens is None:
+                att = ops.cross_entropy(att_output.reshape(b * t, -1), tgt, ignore_index=0)
+            else:
+                att = ops.cross_entropy(att_output.reshape(b * t, -1), tgt, ignore_index=0, reduction="sum") / global_tokens
+            total = total + att * (1 - model.ctc_weight)
+        total.backward()
+        grad_norm = self.optimizer.step()
+        self.step_id += 1
+        self.last = {"ctc": ctc, "att": att, "total": total.detach(), "grad_norm": grad_norm,
+                     "ctc_output": ctc_output, "att_output": att_output, "encode_len": encode_len}
+        return total.detach()

@@ -106,6 +106,14 @@ B200ASR_API int b200asr_lstm_cell_bwd(const float* gates, const float* c_prev, c
                           const float* dc_next /* may be NULL */, float* dpreact, float* dc_prev, int B, int H,
                           b200asr_stream stream);
 
+/* ---- K15: cross-entropy (log-softmax + NLL, ignore_index) forward + logit gradient ----------------------
+ * replaces torch.nn.CrossEntropyLoss(ignore_index=0) at bin/train_asr.py:47,127-131.  row_loss [n_rows] =
+ * lse(x) - x[target] (0 for ignored rows); dlogits (optional) = grad_scale[0] * (softmax(x) - onehot), zero rows
+ * for ignored targets; grad_scale is a DEVICE scalar (e.g. 1 / number of non-ignored rows) or NULL (= 1).     */
+B200ASR_API int b200asr_ce_fwd_bwd(const float* logits, const long long* target, long long ignore_index,
+                                   long long n_rows, int V, const float* grad_scale, float* row_loss,
+                                   float* dlogits, b200asr_stream stream);
+
 /* ---- K16: gradient norm, clip and optimizer update on flat buffers (src/solver.py:84-89, src/optim.py) ----
  * grad_norm (device scalar) may be NULL (no clipping, no NaN skip); max_norm <= 0 disables clipping.          */
 B200ASR_API size_t b200asr_grad_norm_scratch_bytes(void);
