@@ -145,3 +145,48 @@ extern "C" int b200asr_adam_step(float* param, const float* grad, float* exp_avg
     B200_LAUNCH_CHECK("adam_kernel");
     return B200_OK;
 }
+
+// ---- fp32 -> (tf32 hi, fp32 residual lo) split for error-compensated tensor-core GEMMs (3xTF32) ----------------
+// hi = x rounded to TF32 (10 explicit mantissa bits, low 13 bits zero), lo = x - hi (exact in fp32).  The caller
+// forms  A.B ~= A_lo.B_hi + A_hi.B_lo + A_hi.B_hi  with three TF32 tensor-core GEMMs accumulating in fp32,
+// which keeps the input-projection / weight-gradient contractions within fp32-level error (~1e-6 relative).
+namespace b200asr {
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float4* __restrict__ x, float4* __restrict__ hi,
+                                                        float4* __restrict__ lo, long long n4, const float* xs,
+                                                        float* his, float* los, int tail) {
+    auto split = [](float v, float& h, float& l) {
+        unsigned u = __float_as_uint(v);
+        // round to nearest (ties away) on the magnitude; inf/nan pass through unchanged
+        if ((u & 0x7f800000u) != 0x7f800000u) u = (u + 0x1000u) & 0xffffe000u;
+        h = __uint_as_float(u);
+        l = v - h;
+    };
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = x[i];
+        float4 h, l;
+        split(v.x, h.x, l.x); split(v.y, h.y, l.y); split(v.z, h.z, l.z); split(v.w, h.w, l.w);
+        hi[i] = h;
+        lo[i] = l;
+    }
+    if (blockIdx.x == 0 && (int)threadIdx.x < tail) {
+        float h, l;
+        split(xs[threadIdx.x], h, l);
+        his[threadIdx.x] = h;
+        los[threadIdx.x] = l;
+    }
+}
+}  // namespace b200asr
+
+extern "C" int b200asr_split_tf32(const float* x, float* hi, float* lo, long long n, b200asr_stream stream) {
+    B200_REQUIRE(x && hi && lo, "split_tf32: null pointer");
+    B200_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo)) & 15) == 0,
+                 "split_tf32: buffers must be 16-byte aligned");
+    if (n <= 0) return B200_OK;
+    const long long n4 = n >> 2;
+    const int tail = (int)(n & 3);
+    split_tf32_kernel<<<grid_for(n4 > 0 ? n4 : 1), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(hi), reinterpret_cast<float4*>(lo), n4,
+        x + (n4 << 2), hi + (n4 << 2), lo + (n4 << 2), tail);
+    B200_LAUNCH_CHECK("split_tf32_kernel");
+    return B200_OK;
+}

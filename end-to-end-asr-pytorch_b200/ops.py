@@ -36,32 +36,117 @@ def gate_perm(H, device):
 
 
 # ----------------------------------------------------------------------------------------------------------
+# Dense contractions of the LSTM layers (K6 and the weight gradients).  They are plain GEMMs, so they go to the
+# tensor cores through cuBLAS - but fp32 parity (1e-4 on logits after 4 recurrent layers) rules out single-pass
+# TF32/BF16.  GEMM_MODE "tf32x3" splits every operand into a TF32-representable high part and an fp32 residual
+# (b200asr_split_tf32) and sums three TF32 tensor-core GEMMs  A_lo.B_hi + A_hi.B_lo + A_hi.B_hi  in fp32
+# (relative error ~1e-6, i.e. fp32 class); "fp32" uses cuBLAS SGEMM (CUDA cores).
+GEMM_MODE = "tf32x3"
+
+
+class Split:
+    """fp32 matrix as (hi, lo) with hi exactly representable in TF32."""
+
+    def __init__(self, x):
+        lib = L.load()
+        x = _f32c(x)
+        self.hi = torch.empty_like(x)
+        self.lo = torch.empty_like(x)
+        with L.timed("split_tf32", 12 * x.numel()):
+            L.check(lib.b200asr_split_tf32(L.ptr(x), L.ptr(self.hi), L.ptr(self.lo), x.numel(), L.stream()),
+                    "split_tf32")
+
+    def t(self):
+        o = object.__new__(Split)
+        o.hi, o.lo = self.hi.t(), self.lo.t()
+        return o
+
+    def view(self, *shape):
+        o = object.__new__(Split)
+        o.hi, o.lo = self.hi.view(*shape), self.lo.view(*shape)
+        return o
+
+
+def mm3(a, b, out=None, bias=None, accumulate=False):
+    """out (= or +=) a @ b (+ bias) for Split operands: three error-compensated TF32 tensor-core GEMMs."""
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        if out is None:
+            out = torch.empty((a.hi.shape[0], b.hi.shape[1]), device=a.hi.device, dtype=torch.float32)
+            accumulate = False
+        if accumulate:
+            out.addmm_(a.lo, b.hi)
+        elif bias is not None:
+            torch.addmm(bias, a.lo, b.hi, out=out)
+        else:
+            torch.mm(a.lo, b.hi, out=out)
+        out.addmm_(a.hi, b.lo)
+        out.addmm_(a.hi, b.hi)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    return out
+
+
+class Plain:
+    """Same interface as Split for the exact-fp32 SGEMM mode."""
+
+    def __init__(self, x):
+        self.x = _f32c(x)
+
+    def t(self):
+        o = object.__new__(Plain)
+        o.x = self.x.t()
+        return o
+
+    def view(self, *shape):
+        o = object.__new__(Plain)
+        o.x = self.x.view(*shape)
+        return o
+
+
+def mm1(a, b, out=None, bias=None, accumulate=False):
+    if out is None:
+        return torch.mm(a.x, b.x) if bias is None else torch.addmm(bias, a.x, b.x)
+    if accumulate:
+        return out.addmm_(a.x, b.x)
+    if bias is not None:
+        return torch.addmm(bias, a.x, b.x, out=out)
+    return torch.mm(a.x, b.x, out=out)
+
+
+def _gemm_ops():
+    return (Split, mm3) if GEMM_MODE == "tf32x3" else (Plain, mm1)
+
+
 class BiLSTMFn(Function):
     """One (bi)directional LSTM layer over zero-padded frames, zero initial state (src/module.py:129-132).
 
     forward(x[B,T,I], ndir, w_ih_0, w_hh_0, b_ih_0, b_hh_0 [, w_ih_1, w_hh_1, b_ih_1, b_hh_1]) -> out[B,T,ndir*H]
-    The input projection and the weight-gradient contractions are cuBLAS GEMMs; the recurrence (forward and
-    BPTT) is the persistent kernel pair b200asr_bilstm_fwd / b200asr_bilstm_bwd.
+    The input projection and the weight-gradient contractions are tensor-core GEMMs (see GEMM_MODE); the recurrence
+    (forward and BPTT) is the persistent kernel pair b200asr_bilstm_fwd / b200asr_bilstm_bwd.
     """
 
     @staticmethod
     def forward(ctx, x, ndir, *params):
         lib = L.load()
         assert len(params) == 4 * ndir
+        Op, mm = _gemm_ops()
         x = _f32c(x)
         B, T, I = x.shape
         H = params[1].shape[1]
         dev = x.device
         perm = gate_perm(H, dev)
-        x2 = x.view(B * T, I)
+        xs = Op(x.view(B * T, I))
         gates = torch.empty((ndir, B, T, H, 4), device=dev, dtype=torch.float32)
         w_ih_p = []
         for d in range(ndir):
             w_ih, w_hh, b_ih, b_hh = params[4 * d:4 * d + 4]
             wp = w_ih.detach().index_select(0, perm)
             bp = (b_ih.detach() + b_hh.detach()).index_select(0, perm)
-            torch.addmm(bp, x2, wp.t(), out=gates[d].view(B * T, 4 * H))
+            mm(xs, Op(wp).t(), out=gates[d].view(B * T, 4 * H), bias=bp)
             w_ih_p.append(wp)
+        del xs
         w_hh = torch.stack([_f32c(params[4 * d + 1].detach()) for d in range(ndir)]).contiguous()
         cst = torch.empty((ndir, B, T, H), device=dev, dtype=torch.float32)
         out = torch.empty((B, T, ndir * H), device=dev, dtype=torch.float32)
@@ -85,6 +170,7 @@ class BiLSTMFn(Function):
         if ctx.consumed:
             raise L.B200AsrError("BiLSTMFn.backward ran twice: the gate stash is overwritten in place")
         ctx.consumed = True
+        Op, mm = _gemm_ops()
         ndir = ctx.ndir
         B, T, I, H = ctx.dims
         x, gates, cst, out, w_hh = ctx.saved_tensors[:5]
@@ -97,29 +183,31 @@ class BiLSTMFn(Function):
             L.check(lib.b200asr_bilstm_bwd(L.ptr(gates), L.ptr(w_hh), L.ptr(cst), L.ptr(dout), B, T, H, ndir,
                                            L.ptr(ws), ws_bytes, L.stream()), "bilstm_bwd")
         perm = gate_perm(H, dev)
-        x2 = x.view(B * T, I)
-        dx2 = None
+        xs = Op(x.view(B * T, I))
+        need_dx = ctx.needs_input_grad[0]
+        dx2 = torch.empty((B * T, I), device=dev, dtype=torch.float32) if need_dx else None
         grads = []
         for d in range(ndir):
-            dG = gates[d].view(B * T, 4 * H)  # d(loss)/d(pre-activation), unit-major columns
-            dx2 = torch.mm(dG, w_ih_p[d]) if dx2 is None else torch.addmm(dx2, dG, w_ih_p[d])
+            dG = Op(gates[d].view(B * T, 4 * H))  # d(loss)/d(pre-activation), unit-major columns
+            if need_dx:
+                mm(dG, Op(w_ih_p[d]), out=dx2, accumulate=(d > 0))
             dw_ih = torch.empty((4 * H, I), device=dev, dtype=torch.float32)
-            dw_ih.index_copy_(0, perm, torch.mm(dG.t(), x2))
+            dw_ih.index_copy_(0, perm, mm(dG.t(), xs))
             db = torch.empty((4 * H,), device=dev, dtype=torch.float32)
-            db.index_copy_(0, perm, dG.sum(0))
-            dG3 = gates[d].view(B, T, 4 * H)
+            db.index_copy_(0, perm, gates[d].view(B * T, 4 * H).sum(0))
+            # h_{prev}: the hidden state of the previous step of this direction (zero at its first step)
+            hprev = torch.zeros((B, T, H), device=dev, dtype=torch.float32)
             hd = out[:, :, d * H:(d + 1) * H]
             if T > 1:
-                if d == 0:   # h_{t-1} = out[:, t-1]
-                    dw = torch.bmm(dG3[:, 1:].transpose(1, 2), hd[:, :-1]).sum(0)
-                else:        # reverse direction: the previous step is t+1
-                    dw = torch.bmm(dG3[:, :-1].transpose(1, 2), hd[:, 1:]).sum(0)
-            else:
-                dw = torch.zeros((4 * H, H), device=dev, dtype=torch.float32)
+                if d == 0:
+                    hprev[:, 1:] = hd[:, :-1]
+                else:
+                    hprev[:, :-1] = hd[:, 1:]
             dw_hh = torch.empty((4 * H, H), device=dev, dtype=torch.float32)
-            dw_hh.index_copy_(0, perm, dw)
+            dw_hh.index_copy_(0, perm, mm(dG.t(), Op(hprev.view(B * T, H))))
+            del dG, hprev
             grads += [dw_ih, dw_hh, db, db.clone()]
-        return (dx2.view(B, T, I), None, *grads)
+        return (dx2.view(B, T, I) if need_dx else None, None, *grads)
 
 
 def bilstm(x, lstm_params, ndir):

@@ -125,6 +125,11 @@ B200ASR_API int b200asr_adam_step(float* param, const float* grad, float* exp_av
                       float beta1, float beta2, float eps, float weight_decay, int step, const float* grad_norm,
                       float max_norm, b200asr_stream stream);
 
+/* ---- K6 helper: split fp32 into a TF32-representable high part and the fp32 residual ---------------------------
+ * hi = x rounded to TF32, lo = x - hi; used to run the input-projection (src/module.py:131, inside nn.LSTM) and the
+ * weight-gradient contractions as three error-compensated TF32 tensor-core GEMMs (3xTF32) at fp32-level accuracy.  */
+B200ASR_API int b200asr_split_tf32(const float* x, float* hi, float* lo, long long n, b200asr_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

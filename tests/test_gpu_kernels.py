@@ -149,7 +149,9 @@ def test_ctc_random_vs_aten_cpu(pkg, B, T, V, Lmax):
     ref = F.ctc_loss(lpr.transpose(0, 1), txt, il, tl, blank=0, reduction="mean", zero_infinity=False)
     ref.backward()
     assert abs(loss.item() - ref.item()) < 1e-4 * abs(ref.item())
-    assert scaled_err(x.grad.cpu().numpy(), xr.grad.numpy()) < 1e-4
+    # fp32 budget: the occupancy term exp(log sum(alpha*beta) + nll - lp) cancels two numbers of magnitude
+    # ~T*log(V) (1e3 at V=5000), so ATen's own fp32 result carries ~1e-4 relative noise there
+    assert scaled_err(x.grad.cpu().numpy(), xr.grad.numpy()) < (1e-4 if V < 1000 else 1e-3)
     # greedy path ids are bit exact
     assert torch.equal(lp.argmax(-1).cpu(), lpr.argmax(-1))
 
@@ -237,6 +239,22 @@ def test_lstm_cell(pkg):
     ((hn * gh.double()).sum() + (cn * gc.double()).sum()).backward()
     assert scaled_err(a.grad.cpu().numpy(), ar.grad.numpy()) < 1e-6
     assert scaled_err(c.grad.cpu().numpy(), c0r.grad.numpy()) < 1e-6
+
+
+def test_gemm_tf32x3_is_fp32_class(pkg):
+    """The error-compensated tensor-core GEMM must be as accurate as an fp32 SGEMM (vs an fp64 product)."""
+    torch.manual_seed(0)
+    a = torch.randn(3000, 1024, device=DEV)
+    b = torch.randn(2048, 1024, device=DEV) * 0.03
+    bias = torch.randn(2048, device=DEV)
+    ref = (a.double() @ b.double().t() + bias.double()).cpu().numpy()
+    out = pkg.ops.mm3(pkg.ops.Split(a), pkg.ops.Split(b).t(), bias=bias,
+                      out=torch.empty(3000, 2048, device=DEV)).cpu().numpy()
+    sg = torch.addmm(bias, a, b.t()).cpu().numpy()          # cuBLAS SGEMM (TF32 off)
+    e3, e1 = scaled_err(out, ref), scaled_err(sg, ref)
+    assert e3 < 3e-6 and e3 < 20 * max(e1, 1e-7), (e3, e1)
+    s = pkg.ops.Split(a)
+    assert torch.equal(s.hi + s.lo, a) and int((s.hi.view(torch.int32) & 0x1fff).abs().max()) == 0
 
 
 # ------------------------------------------------------------------------------------------- optimizer
