@@ -75,8 +75,9 @@ def test_fbank_filepath_transform_contract(pkg, tmp_path):
 
 def test_fbank_long_batch_linearity_property(pkg):
     """Full-size property (12 s utterances): log-mel of a*x equals log-mel of x + 2*log(a) wherever the floor is
-    inactive; the CMVN output is invariant to that gain except in the 4 edge frames on either side, where the deltas
-    see the reference's ZERO padding (src/audio.py:51-54), which does not shift with the gain."""
+    inactive, so the CMVN-normalised STATIC channel is invariant to the gain.  (The delta channels are not: their
+    edge frames see the reference's ZERO padding, src/audio.py:51-54, which does not shift with the gain, and that
+    moves the per-utterance mean/std of the whole channel.)"""
     torch.manual_seed(0)
     B, N = 8, 192000
     x = torch.clamp(0.05 * torch.randn(B, N), -1, 1).to(DEV)
@@ -85,12 +86,12 @@ def test_fbank_long_batch_linearity_property(pkg):
     fb1, n = raw.batch(x, [N] * B)
     fb2, _ = raw.batch(0.5 * x, [N] * B)
     assert n.tolist() == [1198] * B
-    assert float((fb2 - fb1 - 2 * np.log(0.5)).abs().max()) < 1e-3
+    assert float((fb2 - fb1 - 2 * np.log(0.5)).abs().max()) < 1e-4
     f1, _ = full.batch(x, [N] * B)
     f2, _ = full.batch(0.5 * x, [N] * B)
-    assert float((f1 - f2)[:, 4:-4].abs().max()) < 1e-3
-    assert float((f1 - f2)[:, :, :40].abs().max()) < 1e-3          # static channel: all frames
-    assert float((f1 - f2)[:, :4, 40:].abs().max()) > 0.1           # the edge effect is really there
+    assert float((f1 - f2)[:, :, :40].abs().max()) < 1e-3
+    assert float(f1[:, :, :40].mean(1).abs().max()) < 1e-4           # CMVN: zero mean over time
+    assert float((f1[:, :, :].std(1) - 1).abs().max()) < 1e-4         # unit (unbiased) std, all 120 columns
 
 
 # ------------------------------------------------------------------------------------------- log-softmax / CTC
@@ -184,7 +185,7 @@ def test_bilstm_fwd_bwd_vs_aten_cpu(pkg, B, T, I, H, bidir):
     xg = x.to(DEV).requires_grad_(True)
     y = pkg.ops.bilstm(xg, params, ndir)
     assert y.shape == yr.shape
-    assert rel_err(y.detach().cpu().numpy(), yr.detach().numpy()) < 1e-4
+    assert scaled_err(y.detach().cpu().numpy(), yr.detach().numpy()) < 2e-5
     y.backward(gy.to(DEV))
     assert scaled_err(xg.grad.cpu().numpy(), xr.grad.numpy()) < 1e-4
     for p, q, (name, _) in zip(params, ref.parameters(), ref.named_parameters()):
