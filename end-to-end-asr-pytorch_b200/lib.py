@@ -36,6 +36,12 @@ SIGNATURES = {
     "b200asr_bilstm_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
     "b200asr_lstm_cell_fwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, _P]),
     "b200asr_lstm_cell_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, _P]),
+    "b200asr_locattn_cluster_size": (c_int, [c_int, c_int]),
+    "b200asr_locattn_wpart_floats": (c_size_t, [c_int, c_int, c_int]),
+    "b200asr_locattn_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_float, c_int, c_int, c_int, c_int, c_int,
+                                    c_int, _P, _P, _P]),
+    "b200asr_locattn_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_float, _P, _P, _P, c_int, c_int, c_int, c_int,
+                                    c_int, c_int, _P, _P, _P, _P, _P, _P]),
     "b200asr_ce_fwd_bwd": (c_int, [_P, _P, c_longlong, c_longlong, c_int, _P, _P, _P, _P]),
     "b200asr_split_tf32": (c_int, [_P, _P, _P, c_longlong, _P]),
     "b200asr_grad_norm_scratch_bytes": (c_size_t, []),

@@ -392,3 +392,68 @@ class CrossEntropyFn(Function):
 
 def cross_entropy(logits, target, ignore_index=0, reduction="mean"):
     return CrossEntropyFn.apply(logits, target, ignore_index, reduction)
+
+
+# ----------------------------------------------------------------------------------------------------------
+class LocAttnStepFn(Function):
+    """One location-aware attention step (src/module.py:234-258 + 189-195, single head) in one kernel launch;
+    its backward is one launch too (+ a [B*CS, P] -> [P] reduction of the small weight-gradient partials)."""
+
+    @staticmethod
+    def forward(ctx, q, key, value, prev_att, enc_len, conv_w, proj_w, e_w, e_b, temperature):
+        lib = L.load()
+        q, key, value, prev_att = _f32c(q), _f32c(key), _f32c(value), _f32c(prev_att)
+        B, T, D = key.shape
+        E = value.shape[2]
+        K, _, W = conv_w.shape
+        R = (W - 1) // 2
+        dev = key.device
+        enc_len = enc_len.to(device=dev, dtype=torch.int64).contiguous()
+        cw, pw = _f32c(conv_w.detach()), _f32c(proj_w.detach())
+        ew, eb = _f32c(e_w.detach()).view(-1), _f32c(e_b.detach()).view(-1)
+        attn = torch.empty((B, T), device=dev, dtype=torch.float32)
+        cvec = torch.empty((B, E), device=dev, dtype=torch.float32)
+        # algorithmic bytes (SURVEY.md 8(d)): key + value read once per step
+        with L.timed("locattn_fwd", 4 * B * T * (D + E)):
+            L.check(lib.b200asr_locattn_fwd(L.ptr(q), L.ptr(key), L.ptr(value), L.ptr(prev_att), L.ptr(enc_len),
+                                            L.ptr(cw), L.ptr(pw), L.ptr(ew), L.ptr(eb), float(temperature), B, T, D, E,
+                                            K, R, L.ptr(attn), L.ptr(cvec), L.stream()), "locattn_fwd")
+        ctx.save_for_backward(q, key, value, prev_att, enc_len, cw, pw, ew, attn)
+        ctx.dims = (B, T, D, E, K, R)
+        ctx.temperature = float(temperature)
+        ctx.w_shapes = (conv_w.shape, proj_w.shape, e_w.shape, e_b.shape)
+        return cvec, attn
+
+    @staticmethod
+    def backward(ctx, dctx, dattn):
+        lib = L.load()
+        q, key, value, prev_att, enc_len, cw, pw, ew, attn = ctx.saved_tensors
+        B, T, D, E, K, R = ctx.dims
+        dev = key.device
+        CS = lib.b200asr_locattn_cluster_size(T, E)
+        P = lib.b200asr_locattn_wpart_floats(D, K, R)
+        dctx = _f32c(dctx) if dctx is not None else torch.zeros((B, E), device=dev)
+        dattn = _f32c(dattn) if dattn is not None else None
+        dq_part = torch.empty((B, CS, D), device=dev, dtype=torch.float32)
+        dkey = torch.empty((B, T, D), device=dev, dtype=torch.float32)
+        dvalue = torch.empty((B, T, E), device=dev, dtype=torch.float32)
+        dprev = torch.empty((B, T), device=dev, dtype=torch.float32)
+        wpart = torch.empty((B * CS, P), device=dev, dtype=torch.float32)
+        with L.timed("locattn_bwd", 4 * B * T * (2 * D + 2 * E)):
+            L.check(lib.b200asr_locattn_bwd(L.ptr(q), L.ptr(key), L.ptr(value), L.ptr(prev_att), L.ptr(enc_len),
+                                            L.ptr(cw), L.ptr(pw), L.ptr(ew), ctx.temperature, L.ptr(attn), L.ptr(dctx),
+                                            L.ptr(dattn), B, T, D, E, K, R, L.ptr(dq_part), L.ptr(dkey), L.ptr(dvalue),
+                                            L.ptr(dprev), L.ptr(wpart), L.stream()), "locattn_bwd")
+        wsum = wpart.sum(0)
+        W = 2 * R + 1
+        s_conv, s_proj, s_ew, s_eb = ctx.w_shapes
+        d_proj = wsum[:D * K].view(s_proj)
+        d_conv = wsum[D * K:D * K + K * W].view(s_conv)
+        d_ew = wsum[D * K + K * W:D * K + K * W + D].view(s_ew)
+        d_eb = wsum[D * K + K * W + D:].view(s_eb)
+        return dq_part.sum(1), dkey, dvalue, dprev, None, d_conv, d_proj, d_ew, d_eb, None
+
+
+def loc_attention_step(q, key, value, prev_att, enc_len, conv_w, proj_w, e_w, e_b, temperature):
+    """-> (context [B,E], attn [B,T])"""
+    return LocAttnStepFn.apply(q, key, value, prev_att, enc_len, conv_w, proj_w, e_w, e_b, temperature)

@@ -106,6 +106,28 @@ B200ASR_API int b200asr_lstm_cell_bwd(const float* gates, const float* c_prev, c
                           const float* dc_next /* may be NULL */, float* dpreact, float* dc_prev, int B, int H,
                           b200asr_stream stream);
 
+/* ---- K12: location-aware attention step, forward and backward, one launch each ----------------------------------
+ * replaces src/module.py:234-258 (LocationAwareAttention.forward) + :189-195 (_attend), single head:
+ * Conv1d(1->K, 2R+1, pad R, no bias) over prev_att -> Linear(K->D, no bias) -> tanh -> energy = Linear(D->1)(tanh(key +
+ * q + loc)) / temperature -> masked softmax over t < enc_len[b] -> context = attn . value.
+ *   q [B,D] (already tanh(proj_q(h))), key [B,T,D] (tanh(proj_k(enc))), value [B,T,E], prev_att [B,T], enc_len [B] i64,
+ *   w_conv [K,2R+1], w_proj [D,K], w_energy [D], b_energy [1]  ->  attn [B,T], ctx [B,E].
+ * backward: dctx [B,E], dattn [B,T] or NULL -> dq_part [B,CS,D] (sum over CS = dq), dkey [B,T,D], dvalue [B,T,E],
+ * dprev [B,T], wpart [B*CS, P] with P = D*K + K*(2R+1) + D + 1 laid out (d w_proj | d w_conv | d w_energy | d b_energy);
+ * the caller sums wpart over its first axis.  CS = b200asr_locattn_cluster_size(T, E) CTAs cooperate per utterance
+ * through distributed shared memory.  K <= 16, E % 4 == 0, D <= 1024.                                              */
+B200ASR_API int b200asr_locattn_cluster_size(int T, int E);
+B200ASR_API size_t b200asr_locattn_wpart_floats(int D, int K, int R);
+B200ASR_API int b200asr_locattn_fwd(const float* q, const float* key, const float* value, const float* prev_att,
+                                    const long long* enc_len, const float* w_conv, const float* w_proj,
+                                    const float* w_energy, const float* b_energy, float temperature, int B, int T,
+                                    int D, int E, int K, int R, float* attn, float* ctx, b200asr_stream stream);
+B200ASR_API int b200asr_locattn_bwd(const float* q, const float* key, const float* value, const float* prev_att,
+                                    const long long* enc_len, const float* w_conv, const float* w_proj,
+                                    const float* w_energy, float temperature, const float* attn, const float* dctx,
+                                    const float* dattn, int B, int T, int D, int E, int K, int R, float* dq_part,
+                                    float* dkey, float* dvalue, float* dprev, float* wpart, b200asr_stream stream);
+
 /* ---- K15: cross-entropy (log-softmax + NLL, ignore_index) forward + logit gradient ----------------------
  * replaces torch.nn.CrossEntropyLoss(ignore_index=0) at bin/train_asr.py:47,127-131.  row_loss [n_rows] =
  * lse(x) - x[target] (0 for ignored rows); dlogits (optional) = grad_scale[0] * (softmax(x) - onehot), zero rows

@@ -242,6 +242,47 @@ def test_lstm_cell(pkg):
     assert scaled_err(c.grad.cpu().numpy(), c0r.grad.numpy()) < 1e-6
 
 
+def _loc_attention_torch(q, key, value, prev, lens, cw, pw, ew, eb, temp):
+    T = key.shape[1]
+    R = (cw.shape[2] - 1) // 2
+    conv = F.conv1d(prev.unsqueeze(1), cw, padding=R)
+    loc = torch.tanh(F.linear(conv.transpose(1, 2), pw))
+    e = F.linear(torch.tanh(key + q.unsqueeze(1) + loc), ew, eb).squeeze(2) / temp
+    mask = torch.arange(T)[None, :] >= lens[:, None]
+    a = torch.softmax(e.masked_fill(mask, float("-inf")), -1)
+    return torch.bmm(a.unsqueeze(1), value).squeeze(1), a
+
+
+@pytest.mark.parametrize("B,T,D,E,K,R,lens", [
+    (3, 12, 16, 64, 4, 5, [12, 9, 5]),                 # single-CTA path (cluster size 1)
+    (4, 40, 300, 256, 10, 100, [40, 33, 17, 8]),       # cluster of 4, reference-sized location conv
+    (2, 149, 300, 2048, 10, 100, [149, 120]),          # cfg-C shape
+    (2, 70, 48, 72, 3, 2, [70, 1]),                    # cluster of 2, a single valid frame
+])
+def test_loc_attention_step_fwd_bwd(pkg, B, T, D, E, K, R, lens):
+    g = torch.Generator().manual_seed(B * 100 + T)
+    mk = lambda *s, sc=1.0: (torch.randn(*s, generator=g) * sc)
+    q, key, value = mk(B, D), mk(B, T, D), mk(B, T, E)
+    lens = torch.tensor(lens)
+    prev = torch.rand(B, T, generator=g)
+    prev = prev * (torch.arange(T)[None] < lens[:, None])
+    prev = prev / prev.sum(1, keepdim=True)
+    cw, pw, ew, eb = mk(K, 1, 2 * R + 1, sc=0.3), mk(D, K, sc=0.5), mk(1, D, sc=0.3), mk(1)
+    gc, ga = mk(B, E), mk(B, T)
+    names = ["q", "key", "value", "prev", "cw", "pw", "ew", "eb"]
+    ref_in = [t.double().requires_grad_(True) for t in (q, key, value, prev, cw, pw, ew, eb)]
+    cr, ar = _loc_attention_torch(ref_in[0], ref_in[1], ref_in[2], ref_in[3], lens, *ref_in[4:], 0.5)
+    ((cr * gc.double()).sum() + (ar * ga.double()).sum()).backward()
+    dev_in = [t.to(DEV).requires_grad_(True) for t in (q, key, value, prev, cw, pw, ew, eb)]
+    c, a = pkg.ops.loc_attention_step(dev_in[0], dev_in[1], dev_in[2], dev_in[3], lens.to(DEV), *dev_in[4:], 0.5)
+    assert scaled_err(a.detach().cpu().numpy(), ar.detach().numpy()) < 1e-5
+    assert scaled_err(c.detach().cpu().numpy(), cr.detach().numpy()) < 1e-5
+    assert float(a.detach().cpu()[torch.arange(T)[None] >= lens[:, None]].abs().max()) == 0      # masked frames
+    ((c * gc.to(DEV)).sum() + (a * ga.to(DEV)).sum()).backward()
+    for n, x, r in zip(names, dev_in, ref_in):
+        assert scaled_err(x.grad.cpu().numpy(), r.grad.numpy()) < 2e-5, n
+
+
 def test_gemm_tf32x3_is_fp32_class(pkg):
     """The error-compensated tensor-core GEMM must be as accurate as an fp32 SGEMM (vs an fp64 product)."""
     torch.manual_seed(0)
