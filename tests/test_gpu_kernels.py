@@ -280,7 +280,10 @@ def test_loc_attention_step_fwd_bwd(pkg, B, T, D, E, K, R, lens):
     assert float(a.detach().cpu()[torch.arange(T)[None] >= lens[:, None]].abs().max()) == 0      # masked frames
     ((c * gc.to(DEV)).sum() + (a * ga.to(DEV)).sum()).backward()
     for n, x, r in zip(names, dev_in, ref_in):
-        assert scaled_err(x.grad.cpu().numpy(), r.grad.numpy()) < 2e-5, n
+        if n == "eb":    # softmax is shift invariant: d/d(b_energy) is exactly 0 up to rounding
+            assert float(x.grad.abs().max()) < 1e-5 and float(r.grad.abs().max()) < 1e-12
+        else:
+            assert scaled_err(x.grad.cpu().numpy(), r.grad.numpy()) < 2e-5, n
 
 
 def test_gemm_tf32x3_is_fp32_class(pkg):
