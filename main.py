@@ -1,0 +1,53 @@
+#!/usr/bin/env python
+# coding: utf-8
+"""Same command line as the reference's main.py (/root/reference/main.py:13-47), driving the B200-native Solver.
+    python main.py --config config/b200/cfgB_ctc_char.yaml [--njobs 0] [--seed 0] [--load ckpt]
+    torchrun --nproc-per-node 8 --master-addr 127.0.0.1 main.py --config ...      (data parallel, one process per GPU)
+--cpu / --test / --lm select reference workloads that are outside this hot path and are refused."""
+import argparse
+import importlib
+
+import numpy as np
+import torch
+import yaml
+
+parser = argparse.ArgumentParser(description="Training E2E asr (B200-native hot path).")
+parser.add_argument("--config", type=str, help="Path to experiment config.")
+parser.add_argument("--name", default=None, type=str, help="Name for logging.")
+parser.add_argument("--logdir", default="log/", type=str, help="Logging path.")
+parser.add_argument("--ckpdir", default="ckpt/", type=str, help="Checkpoint path.")
+parser.add_argument("--outdir", default="result/", type=str, help="Decode output path.")
+parser.add_argument("--load", default=None, type=str, help="Load pre-trained model (for training only)")
+parser.add_argument("--seed", default=0, type=int, help="Random seed for reproducable results.")
+parser.add_argument("--cudnn-ctc", action="store_true", help="(reference flag) unsupported: the CTC kernel is ours")
+parser.add_argument("--njobs", default=6, type=int, help="Number of DataLoader worker processes.")
+parser.add_argument("--cpu", action="store_true", help="(reference flag) use the reference itself for CPU runs")
+parser.add_argument("--no-pin", action="store_true", help="Disable pin-memory for dataloader")
+parser.add_argument("--test", action="store_true", help="(reference flag) decoding is outside this hot path")
+parser.add_argument("--no-msg", action="store_true", help="Hide all messages.")
+parser.add_argument("--lm", action="store_true", help="(reference flag) RNNLM training is outside this hot path")
+parser.add_argument("--amp", action="store_true", help="(reference flag) unsupported")
+parser.add_argument("--reserve-gpu", default=0, type=float)
+parser.add_argument("--jit", action="store_true")
+
+
+def main():
+    paras = parser.parse_args()
+    setattr(paras, "gpu", not paras.cpu)
+    setattr(paras, "pin_memory", not paras.no_pin)
+    setattr(paras, "verbose", not paras.no_msg)
+    if paras.cpu or paras.test or paras.lm or paras.cudnn_ctc:
+        raise SystemExit("--cpu / --test / --lm / --cudnn-ctc select reference paths outside the B200 hot path")
+    config = yaml.load(open(paras.config, "r"), Loader=yaml.FullLoader)
+    np.random.seed(paras.seed)
+    torch.manual_seed(paras.seed)
+    torch.cuda.manual_seed_all(paras.seed)
+    pkg = importlib.import_module("end-to-end-asr-pytorch_b200")
+    solver = pkg.train_asr.Solver(config, paras, "train")
+    solver.load_data()
+    solver.set_model()
+    solver.exec()
+
+
+if __name__ == "__main__":
+    main()

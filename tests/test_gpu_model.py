@@ -79,3 +79,65 @@ def test_greedy_inference_ids_bit_exact(pkg, kind):
         _, _, out, _, _ = model(feat, flen, int(txt_len.max()) + 2)
     assert np.array_equal(out.argmax(-1).cpu().numpy(), g["greedy_argmax"])
     assert rel_err(out.cpu().numpy(), g["greedy_output"]) < 1e-4
+
+
+def _tiny_config(kind="hybrid"):
+    from oracle.make_golden import AUDIO_CFG
+    return {"data": {"audio": dict(AUDIO_CFG),
+                     "corpus": {"name": "Synthetic", "path": "", "train_split": ["syn"], "dev_split": ["syn"],
+                                "bucketing": False, "batch_size": 3, "n_samples": 8000, "vocab_size": 12,
+                                "n_batches": 4}, "text": {"mode": "character", "vocab_file": ""}},
+            "hparas": {"valid_step": 1000, "max_step": 2, "tf_start": 1.0, "tf_end": 1.0, "tf_step": 10,
+                       "optimizer": "Adadelta", "lr": 1.0, "eps": 1e-8, "lr_scheduler": "fixed", "curriculum": 0},
+            "model": tiny_model_cfg(kind)}
+
+
+@pytest.mark.parametrize("kind", ["ctc", "hybrid"])
+def test_two_train_steps_match_cpu_reference_path(pkg, kind):
+    """Front end + forward + losses + backward + clip + Adadelta, twice, through the public TrainStep API, against
+    the CPU restatement of the reference's --cpu path (oracle/ref_port.CpuTrainer) from identical weights."""
+    from oracle import ref_port
+    cfg = _tiny_config(kind)
+    step = pkg.TrainStep(cfg, 12, device=DEV, seed=3)
+    P = {k: v.detach().cpu().clone() for k, v in step.model.state_dict().items()}
+    cpu = ref_port.CpuTrainer(P, cfg["model"], cfg["data"]["audio"])
+    g = torch.Generator().manual_seed(9)
+    lens = [9000, 7700, 6400]
+    waves = [torch.clamp(0.05 * torch.randn(1, n, generator=g), -1, 1) for n in lens]
+    texts = [[3, 4, 4, 5, 1], [6, 7, 1], [8, 9, 10, 1]]
+    batch = torch.zeros(3, max(lens))
+    txt = torch.zeros(3, 5, dtype=torch.long)
+    for i in range(3):
+        batch[i, :lens[i]] = waves[i][0]
+        txt[i, :len(texts[i])] = torch.tensor(texts[i])
+    for it in range(2):
+        loss = step(batch.to(DEV), torch.tensor(lens), txt.to(DEV))
+        ref_loss, ref_norm = cpu.step(waves, texts)
+        assert abs(loss.item() - ref_loss) < 1e-4 * abs(ref_loss), (it, loss.item(), ref_loss)
+        assert abs(step.last["grad_norm"].item() - ref_norm) < 2e-4 * ref_norm
+    for k, v in step.model.state_dict().items():                      # parameters after two updates
+        ref = cpu.P[k].detach()
+        assert float((v.cpu() - ref).abs().max()) < 2e-4 * max(float(ref.abs().max()), 1e-2), k
+
+
+def test_solver_drop_in_loop(pkg, tmp_path):
+    """main.py's sequence Solver(config, paras, mode).load_data().set_model().exec() on the synthetic corpus."""
+    import argparse
+    cfg = _tiny_config("hybrid")
+    paras = argparse.Namespace(config="tiny.yaml", name="t", logdir=str(tmp_path / "log"), ckpdir=str(tmp_path / "ck"),
+                               outdir=str(tmp_path / "out"), load=None, seed=0, njobs=0, gpu=True, pin_memory=False,
+                               verbose=False, amp=False)
+    s = pkg.train_asr.Solver(cfg, paras, "train")
+    s.load_data()
+    s.set_model()
+    s.exec()
+    assert s.step >= 2
+    ck = torch.load(str(tmp_path / "ck" / "t" / "latest.pth"), map_location="cpu")
+    assert set(ck.keys()) == {"model", "optimizer", "global_step", "wer"}          # src/solver.py:164-169
+    assert set(ck["model"].keys()) == set(s.model.state_dict().keys())
+    # resume: --load restores weights, optimizer state and the step counter
+    paras.load = str(tmp_path / "ck" / "t" / "latest.pth")
+    s2 = pkg.train_asr.Solver(cfg, paras, "train")
+    s2.load_data()
+    s2.set_model()
+    assert s2.step == ck["global_step"]
