@@ -1,39 +1,49 @@
 // K7/K8: persistent (Bi)LSTM recurrence, forward and BPTT backward, fp32.
 //
-// Decomposition (same for fwd and bwd): one CTA per (direction, batch-group, unit-block). A CTA owns
-// UB hidden units (= 4*UB gate columns) for Bc batch rows and keeps its slice of W_hh resident in
-// shared memory for all T steps. Per step the CTAs of one (direction, batch-group) exchange the
-// small [Bc,H] state through an L2-resident buffer that every CTA pulls into shared memory with a
-// 1-D bulk async copy (TMA) tracked by mbarriers, and synchronise with one release/acquire counter.
+// Decomposition (same for fwd and bwd): one CTA per (direction, batch-group, unit-block). A CTA owns UB hidden units
+// (= 4*UB gate columns) for Bc batch rows and keeps its slice of W_hh resident in shared memory for all T steps.
+// The Bc rows are processed as NH = 2 independent halves that are INTERLEAVED in time: while the state exchange of
+// one half is in flight, the FMA pipes work on the other half, so the cross-SM latency is hidden.
+//
+//   warps 0-7  compute: 64 register tiles (4 gates x 4 rows) per half; the K dimension of a tile is split over 4
+//              lanes (one K-chunk each, matching the 4 bulk-copy chunks) and reduced with two warp shuffles, after
+//              which each of the 4 lanes finishes the pointwise cell update of one row of the tile.
+//   warp 8     producer: waits on the group's release/acquire counter, then pulls the [H,Bh] state block (fwd) or
+//              the [nub,Bh,UB] inbox of partial products (bwd) from L2 with 1-D bulk async copies (TMA) tracked
+//              by per-chunk "full" mbarriers; "empty" mbarriers hand the buffer back.
+// There is no CTA-wide or grid-wide barrier in the forward step loop; the backward has one named barrier among the
+// compute warps per half-step (the dG tile feeds all warps' GEMM tiles).
 //
 //   fwd step : gates[b, 4UB] = Gx[b,t] + h_{t-1}[b,:] . Wslice^T ; pointwise ; publish h_t slice
 //   bwd step : dh = dOut[b,t] + sum_src partial_src[b, my units] ; pointwise -> dG[b,4UB] ;
-//              partial_me[b, :] = dG . Wslice  (scattered to every destination's inbox)
+//              partial_me[b, :] = dG . Wslice  (scattered to every destination's inbox, deterministic, no atomics)
 //
-// The input projection (x . W_ih^T + b_ih + b_hh, K6) and the weight-gradient contractions are plain
-// GEMMs done by the caller; this file is the sequential part.
+// The input projection (x . W_ih^T + b_ih + b_hh, K6) and the weight-gradient contractions are tensor-core GEMMs
+// done by the caller; this file is the sequential part.
 //
-// Reference behaviour restated: torch.nn.LSTM as called from /root/reference/src/module.py:112-113,
-// 129-132 (single layer, batch_first, zero initial state, run over the zero-padded frames - no
-// packing), gate order i,f,g,o.
+// Reference behaviour restated: torch.nn.LSTM as called from /root/reference/src/module.py:112-113,129-132 (single
+// layer, batch_first, zero initial state, run over the zero-padded frames - no packing), gates i,f,g,o.
 #include "common.cuh"
 #include "../../include/b200asr.h"
 
 namespace b200asr {
 
-constexpr int LSTM_THREADS = 256;
-constexpr int LSTM_HALF = 128;
+constexpr int LSTM_CWARPS = 8;                      // compute warps
+constexpr int LSTM_CTHREADS = LSTM_CWARPS * 32;     // 256
+constexpr int LSTM_THREADS = LSTM_CTHREADS + 32;    // + producer warp
 constexpr int LSTM_NCHUNK = 4;
+constexpr int LSTM_MAX_TILES = 64;                  // register tiles per half
+constexpr int LSTM_COUNTER_BYTES = 4096;
 
 struct LstmParams {
     float* gates;        // [ndir][B][T][H][4]
-    const float* whh;    // packed, see lstm_pack kernels
+    const float* whh;    // packed, see lstm_pack_kernel
     float* cst;          // [ndir][B][T][H]
     float* out;          // fwd: layer output [B][T][ndir*H]; bwd: dOut (read only)
     float* xbuf;         // exchange buffers
-    unsigned* counters;  // [ndir][nbg]
+    unsigned* counters;  // [ndir][nbg][NH]
     int* err_flag;
-    int B, T, H, ndir, UB, Bc, nub, nbg;
+    int B, T, H, ndir, UB, Bc, nub, nbg, NH;
 };
 
 __device__ __forceinline__ void spin_until(const unsigned* ctr, unsigned target, int* err_flag) {
@@ -47,6 +57,13 @@ __device__ __forceinline__ void spin_until(const unsigned* ctr, unsigned target,
     }
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------
 // Weight packing. Source: PyTorch layout w[dir][g*H + j][k] (gate-major rows).
 //   fwd pack: dst[dir][ub][k][u][g]           (per-CTA slice contiguous, k-major)
@@ -55,7 +72,6 @@ __global__ void lstm_pack_kernel(const float* __restrict__ w, float* __restrict_
                                  int for_bwd) {
     const long long n = (long long)ndir * 4 * H * H;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        // i indexes the destination
         long long r = i;
         const int dir = (int)(r / (4LL * H * H));
         r -= (long long)dir * 4 * H * H;
@@ -78,185 +94,180 @@ __global__ void lstm_pack_kernel(const float* __restrict__ w, float* __restrict_
     }
 }
 
-// exchange-buffer index (in float4 units) of (k, bq) inside one [H][Bc] state block:
-// chunk-major over k so that each of the LSTM_NCHUNK pieces is one contiguous bulk copy and a
-// producer's UB consecutive units land in consecutive 16-B slots.
-__device__ __forceinline__ int hx_index(int k, int bq, int KC, int NBQ) {
-    const int kc = k / KC;
-    return (kc * NBQ + bq) * KC + (k - kc * KC);
-}
+#define FMA16(hv, wv)                                                                                 \
+    acc[0][0] = fmaf(hv.x, wv.x, acc[0][0]); acc[0][1] = fmaf(hv.x, wv.y, acc[0][1]);                 \
+    acc[0][2] = fmaf(hv.x, wv.z, acc[0][2]); acc[0][3] = fmaf(hv.x, wv.w, acc[0][3]);                 \
+    acc[1][0] = fmaf(hv.y, wv.x, acc[1][0]); acc[1][1] = fmaf(hv.y, wv.y, acc[1][1]);                 \
+    acc[1][2] = fmaf(hv.y, wv.z, acc[1][2]); acc[1][3] = fmaf(hv.y, wv.w, acc[1][3]);                 \
+    acc[2][0] = fmaf(hv.z, wv.x, acc[2][0]); acc[2][1] = fmaf(hv.z, wv.y, acc[2][1]);                 \
+    acc[2][2] = fmaf(hv.z, wv.z, acc[2][2]); acc[2][3] = fmaf(hv.z, wv.w, acc[2][3]);                 \
+    acc[3][0] = fmaf(hv.w, wv.x, acc[3][0]); acc[3][1] = fmaf(hv.w, wv.y, acc[3][1]);                 \
+    acc[3][2] = fmaf(hv.w, wv.z, acc[3][2]); acc[3][3] = fmaf(hv.w, wv.w, acc[3][3]);
 
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(LSTM_THREADS, 1) bilstm_fwd_kernel(LstmParams p) {
     extern __shared__ __align__(128) unsigned char s_raw[];
-    const int H = p.H, UB = p.UB, Bc = p.Bc, T = p.T;
-    const int NBQ = Bc >> 2;
+    const int H = p.H, UB = p.UB, Bc = p.Bc, T = p.T, NH = p.NH;
+    const int Bh = Bc / NH;
+    const int NBQ = Bh >> 2;                 // batch quads per half
     const int KC = H / LSTM_NCHUNK;
-    float4* Ws = reinterpret_cast<float4*>(s_raw);                           // [H][UB] float4 (4 gates)
-    float4* hs = Ws + (size_t)H * UB;                                        // [H*NBQ] float4 (4 batch rows)
-    float* red = reinterpret_cast<float*>(hs + (size_t)H * NBQ);             // [16][128]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(red + 16 * LSTM_HALF);      // [LSTM_NCHUNK]
+    float4* Ws = reinterpret_cast<float4*>(s_raw);                               // [H][UB] float4 (4 gates)
+    float* hs = reinterpret_cast<float*>(Ws + (size_t)H * UB);                   // [NH][H*Bh]
+    uint64_t* full = reinterpret_cast<uint64_t*>(hs + (size_t)H * Bc);           // [NH][NCHUNK]
+    uint64_t* empty = full + 2 * LSTM_NCHUNK;                                    // [NH]
 
     const int tid = threadIdx.x;
-    const int half = tid / LSTM_HALF;
-    const int pidx = tid % LSTM_HALF;
+    const int warp = tid >> 5, lane = tid & 31;
     int blk = blockIdx.x;
     const int ub = blk % p.nub; blk /= p.nub;
     const int bg = blk % p.nbg; blk /= p.nbg;
     const int dir = blk;
 
-    const int NP = UB * NBQ;
-    const bool has_tile = pidx < NP;
-    const int u = has_tile ? pidx % UB : 0;
-    const int bq = has_tile ? pidx / UB : 0;
-    const int ug = ub * UB + u;
-
-    // resident W_hh slice
-    {
+    {   // resident W_hh slice
         const float4* src = reinterpret_cast<const float4*>(p.whh) + ((size_t)dir * p.nub + ub) * (size_t)H * UB;
         for (int i = tid; i < H * UB; i += LSTM_THREADS) Ws[i] = src[i];
     }
     if (tid == 0) {
-        for (int c = 0; c < LSTM_NCHUNK; ++c) mbar_init(&bars[c], 1);
+        for (int i = 0; i < 2 * LSTM_NCHUNK; ++i) mbar_init(&full[i], 1);
+        for (int i = 0; i < 2; ++i) mbar_init(&empty[i], LSTM_CWARPS);
         mbar_fence_init();
     }
     __syncthreads();
 
-    const size_t blk_f4 = (size_t)H * NBQ;  // float4 per state block
-    float4* xb = reinterpret_cast<float4*>(p.xbuf) + ((size_t)dir * p.nbg + bg) * 2 * blk_f4;
-    unsigned* ctr = p.counters + dir * p.nbg + bg;
-    const uint32_t chunk_bytes = (uint32_t)((size_t)KC * NBQ * sizeof(float4));
+    const size_t half_elems = (size_t)H * Bh;                                    // floats per state block
+    float* xb = p.xbuf + ((size_t)dir * p.nbg + bg) * NH * 2 * half_elems;       // [NH][2][H*Bh]
+    unsigned* ctr = p.counters + ((size_t)dir * p.nbg + bg) * NH;
+    const uint32_t chunk_bytes = (uint32_t)((size_t)KC * Bh * sizeof(float));
+    const unsigned per_step = (unsigned)p.nub * LSTM_CWARPS;                     // releases per step per half
 
-    float c_reg[4] = {0.f, 0.f, 0.f, 0.f};
-    uint32_t phase = 0;
-    const int b0 = bg * Bc + bq * 4;
+    if (warp == LSTM_CWARPS) {
+        // ===== producer warp =====
+        if (lane == 0) {
+            for (int step = 1; step < T; ++step) {
+                for (int hf = 0; hf < NH; ++hf) {
+                    spin_until(ctr + hf, (unsigned)step * per_step, p.err_flag);
+                    if (step >= 2) mbar_wait(&empty[hf], (uint32_t)(step & 1));   // fill #(step-1) needs release #(step-2)
+                    fence_proxy_async();
+                    const float* src = xb + ((size_t)hf * 2 + ((step - 1) & 1)) * half_elems;
+                    float* dst = hs + (size_t)hf * half_elems;
+                    for (int c = 0; c < LSTM_NCHUNK; ++c) {
+                        mbar_expect_tx(&full[hf * LSTM_NCHUNK + c], chunk_bytes);
+                        bulk_g2s(dst + (size_t)c * KC * Bh, src + (size_t)c * KC * Bh, chunk_bytes,
+                                 &full[hf * LSTM_NCHUNK + c]);
+                    }
+                }
+            }
+        }
+        return;
+    }
+
+    // ===== compute warps =====
+    const int kq = lane >> 3;                 // K chunk of this lane
+    const int tl = lane & 7;
+    const int tile = warp * 8 + tl;
+    const int NT = UB * NBQ;
+    const bool has_tile = tile < NT;
+    const int u = has_tile ? tile % UB : 0;
+    const int bq = has_tile ? tile / UB : 0;
+    const int ug = ub * UB + u;
+    float c_reg[2] = {0.f, 0.f};
 
     for (int step = 0; step < T; ++step) {
         const int tt = dir ? (T - 1 - step) : step;
-        float4 gx[4];
-        if (half == 0 && has_tile) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int b = b0 + i;
-                gx[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (b < p.B)
-                    gx[i] = *reinterpret_cast<const float4*>(p.gates + ((((size_t)dir * p.B + b) * T + tt) * H + ug) * 4);
-            }
-        }
-        float acc[4][4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int g = 0; g < 4; ++g) acc[i][g] = 0.f;
+        for (int hf = 0; hf < 2; ++hf) {
+            if (hf >= NH) break;
+            const int bl = bq * 4 + kq;                                // my row within the half
+            const int b = bg * Bc + hf * Bh + bl;
+            const bool valid = has_tile && b < p.B;
+            const size_t row = ((size_t)dir * p.B + (valid ? b : 0)) * T + tt;
+            float4 gx = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid) gx = *reinterpret_cast<const float4*>(p.gates + (row * H + ug) * 4);
 
-        if (step > 0) {
-            if (tid == 0) {
-                spin_until(ctr, (unsigned)step * p.nub, p.err_flag);
-                fence_proxy_async();
-                const float4* src = xb + (size_t)((step - 1) & 1) * blk_f4;
-                for (int c = 0; c < LSTM_NCHUNK; ++c) {
-                    mbar_expect_tx(&bars[c], chunk_bytes);
-                    bulk_g2s(hs + (size_t)c * KC * NBQ, src + (size_t)c * KC * NBQ, chunk_bytes, &bars[c]);
-                }
-            }
-            if (has_tile) {
-#pragma unroll 1
-                for (int cc = 0; cc < LSTM_NCHUNK / 2; ++cc) {
-                    const int c = half * (LSTM_NCHUNK / 2) + cc;
-                    mbar_wait(&bars[c], phase);
-                    const float4* hp = hs + ((size_t)c * NBQ + bq) * KC;
-                    const float4* wp = Ws + (size_t)c * KC * UB + u;
+            float acc[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int g = 0; g < 4; ++g) acc[i][g] = 0.f;
+
+            if (step > 0) {
+                mbar_wait(&full[hf * LSTM_NCHUNK + kq], (uint32_t)((step - 1) & 1));
+                const float4* hp = reinterpret_cast<const float4*>(hs + (size_t)hf * half_elems + (size_t)kq * KC * Bh) + bq;
+                const float4* wp = Ws + (size_t)kq * KC * UB + u;
+                // software pipelined: the loads of k+1 are in flight while the 16 FMAs of k issue
+                float4 h0 = hp[0], w0 = wp[0];
 #pragma unroll 4
-                    for (int kk = 0; kk < KC; ++kk) {
-                        const float4 hv = hp[kk];
-                        const float4 wv = wp[(size_t)kk * UB];
-                        acc[0][0] = fmaf(hv.x, wv.x, acc[0][0]); acc[0][1] = fmaf(hv.x, wv.y, acc[0][1]);
-                        acc[0][2] = fmaf(hv.x, wv.z, acc[0][2]); acc[0][3] = fmaf(hv.x, wv.w, acc[0][3]);
-                        acc[1][0] = fmaf(hv.y, wv.x, acc[1][0]); acc[1][1] = fmaf(hv.y, wv.y, acc[1][1]);
-                        acc[1][2] = fmaf(hv.y, wv.z, acc[1][2]); acc[1][3] = fmaf(hv.y, wv.w, acc[1][3]);
-                        acc[2][0] = fmaf(hv.z, wv.x, acc[2][0]); acc[2][1] = fmaf(hv.z, wv.y, acc[2][1]);
-                        acc[2][2] = fmaf(hv.z, wv.z, acc[2][2]); acc[2][3] = fmaf(hv.z, wv.w, acc[2][3]);
-                        acc[3][0] = fmaf(hv.w, wv.x, acc[3][0]); acc[3][1] = fmaf(hv.w, wv.y, acc[3][1]);
-                        acc[3][2] = fmaf(hv.w, wv.z, acc[3][2]); acc[3][3] = fmaf(hv.w, wv.w, acc[3][3]);
+                for (int kk = 1; kk < KC; ++kk) {
+                    const float4 h1 = hp[(size_t)kk * NBQ];
+                    const float4 w1 = wp[(size_t)kk * UB];
+                    FMA16(h0, w0)
+                    h0 = h1;
+                    w0 = w1;
+                }
+                FMA16(h0, w0)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[hf]);
+                // reduce the 4 K-chunks (lanes l, l^8, l^16, l^24)
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        float v = acc[i][g];
+                        v += __shfl_xor_sync(0xffffffffu, v, 8);
+                        v += __shfl_xor_sync(0xffffffffu, v, 16);
+                        acc[i][g] = v;
                     }
-                }
-            } else {
-                // threads without a tile still must observe the barriers' phases consistently: nothing to do
             }
-            phase ^= 1;
-            if (half == 1 && has_tile) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) red[(i * 4 + g) * LSTM_HALF + pidx] = acc[i][g];
+            // lane kq finishes row kq of the tile
+            float a0, a1, a2, a3;
+            if (kq == 0) { a0 = acc[0][0]; a1 = acc[0][1]; a2 = acc[0][2]; a3 = acc[0][3]; }
+            else if (kq == 1) { a0 = acc[1][0]; a1 = acc[1][1]; a2 = acc[1][2]; a3 = acc[1][3]; }
+            else if (kq == 2) { a0 = acc[2][0]; a1 = acc[2][1]; a2 = acc[2][2]; a3 = acc[2][3]; }
+            else { a0 = acc[3][0]; a1 = acc[3][1]; a2 = acc[3][2]; a3 = acc[3][3]; }
+            float hval = 0.f;
+            if (valid) {
+                const float ig = sigmoidf_(gx.x + a0);
+                const float fg = sigmoidf_(gx.y + a1);
+                const float gg = tanhf(gx.z + a2);
+                const float og = sigmoidf_(gx.w + a3);
+                const float c = fmaf(fg, c_reg[hf], ig * gg);
+                c_reg[hf] = c;
+                hval = og * tanhf(c);
+                *reinterpret_cast<float4*>(p.gates + (row * H + ug) * 4) = make_float4(ig, fg, gg, og);
+                p.cst[row * H + ug] = c;
+                p.out[((size_t)b * T + tt) * (p.ndir * H) + (size_t)dir * H + ug] = hval;
             }
-            __syncthreads();
-            if (half == 0 && has_tile) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) acc[i][g] += red[(i * 4 + g) * LSTM_HALF + pidx];
-            }
-        }
-
-        if (half == 0 && has_tile) {
-            float hq[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int b = b0 + i;
-                hq[i] = 0.f;
-                if (b < p.B) {
-                    const float ig = sigmoidf_(gx[i].x + acc[i][0]);
-                    const float fg = sigmoidf_(gx[i].y + acc[i][1]);
-                    const float gg = tanhf(gx[i].z + acc[i][2]);
-                    const float og = sigmoidf_(gx[i].w + acc[i][3]);
-                    const float c = fmaf(fg, c_reg[i], ig * gg);
-                    c_reg[i] = c;
-                    const float h = og * tanhf(c);
-                    hq[i] = h;
-                    const size_t row = ((size_t)dir * p.B + b) * T + tt;
-                    *reinterpret_cast<float4*>(p.gates + (row * H + ug) * 4) = make_float4(ig, fg, gg, og);
-                    p.cst[row * H + ug] = c;
-                    p.out[((size_t)b * T + tt) * (p.ndir * H) + (size_t)dir * H + ug] = h;
+            if (step + 1 < T) {
+                if (has_tile) xb[((size_t)hf * 2 + (step & 1)) * half_elems + (size_t)ug * Bh + bl] = hval;
+                __syncwarp();
+                if (lane == 0) {
+                    __threadfence();
+                    red_release_add_u32(ctr + hf, 1u);
                 }
             }
-            if (step + 1 < T)
-                xb[(size_t)(step & 1) * blk_f4 + hx_index(ug, bq, KC, NBQ)] = make_float4(hq[0], hq[1], hq[2], hq[3]);
-        }
-        __syncthreads();
-        if (tid == 0 && step + 1 < T) {
-            __threadfence();
-            red_release_add_u32(ctr, 1u);
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// Backward. Shared memory: Wr[4UB][H] | inbox[nub][Bc][UB] (== Bc*H floats) | dGs[4UB][Bc] | red | bars
+// Backward. Shared memory: Wr[4UB][H] | inbox[NH][nub*Bh*UB] | dGs[2][4UB*Bh] | barriers
 __global__ void __launch_bounds__(LSTM_THREADS, 1) bilstm_bwd_kernel(LstmParams p) {
     extern __shared__ __align__(128) unsigned char s_raw[];
-    const int H = p.H, UB = p.UB, Bc = p.Bc, T = p.T, nub = p.nub;
-    const int NBQ = Bc >> 2;
+    const int H = p.H, UB = p.UB, Bc = p.Bc, T = p.T, nub = p.nub, NH = p.NH;
+    const int Bh = Bc / NH;
+    const int NBQ = Bh >> 2;
     float* Wr = reinterpret_cast<float*>(s_raw);                 // [4UB][H]
-    float* inbox = Wr + (size_t)4 * UB * H;                      // [nub][Bc][UB]
-    float* dGs = inbox + (size_t)Bc * H;                         // [4UB][Bc]
-    float* red = dGs + (size_t)4 * UB * Bc;                      // [4][128]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(red + 4 * LSTM_HALF);
+    float* inbox = Wr + (size_t)4 * UB * H;                      // [NH][nub*Bh*UB]  (= Bc*H floats)
+    float* dGs = inbox + (size_t)Bc * H;                         // [2][4UB*Bh]
+    uint64_t* full = reinterpret_cast<uint64_t*>(dGs + (size_t)2 * 4 * UB * Bh);
+    uint64_t* empty = full + 2 * LSTM_NCHUNK;
 
     const int tid = threadIdx.x;
-    const int half = tid / LSTM_HALF;
-    const int pidx = tid % LSTM_HALF;
+    const int warp = tid >> 5, lane = tid & 31;
     int blk = blockIdx.x;
     const int ub = blk % nub; blk /= nub;
     const int bg = blk % p.nbg; blk /= p.nbg;
     const int dir = blk;
-
-    const int NP = UB * NBQ;
-    const bool has_tile = pidx < NP;
-    const int u = has_tile ? pidx % UB : 0;
-    const int bq = has_tile ? pidx / UB : 0;
-    const int ug = ub * UB + u;
-    const int b0 = bg * Bc + bq * 4;
 
     {
         const float4* src = reinterpret_cast<const float4*>(p.whh) + ((size_t)dir * nub + ub) * (size_t)H * UB;
@@ -264,166 +275,169 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) bilstm_bwd_kernel(LstmParams 
         for (int i = tid; i < H * UB; i += LSTM_THREADS) dst[i] = src[i];
     }
     if (tid == 0) {
-        for (int c = 0; c < LSTM_NCHUNK; ++c) mbar_init(&bars[c], 1);
+        for (int i = 0; i < 2 * LSTM_NCHUNK; ++i) mbar_init(&full[i], 1);
+        for (int i = 0; i < 2; ++i) mbar_init(&empty[i], LSTM_CWARPS);
         mbar_fence_init();
     }
     __syncthreads();
 
-    // inbox of destination d (for one parity): [src nub][Bc][UB]  -> Bc*H floats
-    const size_t inbox_elems = (size_t)Bc * H;
-    float* xb = p.xbuf + ((size_t)dir * p.nbg + bg) * 2 * (size_t)nub * inbox_elems;
-    unsigned* ctr = p.counters + dir * p.nbg + bg;
-    // the inbox is pulled in LSTM_NCHUNK pieces along the source index
-    const int SC = (nub + LSTM_NCHUNK - 1) / LSTM_NCHUNK;  // sources per chunk
+    // global inbox layout per (dir, bg, half, parity): [dst nub][src nub][Bh][UB]
+    const size_t inbox_elems = (size_t)Bh * H;                   // floats one destination receives per half-step
+    float* xb = p.xbuf + ((size_t)dir * p.nbg + bg) * NH * 2 * (size_t)nub * inbox_elems;
+    unsigned* ctr = p.counters + ((size_t)dir * p.nbg + bg) * NH;
+    const int SC = (nub + LSTM_NCHUNK - 1) / LSTM_NCHUNK;        // sources per chunk
+    const unsigned per_step = (unsigned)nub * LSTM_CWARPS;
 
-    float dc_reg[4] = {0.f, 0.f, 0.f, 0.f};
-    uint32_t phase = 0;
+    if (warp == LSTM_CWARPS) {
+        if (lane == 0) {
+            for (int step = 1; step < T; ++step) {
+                for (int hf = 0; hf < NH; ++hf) {
+                    spin_until(ctr + hf, (unsigned)step * per_step, p.err_flag);
+                    if (step >= 2) mbar_wait(&empty[hf], (uint32_t)(step & 1));
+                    fence_proxy_async();
+                    const float* src = xb + (((size_t)hf * 2 + ((step - 1) & 1)) * nub + ub) * inbox_elems;
+                    float* dst = inbox + (size_t)hf * inbox_elems;
+                    for (int c = 0; c < LSTM_NCHUNK; ++c) {
+                        const int s0 = c * SC;
+                        const int s1 = min(nub, s0 + SC);
+                        const uint32_t bytes = (s1 > s0) ? (uint32_t)((size_t)(s1 - s0) * Bh * UB * sizeof(float)) : 0u;
+                        mbar_expect_tx(&full[hf * LSTM_NCHUNK + c], bytes);
+                        if (bytes)
+                            bulk_g2s(dst + (size_t)s0 * Bh * UB, src + (size_t)s0 * Bh * UB, bytes,
+                                     &full[hf * LSTM_NCHUNK + c]);
+                    }
+                }
+            }
+        }
+        return;
+    }
+
+    const int kq = lane >> 3;
+    const int tl = lane & 7;
+    const int tile = warp * 8 + tl;
+    const int NT = UB * NBQ;
+    const bool has_tile = tile < NT;
+    const int u = has_tile ? tile % UB : 0;
+    const int bq = has_tile ? tile / UB : 0;
+    const int ug = ub * UB + u;
     const bool vec_ok = (UB % 4) == 0;
+    float dc_reg[2] = {0.f, 0.f};
 
     for (int step = 0; step < T; ++step) {
         const int fstep = T - 1 - step;                    // forward step index being differentiated
         const int tt = dir ? (T - 1 - fstep) : fstep;      // its time index
         const int tt_prev = dir ? tt + 1 : tt - 1;         // time index of the previous forward step
-        float4 gt[4];
-        float ct[4], cp[4], dh[4];
-        if (half == 0 && has_tile) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int b = b0 + i;
-                gt[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                ct[i] = cp[i] = dh[i] = 0.f;
-                if (b < p.B) {
-                    const size_t row = ((size_t)dir * p.B + b) * T + tt;
-                    gt[i] = *reinterpret_cast<const float4*>(p.gates + (row * H + ug) * 4);
-                    ct[i] = p.cst[row * H + ug];
-                    if (fstep > 0) cp[i] = p.cst[(((size_t)dir * p.B + b) * T + tt_prev) * H + ug];
-                    dh[i] = p.out[((size_t)b * T + tt) * (p.ndir * H) + (size_t)dir * H + ug];
-                }
+        for (int hf = 0; hf < 2; ++hf) {
+            if (hf >= NH) break;
+            const int ps = (step * NH + hf) & 1;           // dGs buffer of this half-step
+            const int bl = bq * 4 + kq;
+            const int b = bg * Bc + hf * Bh + bl;
+            const bool valid = has_tile && b < p.B;
+            const size_t row = ((size_t)dir * p.B + (valid ? b : 0)) * T + tt;
+            float4 gt = make_float4(0.f, 0.f, 0.f, 0.f);
+            float ct = 0.f, cp = 0.f, dh = 0.f;
+            if (valid) {
+                gt = *reinterpret_cast<const float4*>(p.gates + (row * H + ug) * 4);
+                ct = p.cst[row * H + ug];
+                if (fstep > 0) cp = p.cst[(((size_t)dir * p.B + b) * T + tt_prev) * H + ug];
+                dh = p.out[((size_t)b * T + tt) * (p.ndir * H) + (size_t)dir * H + ug];
             }
-        }
-        if (step > 0) {
-            if (tid == 0) {
-                spin_until(ctr, (unsigned)step * nub, p.err_flag);
-                fence_proxy_async();
-                const float* src = xb + ((size_t)((step - 1) & 1) * nub + ub) * inbox_elems;
+            if (step > 0) {
+                float part = 0.f;
+                const float* ib = inbox + (size_t)hf * inbox_elems + (size_t)bl * UB + u;
                 for (int c = 0; c < LSTM_NCHUNK; ++c) {
+                    mbar_wait(&full[hf * LSTM_NCHUNK + c], (uint32_t)((step - 1) & 1));
                     const int s0 = c * SC;
                     const int s1 = min(nub, s0 + SC);
-                    const uint32_t bytes = (s1 > s0) ? (uint32_t)((size_t)(s1 - s0) * Bc * UB * sizeof(float)) : 0u;
-                    mbar_expect_tx(&bars[c], bytes);
-                    if (bytes) bulk_g2s(inbox + (size_t)s0 * Bc * UB, src + (size_t)s0 * Bc * UB, bytes, &bars[c]);
+                    if (has_tile)
+                        for (int s = s0; s < s1; ++s) part += ib[(size_t)s * Bh * UB];
                 }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[hf]);
+                dh += part;
             }
-            float part[4] = {0.f, 0.f, 0.f, 0.f};
+            // pointwise backward of the cell
+            float4 dg = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid) {
+                const float ig = gt.x, fg = gt.y, gg = gt.z, og = gt.w;
+                const float tc = tanhf(ct);
+                const float dc = dc_reg[hf] + dh * og * (1.f - tc * tc);
+                dg.x = dc * gg * ig * (1.f - ig);
+                dg.y = dc * cp * fg * (1.f - fg);
+                dg.z = dc * ig * (1.f - gg * gg);
+                dg.w = dh * tc * og * (1.f - og);
+                dc_reg[hf] = dc * fg;
+                *reinterpret_cast<float4*>(p.gates + (row * H + ug) * 4) = dg;
+            }
             if (has_tile) {
-                for (int cc = 0; cc < LSTM_NCHUNK / 2; ++cc) {
-                    const int c = half * (LSTM_NCHUNK / 2) + cc;
-                    mbar_wait(&bars[c], phase);
-                    const int s0 = c * SC;
-                    const int s1 = min(nub, s0 + SC);
-                    for (int s = s0; s < s1; ++s) {
-                        const float* ib = inbox + ((size_t)s * Bc + bq * 4) * UB + u;
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) part[i] += ib[i * UB];
-                    }
-                }
+                float* d = dGs + (size_t)ps * 4 * UB * Bh + (size_t)(u * 4) * Bh + bl;
+                d[0] = dg.x; d[Bh] = dg.y; d[2 * Bh] = dg.z; d[3 * Bh] = dg.w;
             }
-            phase ^= 1;
-            if (half == 1 && has_tile) {
+            named_bar_sync(1, LSTM_CTHREADS);              // the dG tile of this half-step is complete
+            if (step + 1 < T) {
+                // partial[b][k] = sum_c dGs[c][b] * Wr[c][k]; thread tiles of 4 rows x (2 strided float4 of k)
+                const float* dgs = dGs + (size_t)ps * 4 * UB * Bh;
+                const int NKQ = H / 8;
+                const int ntiles = NKQ * NBQ;
+                float* outbase = xb + ((size_t)hf * 2 + (step & 1)) * nub * inbox_elems;
+                for (int t2 = tid; t2 < ntiles; t2 += LSTM_CTHREADS) {
+                    const int kq2 = t2 % NKQ;
+                    const int bq2 = t2 / NKQ;
+                    float a[4][8];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) red[i * LSTM_HALF + pidx] = part[i];
-            }
-            __syncthreads();
-            if (half == 0 && has_tile) {
+                    for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int i = 0; i < 4; ++i) dh[i] += part[i] + red[i * LSTM_HALF + pidx];
-            }
-        }
-        // pointwise backward of the cell
-        if (half == 0 && has_tile) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int b = b0 + i;
-                float4 dg = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (b < p.B) {
-                    const float ig = gt[i].x, fg = gt[i].y, gg = gt[i].z, og = gt[i].w;
-                    const float tc = tanhf(ct[i]);
-                    const float dout_o = dh[i] * tc;
-                    const float dc = dc_reg[i] + dh[i] * og * (1.f - tc * tc);
-                    dg.x = dc * gg * ig * (1.f - ig);
-                    dg.y = dc * cp[i] * fg * (1.f - fg);
-                    dg.z = dc * ig * (1.f - gg * gg);
-                    dg.w = dout_o * og * (1.f - og);
-                    dc_reg[i] = dc * fg;
-                    const size_t row = ((size_t)dir * p.B + b) * T + tt;
-                    *reinterpret_cast<float4*>(p.gates + (row * H + ug) * 4) = dg;
-                }
-                // stage for the matmul: dGs[(u*4+g)][b_local]
-                const int bl = bq * 4 + i;
-                dGs[(u * 4 + 0) * Bc + bl] = dg.x;
-                dGs[(u * 4 + 1) * Bc + bl] = dg.y;
-                dGs[(u * 4 + 2) * Bc + bl] = dg.z;
-                dGs[(u * 4 + 3) * Bc + bl] = dg.w;
-            }
-        }
-        __syncthreads();
-        if (step + 1 < T) {
-            // partial[b][k] = sum_c dGs[c][b] * Wr[c][k]; tiles of 4 batch rows x (4 strided float4 of k)
-            const int NKQ = H / 16;              // threads along k; each owns k = r*(H/4) + kq*4 + j
-            const int ntiles = NKQ * NBQ;
-            float* outbase = xb + (size_t)(step & 1) * nub * inbox_elems;
-            for (int tile = tid; tile < ntiles; tile += LSTM_THREADS) {
-                const int kq = tile % NKQ;
-                const int tbq = tile / NKQ;
-                float a[4][16];
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) a[i][j] = 0.f;
-                const int C = 4 * UB;
-#pragma unroll 2
-                for (int c = 0; c < C; ++c) {
-                    const float4 d4 = *reinterpret_cast<const float4*>(dGs + (size_t)c * Bc + tbq * 4);
-                    const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        const float4 w4 = *reinterpret_cast<const float4*>(Wr + (size_t)c * H + r * (H / 4) + kq * 4);
+                        for (int j = 0; j < 8; ++j) a[i][j] = 0.f;
+                    const int C = 4 * UB;
+                    const float* wbase = Wr + kq2 * 4;
+                    float4 d4 = *reinterpret_cast<const float4*>(dgs + bq2 * 4);
+                    float4 wa = *reinterpret_cast<const float4*>(wbase);
+                    float4 wb = *reinterpret_cast<const float4*>(wbase + (H >> 1));
+#pragma unroll 4
+                    for (int c = 0; c < C; ++c) {
+                        const int cn = (c + 1 < C) ? c + 1 : c;
+                        const float4 d4n = *reinterpret_cast<const float4*>(dgs + (size_t)cn * Bh + bq2 * 4);
+                        const float4 wan = *reinterpret_cast<const float4*>(wbase + (size_t)cn * H);
+                        const float4 wbn = *reinterpret_cast<const float4*>(wbase + (size_t)cn * H + (H >> 1));
+                        const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
-                            a[i][r * 4 + 0] = fmaf(dv[i], w4.x, a[i][r * 4 + 0]);
-                            a[i][r * 4 + 1] = fmaf(dv[i], w4.y, a[i][r * 4 + 1]);
-                            a[i][r * 4 + 2] = fmaf(dv[i], w4.z, a[i][r * 4 + 2]);
-                            a[i][r * 4 + 3] = fmaf(dv[i], w4.w, a[i][r * 4 + 3]);
+                            a[i][0] = fmaf(dv[i], wa.x, a[i][0]); a[i][1] = fmaf(dv[i], wa.y, a[i][1]);
+                            a[i][2] = fmaf(dv[i], wa.z, a[i][2]); a[i][3] = fmaf(dv[i], wa.w, a[i][3]);
+                            a[i][4] = fmaf(dv[i], wb.x, a[i][4]); a[i][5] = fmaf(dv[i], wb.y, a[i][5]);
+                            a[i][6] = fmaf(dv[i], wb.z, a[i][6]); a[i][7] = fmaf(dv[i], wb.w, a[i][7]);
                         }
+                        d4 = d4n; wa = wan; wb = wbn;
                     }
-                }
-                // scatter to the destination inboxes: element (dst, src=ub, b_local, u')
+                    // scatter to the destination inboxes: element (dst, src=ub, row, u')
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const int k0 = r * (H / 4) + kq * 4;
+                    for (int r = 0; r < 2; ++r) {
+                        const int k0 = r * (H >> 1) + kq2 * 4;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int bl = tbq * 4 + i;
-                        if (vec_ok) {
-                            const int dst = k0 / UB, uu = k0 - dst * UB;
-                            float* o = outbase + (((size_t)dst * nub + ub) * Bc + bl) * UB + uu;
-                            *reinterpret_cast<float4*>(o) =
-                                make_float4(a[i][r * 4], a[i][r * 4 + 1], a[i][r * 4 + 2], a[i][r * 4 + 3]);
-                        } else {
+                        for (int i = 0; i < 4; ++i) {
+                            const int rowl = bq2 * 4 + i;
+                            if (vec_ok) {
+                                const int dst = k0 / UB, uu = k0 - dst * UB;
+                                float* o = outbase + (((size_t)dst * nub + ub) * Bh + rowl) * UB + uu;
+                                *reinterpret_cast<float4*>(o) =
+                                    make_float4(a[i][r * 4], a[i][r * 4 + 1], a[i][r * 4 + 2], a[i][r * 4 + 3]);
+                            } else {
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const int k = k0 + j;
-                                const int dst = k / UB, uu = k - dst * UB;
-                                outbase[(((size_t)dst * nub + ub) * Bc + bl) * UB + uu] = a[i][r * 4 + j];
+                                for (int j = 0; j < 4; ++j) {
+                                    const int k = k0 + j;
+                                    const int dst = k / UB, uu = k - dst * UB;
+                                    outbase[(((size_t)dst * nub + ub) * Bh + rowl) * UB + uu] = a[i][r * 4 + j];
+                                }
                             }
                         }
                     }
                 }
-            }
-            __syncthreads();
-            if (tid == 0) {
-                __threadfence();
-                red_release_add_u32(ctr, 1u);
+                __syncwarp();
+                if (lane == 0) {
+                    __threadfence();
+                    red_release_add_u32(ctr + hf, 1u);
+                }
             }
         }
     }
@@ -468,16 +482,17 @@ __global__ void lstm_cell_bwd_kernel(const float* __restrict__ gates, const floa
 
 // ------------------------------------------------------------------------------------------
 struct Plan {
-    int UB, Bc, nub, nbg, ctas;
+    int UB, Bc, nub, nbg, ctas, NH;
     size_t smem_fwd, smem_bwd, pack_bytes, xbuf_fwd_bytes, xbuf_bwd_bytes;
 };
 
+static int halves_for(int Bc) { return (Bc % 8 == 0) ? 2 : 1; }
 static size_t smem_fwd_bytes(int H, int UB, int Bc) {
-    return (size_t)H * UB * 16 + (size_t)H * (Bc / 4) * 16 + 16 * LSTM_HALF * 4 + LSTM_NCHUNK * 8 + 128;
+    return (size_t)H * UB * 16 + (size_t)H * Bc * 4 + (2 * LSTM_NCHUNK + 2) * 8 + 128;
 }
 static size_t smem_bwd_bytes(int H, int UB, int Bc) {
-    return (size_t)4 * UB * H * 4 + (size_t)Bc * H * 4 + (size_t)4 * UB * Bc * 4 + 4 * LSTM_HALF * 4 +
-           LSTM_NCHUNK * 8 + 128;
+    const int Bh = Bc / halves_for(Bc);
+    return (size_t)4 * UB * H * 4 + (size_t)Bc * H * 4 + (size_t)2 * 4 * UB * Bh * 4 + (2 * LSTM_NCHUNK + 2) * 8 + 128;
 }
 
 static int make_plan(int B, int H, int ndir, Plan* out) {
@@ -489,8 +504,8 @@ static int make_plan(int B, int H, int ndir, Plan* out) {
     for (int UB = 1; UB <= H; ++UB) {
         if (H % UB) continue;
         for (int Bc = 4; Bc <= 64; Bc += 4) {
-            const int NP = UB * (Bc / 4);
-            if (NP > LSTM_HALF) continue;
+            const int NH = halves_for(Bc);
+            if (UB * (Bc / NH / 4) > LSTM_MAX_TILES) continue;   // register tiles per half
             const int nbg = (B + Bc - 1) / Bc;
             const int nub = H / UB;
             const int ctas = ndir * nbg * nub;
@@ -498,13 +513,14 @@ static int make_plan(int B, int H, int ndir, Plan* out) {
             const size_t sf = smem_fwd_bytes(H, UB, Bc), sb = smem_bwd_bytes(H, UB, Bc);
             if (sf > smem_cap || sb > smem_cap) continue;
             // bulk copies need 16-B multiples
-            if (((size_t)(H / LSTM_NCHUNK) * (Bc / 4) * 16) % 16) continue;
-            if (((size_t)Bc * UB * 4) % 16) continue;
+            if (((size_t)(H / LSTM_NCHUNK) * (Bc / NH) * 4) % 16) continue;
+            if (((size_t)(Bc / NH) * UB * 4) % 16) continue;
+            if ((long long)ndir * nbg * NH * 4 > LSTM_COUNTER_BYTES - 64) continue;
             // cost: per-CTA FMA work per step; tie-break on the state tile pulled per step
             const long long cost = (long long)UB * Bc * 1000 + Bc;
             if (best_cost < 0 || cost < best_cost) {
                 best_cost = cost;
-                best.UB = UB; best.Bc = Bc; best.nub = nub; best.nbg = nbg; best.ctas = ctas;
+                best.UB = UB; best.Bc = Bc; best.nub = nub; best.nbg = nbg; best.ctas = ctas; best.NH = NH;
                 best.smem_fwd = sf; best.smem_bwd = sb;
             }
         }
@@ -528,7 +544,7 @@ extern "C" size_t b200asr_bilstm_workspace_bytes(int B, int T, int H, int ndir) 
     Plan pl;
     if (make_plan(B, H, ndir, &pl) != 0) return 0;
     const size_t x = pl.xbuf_fwd_bytes > pl.xbuf_bwd_bytes ? pl.xbuf_fwd_bytes : pl.xbuf_bwd_bytes;
-    return align_up(pl.pack_bytes, 256) + align_up(x, 256) + 256 /*counters + err flag*/;
+    return align_up(pl.pack_bytes, 256) + align_up(x, 256) + LSTM_COUNTER_BYTES /*counters + err flag*/;
 }
 
 extern "C" int b200asr_bilstm_plan(int B, int H, int ndir, int* unit_block, int* batch_block, int* n_ctas) {
@@ -557,9 +573,9 @@ static int bilstm_run(bool bwd, float* gates, const float* w_hh, float* cstate, 
     const size_t xbytes = pl.xbuf_fwd_bytes > pl.xbuf_bwd_bytes ? pl.xbuf_fwd_bytes : pl.xbuf_bwd_bytes;
     float* xbuf = reinterpret_cast<float*>(ws + xoff);
     unsigned* counters = reinterpret_cast<unsigned*>(ws + xoff + align_up(xbytes, 256));
-    int* err_flag = reinterpret_cast<int*>(counters + 32);
+    int* err_flag = reinterpret_cast<int*>(counters + (LSTM_COUNTER_BYTES / 4 - 4));
 
-    B200_CUDA(cudaMemsetAsync(counters, 0, 256, stream));
+    B200_CUDA(cudaMemsetAsync(counters, 0, LSTM_COUNTER_BYTES, stream));
     {
         const long long n = (long long)ndir * 4 * H * H;
         int blocks = (int)((n + 255) / 256);
@@ -570,7 +586,7 @@ static int bilstm_run(bool bwd, float* gates, const float* w_hh, float* cstate, 
     LstmParams p;
     p.gates = gates; p.whh = packed; p.cst = cstate; p.out = out_or_dout; p.xbuf = xbuf; p.counters = counters;
     p.err_flag = err_flag; p.B = B; p.T = T; p.H = H; p.ndir = ndir; p.UB = pl.UB; p.Bc = pl.Bc; p.nub = pl.nub;
-    p.nbg = pl.nbg;
+    p.nbg = pl.nbg; p.NH = pl.NH;
     const void* fn = bwd ? (const void*)bilstm_bwd_kernel : (const void*)bilstm_fwd_kernel;
     const size_t smem = bwd ? pl.smem_bwd : pl.smem_fwd;
     B200_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
