@@ -2,17 +2,18 @@
 //
 // Decomposition (same for fwd and bwd): one CTA per (direction, batch-group, unit-block). A CTA owns UB hidden units
 // (= 4*UB gate columns) for Bc batch rows and keeps its slice of W_hh resident in shared memory for all T steps.
-// The Bc rows are processed as NH = 2 independent halves that are INTERLEAVED in time: while the state exchange of
-// one half is in flight, the FMA pipes work on the other half, so the cross-SM latency is hidden.
+// The Bc rows are processed as NH = 2 independent halves by two thread GROUPS of 128 threads that run their own
+// step loops and drift out of phase: while one group waits for its state exchange, the FMA pipes work for the other,
+// so the cross-SM latency is hidden behind compute.
 //
-//   warps 0-7  compute: 64 register tiles (4 gates x 4 rows) per half; the K dimension of a tile is split over 4
-//              lanes (one K-chunk each, matching the 4 bulk-copy chunks) and reduced with two warp shuffles, after
-//              which each of the 4 lanes finishes the pointwise cell update of one row of the tile.
-//   warp 8     producer: waits on the group's release/acquire counter, then pulls the [H,Bh] state block (fwd) or
-//              the [nub,Bh,UB] inbox of partial products (bwd) from L2 with 1-D bulk async copies (TMA) tracked
-//              by per-chunk "full" mbarriers; "empty" mbarriers hand the buffer back.
-// There is no CTA-wide or grid-wide barrier in the forward step loop; the backward has one named barrier among the
-// compute warps per half-step (the dG tile feeds all warps' GEMM tiles).
+//   group g (4 warps): 64 register tiles (4 gates x 4 rows), K split over the two warp pairs (each waits only for
+//              its own two bulk-copy chunks), software-pipelined LDS->FMA loop, partner rows exchanged through
+//              shared memory, then every thread finishes the pointwise cell update of two rows.
+//   control warp g (1 lane): waits on the group's "done" mbarrier, issues ONE fence + release for the whole group
+//              (off the compute warps' critical path), spins on the peers' counter, then pulls the next [H,Bh] state
+//              block (fwd) / [nub,Bh,UB] inbox of partial products (bwd) from L2 with 1-D bulk async copies (TMA)
+//              that complete on per-chunk "full" mbarriers.
+// There is no CTA-wide or grid-wide barrier in the step loops, only 128-thread named barriers inside a group.
 //
 //   fwd step : gates[b, 4UB] = Gx[b,t] + h_{t-1}[b,:] . Wslice^T ; pointwise ; publish h_t slice
 //   bwd step : dh = dOut[b,t] + sum_src partial_src[b, my units] ; pointwise -> dG[b,4UB] ;
@@ -28,9 +29,8 @@
 
 namespace b200asr {
 
-constexpr int LSTM_CWARPS = 8;                      // compute warps
-constexpr int LSTM_CTHREADS = LSTM_CWARPS * 32;     // 256
-constexpr int LSTM_THREADS = LSTM_CTHREADS + 32;    // + producer warp
+constexpr int LSTM_GTHREADS = 128;                  // compute threads per group (one group per batch half)
+constexpr int LSTM_THREADS = 2 * LSTM_GTHREADS + 64;  // two groups + two control warps
 constexpr int LSTM_NCHUNK = 4;
 constexpr int LSTM_MAX_TILES = 64;                  // register tiles per half
 constexpr int LSTM_COUNTER_BYTES = 4096;
@@ -104,6 +104,25 @@ __global__ void lstm_pack_kernel(const float* __restrict__ w, float* __restrict_
     acc[3][0] = fmaf(hv.w, wv.x, acc[3][0]); acc[3][1] = fmaf(hv.w, wv.y, acc[3][1]);                 \
     acc[3][2] = fmaf(hv.w, wv.z, acc[3][2]); acc[3][3] = fmaf(hv.w, wv.w, acc[3][3]);
 
+// Control lane of one group: publishes the group's step (one fence + one release per CTA-group and step, off the
+// compute warps' critical path), waits for the peers, then pulls the next step's block into shared memory.
+__device__ __forceinline__ void control_loop(const LstmParams& p, int T, unsigned nub, uint64_t* done, uint64_t* full,
+                                             unsigned* ctr, const float* src_even, const float* src_odd, float* dst,
+                                             const uint32_t* chunk_off, const uint32_t* chunk_bytes) {
+    for (int step = 0; step + 1 < T; ++step) {
+        mbar_wait(done, (uint32_t)(step & 1));          // every compute warp of the group finished `step`
+        __threadfence();                                // their global stores (made visible to me through the
+        red_release_add_u32(ctr, 1u);                   // mbarrier) are ordered before the release
+        spin_until(ctr, (unsigned)(step + 1) * nub, p.err_flag);
+        fence_proxy_async();
+        const float* src = (step & 1) ? src_odd : src_even;
+        for (int c = 0; c < LSTM_NCHUNK; ++c) {
+            mbar_expect_tx(&full[c], chunk_bytes[c]);
+            if (chunk_bytes[c]) bulk_g2s(dst + chunk_off[c], src + chunk_off[c], chunk_bytes[c], &full[c]);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(LSTM_THREADS, 1) bilstm_fwd_kernel(LstmParams p) {
     extern __shared__ __align__(128) unsigned char s_raw[];
@@ -113,8 +132,9 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) bilstm_fwd_kernel(LstmParams 
     const int KC = H / LSTM_NCHUNK;
     float4* Ws = reinterpret_cast<float4*>(s_raw);                               // [H][UB] float4 (4 gates)
     float* hs = reinterpret_cast<float*>(Ws + (size_t)H * UB);                   // [NH][H*Bh]
-    uint64_t* full = reinterpret_cast<uint64_t*>(hs + (size_t)H * Bc);           // [NH][NCHUNK]
-    uint64_t* empty = full + 2 * LSTM_NCHUNK;                                    // [NH]
+    float* red = hs + (size_t)H * Bc;                                            // [2][8][128]
+    uint64_t* full = reinterpret_cast<uint64_t*>(red + 2 * 8 * LSTM_GTHREADS);   // [2][NCHUNK]
+    uint64_t* done = full + 2 * LSTM_NCHUNK;                                     // [2]
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -129,128 +149,135 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) bilstm_fwd_kernel(LstmParams 
     }
     if (tid == 0) {
         for (int i = 0; i < 2 * LSTM_NCHUNK; ++i) mbar_init(&full[i], 1);
-        for (int i = 0; i < 2; ++i) mbar_init(&empty[i], LSTM_CWARPS);
+        for (int i = 0; i < 2; ++i) mbar_init(&done[i], LSTM_GTHREADS / 32);
         mbar_fence_init();
     }
     __syncthreads();
 
     const size_t half_elems = (size_t)H * Bh;                                    // floats per state block
     float* xb = p.xbuf + ((size_t)dir * p.nbg + bg) * NH * 2 * half_elems;       // [NH][2][H*Bh]
-    unsigned* ctr = p.counters + ((size_t)dir * p.nbg + bg) * NH;
-    const uint32_t chunk_bytes = (uint32_t)((size_t)KC * Bh * sizeof(float));
-    const unsigned per_step = (unsigned)p.nub * LSTM_CWARPS;                     // releases per step per half
+    unsigned* ctr0 = p.counters + ((size_t)dir * p.nbg + bg) * NH;
 
-    if (warp == LSTM_CWARPS) {
-        // ===== producer warp =====
-        if (lane == 0) {
-            for (int step = 1; step < T; ++step) {
-                for (int hf = 0; hf < NH; ++hf) {
-                    spin_until(ctr + hf, (unsigned)step * per_step, p.err_flag);
-                    if (step >= 2) mbar_wait(&empty[hf], (uint32_t)(step & 1));   // fill #(step-1) needs release #(step-2)
-                    fence_proxy_async();
-                    const float* src = xb + ((size_t)hf * 2 + ((step - 1) & 1)) * half_elems;
-                    float* dst = hs + (size_t)hf * half_elems;
-                    for (int c = 0; c < LSTM_NCHUNK; ++c) {
-                        mbar_expect_tx(&full[hf * LSTM_NCHUNK + c], chunk_bytes);
-                        bulk_g2s(dst + (size_t)c * KC * Bh, src + (size_t)c * KC * Bh, chunk_bytes,
-                                 &full[hf * LSTM_NCHUNK + c]);
-                    }
-                }
+    if (warp >= 2 * (LSTM_GTHREADS / 32)) {
+        // ===== control warps: warp 8 -> group 0, warp 9 -> group 1 =====
+        const int g = warp - 2 * (LSTM_GTHREADS / 32);
+        if (lane == 0 && g < NH) {
+            uint32_t off[LSTM_NCHUNK], bytes[LSTM_NCHUNK];
+            for (int c = 0; c < LSTM_NCHUNK; ++c) {
+                off[c] = (uint32_t)((size_t)c * KC * Bh);
+                bytes[c] = (uint32_t)((size_t)KC * Bh * sizeof(float));
             }
+            control_loop(p, T, (unsigned)p.nub, &done[g], &full[g * LSTM_NCHUNK], ctr0 + g,
+                         xb + ((size_t)g * 2 + 0) * half_elems, xb + ((size_t)g * 2 + 1) * half_elems,
+                         hs + (size_t)g * half_elems, off, bytes);
         }
         return;
     }
 
-    // ===== compute warps =====
-    const int kq = lane >> 3;                 // K chunk of this lane
-    const int tl = lane & 7;
-    const int tile = warp * 8 + tl;
+    // ===== compute groups: threads [0,128) -> batch half 0, [128,256) -> batch half 1 =====
+    const int g = tid / LSTM_GTHREADS;
+    if (g >= NH) return;
+    const int gt = tid - g * LSTM_GTHREADS;
+    const int kh = gt >> 6;                   // K half of this thread
+    const int pidx = gt & 63;
     const int NT = UB * NBQ;
-    const bool has_tile = tile < NT;
-    const int u = has_tile ? tile % UB : 0;
-    const int bq = has_tile ? tile / UB : 0;
+    const bool has_tile = pidx < NT;
+    const int u = has_tile ? pidx % UB : 0;
+    const int bq = has_tile ? pidx / UB : 0;
     const int ug = ub * UB + u;
+    const int bl0 = bq * 4 + 2 * kh;          // my two rows within the half: bl0, bl0+1
+    const int bglob0 = bg * Bc + g * Bh + bl0;
+    float* redg = red + (size_t)g * 8 * LSTM_GTHREADS;
+    const float* hsg = hs + (size_t)g * half_elems;
     float c_reg[2] = {0.f, 0.f};
 
     for (int step = 0; step < T; ++step) {
         const int tt = dir ? (T - 1 - step) : step;
+        float4 gx[2];
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-            if (hf >= NH) break;
-            const int bl = bq * 4 + kq;                                // my row within the half
-            const int b = bg * Bc + hf * Bh + bl;
-            const bool valid = has_tile && b < p.B;
-            const size_t row = ((size_t)dir * p.B + (valid ? b : 0)) * T + tt;
-            float4 gx = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (valid) gx = *reinterpret_cast<const float4*>(p.gates + (row * H + ug) * 4);
+        for (int i = 0; i < 2; ++i) {
+            gx[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int b = bglob0 + i;
+            if (has_tile && b < p.B)
+                gx[i] = *reinterpret_cast<const float4*>(p.gates + ((((size_t)dir * p.B + b) * T + tt) * H + ug) * 4);
+        }
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[i][q] = 0.f;
 
-            float acc[4][4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int g = 0; g < 4; ++g) acc[i][g] = 0.f;
-
-            if (step > 0) {
-                mbar_wait(&full[hf * LSTM_NCHUNK + kq], (uint32_t)((step - 1) & 1));
-                const float4* hp = reinterpret_cast<const float4*>(hs + (size_t)hf * half_elems + (size_t)kq * KC * Bh) + bq;
-                const float4* wp = Ws + (size_t)kq * KC * UB + u;
-                // software pipelined: the loads of k+1 are in flight while the 16 FMAs of k issue
-                float4 h0 = hp[0], w0 = wp[0];
+        if (step > 0) {
+            if (has_tile) {
+#pragma unroll 1
+                for (int cc = 0; cc < LSTM_NCHUNK / 2; ++cc) {
+                    const int c = kh * (LSTM_NCHUNK / 2) + cc;
+                    mbar_wait(&full[g * LSTM_NCHUNK + c], (uint32_t)((step - 1) & 1));
+                    const float4* hp = reinterpret_cast<const float4*>(hsg + (size_t)c * KC * Bh) + bq;
+                    const float4* wp = Ws + (size_t)c * KC * UB + u;
+                    // software pipelined: the loads of k+1 are in flight while the 16 FMAs of k issue
+                    float4 h0 = hp[0], w0 = wp[0];
 #pragma unroll 4
-                for (int kk = 1; kk < KC; ++kk) {
-                    const float4 h1 = hp[(size_t)kk * NBQ];
-                    const float4 w1 = wp[(size_t)kk * UB];
-                    FMA16(h0, w0)
-                    h0 = h1;
-                    w0 = w1;
-                }
-                FMA16(h0, w0)
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[hf]);
-                // reduce the 4 K-chunks (lanes l, l^8, l^16, l^24)
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        float v = acc[i][g];
-                        v += __shfl_xor_sync(0xffffffffu, v, 8);
-                        v += __shfl_xor_sync(0xffffffffu, v, 16);
-                        acc[i][g] = v;
+                    for (int kk = 1; kk < KC; ++kk) {
+                        const float4 h1 = hp[(size_t)kk * NBQ];
+                        const float4 w1 = wp[(size_t)kk * UB];
+                        FMA16(h0, w0)
+                        h0 = h1;
+                        w0 = w1;
                     }
+                    FMA16(h0, w0)
+                }
             }
-            // lane kq finishes row kq of the tile
-            float a0, a1, a2, a3;
-            if (kq == 0) { a0 = acc[0][0]; a1 = acc[0][1]; a2 = acc[0][2]; a3 = acc[0][3]; }
-            else if (kq == 1) { a0 = acc[1][0]; a1 = acc[1][1]; a2 = acc[1][2]; a3 = acc[1][3]; }
-            else if (kq == 2) { a0 = acc[2][0]; a1 = acc[2][1]; a2 = acc[2][2]; a3 = acc[2][3]; }
-            else { a0 = acc[3][0]; a1 = acc[3][1]; a2 = acc[3][2]; a3 = acc[3][3]; }
-            float hval = 0.f;
-            if (valid) {
-                const float ig = sigmoidf_(gx.x + a0);
-                const float fg = sigmoidf_(gx.y + a1);
-                const float gg = tanhf(gx.z + a2);
-                const float og = sigmoidf_(gx.w + a3);
-                const float c = fmaf(fg, c_reg[hf], ig * gg);
-                c_reg[hf] = c;
-                hval = og * tanhf(c);
+            // exchange the two rows the partner K-half finishes
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    redg[(i * 4 + q) * LSTM_GTHREADS + gt] = kh ? acc[i][q] : acc[2 + i][q];
+            named_bar_sync(1 + g, LSTM_GTHREADS);
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float o = redg[(i * 4 + q) * LSTM_GTHREADS + (gt ^ 64)];
+                    if (kh) acc[2 + i][q] += o; else acc[i][q] += o;
+                }
+        }
+        float hq[2] = {0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int b = bglob0 + i;
+            if (has_tile && b < p.B) {
+                const float a0 = kh ? acc[2 + i][0] : acc[i][0];
+                const float a1 = kh ? acc[2 + i][1] : acc[i][1];
+                const float a2 = kh ? acc[2 + i][2] : acc[i][2];
+                const float a3 = kh ? acc[2 + i][3] : acc[i][3];
+                const float ig = sigmoidf_(gx[i].x + a0);
+                const float fg = sigmoidf_(gx[i].y + a1);
+                const float gg = tanhf(gx[i].z + a2);
+                const float og = sigmoidf_(gx[i].w + a3);
+                const float c = fmaf(fg, c_reg[i], ig * gg);
+                c_reg[i] = c;
+                const float h = og * tanhf(c);
+                hq[i] = h;
+                const size_t row = ((size_t)dir * p.B + b) * T + tt;
                 *reinterpret_cast<float4*>(p.gates + (row * H + ug) * 4) = make_float4(ig, fg, gg, og);
                 p.cst[row * H + ug] = c;
-                p.out[((size_t)b * T + tt) * (p.ndir * H) + (size_t)dir * H + ug] = hval;
+                p.out[((size_t)b * T + tt) * (p.ndir * H) + (size_t)dir * H + ug] = h;
             }
-            if (step + 1 < T) {
-                if (has_tile) xb[((size_t)hf * 2 + (step & 1)) * half_elems + (size_t)ug * Bh + bl] = hval;
-                __syncwarp();
-                if (lane == 0) {
-                    __threadfence();
-                    red_release_add_u32(ctr + hf, 1u);
-                }
-            }
+        }
+        if (step + 1 < T) {
+            if (has_tile)
+                *reinterpret_cast<float2*>(xb + ((size_t)g * 2 + (step & 1)) * half_elems + (size_t)ug * Bh + bl0) =
+                    make_float2(hq[0], hq[1]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&done[g]);
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// Backward. Shared memory: Wr[4UB][H] | inbox[NH][nub*Bh*UB] | dGs[2][4UB*Bh] | barriers
+// Backward. Shared memory: Wr[4UB][H] | inbox[NH][nub*Bh*UB] | dGs[NH][4UB*Bh] | red[2][2][128] | barriers
 __global__ void __launch_bounds__(LSTM_THREADS, 1) bilstm_bwd_kernel(LstmParams p) {
     extern __shared__ __align__(128) unsigned char s_raw[];
     const int H = p.H, UB = p.UB, Bc = p.Bc, T = p.T, nub = p.nub, NH = p.NH;
@@ -258,9 +285,10 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) bilstm_bwd_kernel(LstmParams 
     const int NBQ = Bh >> 2;
     float* Wr = reinterpret_cast<float*>(s_raw);                 // [4UB][H]
     float* inbox = Wr + (size_t)4 * UB * H;                      // [NH][nub*Bh*UB]  (= Bc*H floats)
-    float* dGs = inbox + (size_t)Bc * H;                         // [2][4UB*Bh]
-    uint64_t* full = reinterpret_cast<uint64_t*>(dGs + (size_t)2 * 4 * UB * Bh);
-    uint64_t* empty = full + 2 * LSTM_NCHUNK;
+    float* dGs = inbox + (size_t)Bc * H;                         // [NH][4UB*Bh]
+    float* red = dGs + (size_t)4 * UB * Bc;                      // [2][2][128]
+    uint64_t* full = reinterpret_cast<uint64_t*>(red + 2 * 2 * LSTM_GTHREADS);
+    uint64_t* done = full + 2 * LSTM_NCHUNK;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -276,169 +304,175 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) bilstm_bwd_kernel(LstmParams 
     }
     if (tid == 0) {
         for (int i = 0; i < 2 * LSTM_NCHUNK; ++i) mbar_init(&full[i], 1);
-        for (int i = 0; i < 2; ++i) mbar_init(&empty[i], LSTM_CWARPS);
+        for (int i = 0; i < 2; ++i) mbar_init(&done[i], LSTM_GTHREADS / 32);
         mbar_fence_init();
     }
     __syncthreads();
 
     // global inbox layout per (dir, bg, half, parity): [dst nub][src nub][Bh][UB]
-    const size_t inbox_elems = (size_t)Bh * H;                   // floats one destination receives per half-step
+    const size_t inbox_elems = (size_t)Bh * H;                   // floats one destination receives per step
     float* xb = p.xbuf + ((size_t)dir * p.nbg + bg) * NH * 2 * (size_t)nub * inbox_elems;
-    unsigned* ctr = p.counters + ((size_t)dir * p.nbg + bg) * NH;
+    unsigned* ctr0 = p.counters + ((size_t)dir * p.nbg + bg) * NH;
     const int SC = (nub + LSTM_NCHUNK - 1) / LSTM_NCHUNK;        // sources per chunk
-    const unsigned per_step = (unsigned)nub * LSTM_CWARPS;
 
-    if (warp == LSTM_CWARPS) {
-        if (lane == 0) {
-            for (int step = 1; step < T; ++step) {
-                for (int hf = 0; hf < NH; ++hf) {
-                    spin_until(ctr + hf, (unsigned)step * per_step, p.err_flag);
-                    if (step >= 2) mbar_wait(&empty[hf], (uint32_t)(step & 1));
-                    fence_proxy_async();
-                    const float* src = xb + (((size_t)hf * 2 + ((step - 1) & 1)) * nub + ub) * inbox_elems;
-                    float* dst = inbox + (size_t)hf * inbox_elems;
-                    for (int c = 0; c < LSTM_NCHUNK; ++c) {
-                        const int s0 = c * SC;
-                        const int s1 = min(nub, s0 + SC);
-                        const uint32_t bytes = (s1 > s0) ? (uint32_t)((size_t)(s1 - s0) * Bh * UB * sizeof(float)) : 0u;
-                        mbar_expect_tx(&full[hf * LSTM_NCHUNK + c], bytes);
-                        if (bytes)
-                            bulk_g2s(dst + (size_t)s0 * Bh * UB, src + (size_t)s0 * Bh * UB, bytes,
-                                     &full[hf * LSTM_NCHUNK + c]);
-                    }
-                }
+    if (warp >= 2 * (LSTM_GTHREADS / 32)) {
+        const int g = warp - 2 * (LSTM_GTHREADS / 32);
+        if (lane == 0 && g < NH) {
+            uint32_t off[LSTM_NCHUNK], bytes[LSTM_NCHUNK];
+            for (int c = 0; c < LSTM_NCHUNK; ++c) {
+                const int s0 = min(nub, c * SC), s1 = min(nub, s0 + SC);
+                off[c] = (uint32_t)((size_t)s0 * Bh * UB);
+                bytes[c] = (uint32_t)((size_t)(s1 - s0) * Bh * UB * sizeof(float));
             }
+            control_loop(p, T, (unsigned)nub, &done[g], &full[g * LSTM_NCHUNK], ctr0 + g,
+                         xb + (((size_t)g * 2 + 0) * nub + ub) * inbox_elems,
+                         xb + (((size_t)g * 2 + 1) * nub + ub) * inbox_elems, inbox + (size_t)g * inbox_elems, off,
+                         bytes);
         }
         return;
     }
 
-    const int kq = lane >> 3;
-    const int tl = lane & 7;
-    const int tile = warp * 8 + tl;
+    const int g = tid / LSTM_GTHREADS;
+    if (g >= NH) return;
+    const int gt = tid - g * LSTM_GTHREADS;
+    const int kh = gt >> 6;
+    const int pidx = gt & 63;
     const int NT = UB * NBQ;
-    const bool has_tile = tile < NT;
-    const int u = has_tile ? tile % UB : 0;
-    const int bq = has_tile ? tile / UB : 0;
+    const bool has_tile = pidx < NT;
+    const int u = has_tile ? pidx % UB : 0;
+    const int bq = has_tile ? pidx / UB : 0;
     const int ug = ub * UB + u;
+    const int bl0 = bq * 4 + 2 * kh;
+    const int bglob0 = bg * Bc + g * Bh + bl0;
     const bool vec_ok = (UB % 4) == 0;
+    float* redg = red + (size_t)g * 2 * LSTM_GTHREADS;
+    const float* inb = inbox + (size_t)g * inbox_elems;
+    float* dgs = dGs + (size_t)g * 4 * UB * Bh;
     float dc_reg[2] = {0.f, 0.f};
 
     for (int step = 0; step < T; ++step) {
         const int fstep = T - 1 - step;                    // forward step index being differentiated
         const int tt = dir ? (T - 1 - fstep) : fstep;      // its time index
         const int tt_prev = dir ? tt + 1 : tt - 1;         // time index of the previous forward step
+        float4 gtv[2];
+        float ct[2], cp[2], dh[2];
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-            if (hf >= NH) break;
-            const int ps = (step * NH + hf) & 1;           // dGs buffer of this half-step
-            const int bl = bq * 4 + kq;
-            const int b = bg * Bc + hf * Bh + bl;
-            const bool valid = has_tile && b < p.B;
-            const size_t row = ((size_t)dir * p.B + (valid ? b : 0)) * T + tt;
-            float4 gt = make_float4(0.f, 0.f, 0.f, 0.f);
-            float ct = 0.f, cp = 0.f, dh = 0.f;
-            if (valid) {
-                gt = *reinterpret_cast<const float4*>(p.gates + (row * H + ug) * 4);
-                ct = p.cst[row * H + ug];
-                if (fstep > 0) cp = p.cst[(((size_t)dir * p.B + b) * T + tt_prev) * H + ug];
-                dh = p.out[((size_t)b * T + tt) * (p.ndir * H) + (size_t)dir * H + ug];
+        for (int i = 0; i < 2; ++i) {
+            gtv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            ct[i] = cp[i] = dh[i] = 0.f;
+            const int b = bglob0 + i;
+            if (has_tile && b < p.B) {
+                const size_t row = ((size_t)dir * p.B + b) * T + tt;
+                gtv[i] = *reinterpret_cast<const float4*>(p.gates + (row * H + ug) * 4);
+                ct[i] = p.cst[row * H + ug];
+                if (fstep > 0) cp[i] = p.cst[(((size_t)dir * p.B + b) * T + tt_prev) * H + ug];
+                dh[i] = p.out[((size_t)b * T + tt) * (p.ndir * H) + (size_t)dir * H + ug];
             }
-            if (step > 0) {
-                float part = 0.f;
-                const float* ib = inbox + (size_t)hf * inbox_elems + (size_t)bl * UB + u;
-                for (int c = 0; c < LSTM_NCHUNK; ++c) {
-                    mbar_wait(&full[hf * LSTM_NCHUNK + c], (uint32_t)((step - 1) & 1));
-                    const int s0 = c * SC;
-                    const int s1 = min(nub, s0 + SC);
-                    if (has_tile)
-                        for (int s = s0; s < s1; ++s) part += ib[(size_t)s * Bh * UB];
+        }
+        if (step > 0) {
+            // sum the partial products of my K-half of the sources for all 4 rows of the tile
+            float part[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+            for (int cc = 0; cc < LSTM_NCHUNK / 2; ++cc) {
+                const int c = kh * (LSTM_NCHUNK / 2) + cc;
+                mbar_wait(&full[g * LSTM_NCHUNK + c], (uint32_t)((step - 1) & 1));
+                const int s0 = min(nub, c * SC), s1 = min(nub, s0 + SC);
+                if (has_tile) {
+                    for (int s = s0; s < s1; ++s) {
+                        const float* ib = inb + ((size_t)s * Bh + bq * 4) * UB + u;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) part[i] += ib[i * UB];
+                    }
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[hf]);
-                dh += part;
             }
-            // pointwise backward of the cell
+            redg[0 * LSTM_GTHREADS + gt] = kh ? part[0] : part[2];
+            redg[1 * LSTM_GTHREADS + gt] = kh ? part[1] : part[3];
+            named_bar_sync(1 + g, LSTM_GTHREADS);
+            dh[0] += (kh ? part[2] : part[0]) + redg[0 * LSTM_GTHREADS + (gt ^ 64)];
+            dh[1] += (kh ? part[3] : part[1]) + redg[1 * LSTM_GTHREADS + (gt ^ 64)];
+        }
+        // pointwise backward of the cell for my two rows
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int b = bglob0 + i;
             float4 dg = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (valid) {
-                const float ig = gt.x, fg = gt.y, gg = gt.z, og = gt.w;
-                const float tc = tanhf(ct);
-                const float dc = dc_reg[hf] + dh * og * (1.f - tc * tc);
+            if (has_tile && b < p.B) {
+                const float ig = gtv[i].x, fg = gtv[i].y, gg = gtv[i].z, og = gtv[i].w;
+                const float tc = tanhf(ct[i]);
+                const float dc = dc_reg[i] + dh[i] * og * (1.f - tc * tc);
                 dg.x = dc * gg * ig * (1.f - ig);
-                dg.y = dc * cp * fg * (1.f - fg);
+                dg.y = dc * cp[i] * fg * (1.f - fg);
                 dg.z = dc * ig * (1.f - gg * gg);
-                dg.w = dh * tc * og * (1.f - og);
-                dc_reg[hf] = dc * fg;
+                dg.w = dh[i] * tc * og * (1.f - og);
+                dc_reg[i] = dc * fg;
+                const size_t row = ((size_t)dir * p.B + b) * T + tt;
                 *reinterpret_cast<float4*>(p.gates + (row * H + ug) * 4) = dg;
             }
             if (has_tile) {
-                float* d = dGs + (size_t)ps * 4 * UB * Bh + (size_t)(u * 4) * Bh + bl;
+                float* d = dgs + (size_t)(u * 4) * Bh + bl0 + i;
                 d[0] = dg.x; d[Bh] = dg.y; d[2 * Bh] = dg.z; d[3 * Bh] = dg.w;
             }
-            named_bar_sync(1, LSTM_CTHREADS);              // the dG tile of this half-step is complete
-            if (step + 1 < T) {
-                // partial[b][k] = sum_c dGs[c][b] * Wr[c][k]; thread tiles of 4 rows x (2 strided float4 of k)
-                const float* dgs = dGs + (size_t)ps * 4 * UB * Bh;
-                const int NKQ = H / 8;
-                const int ntiles = NKQ * NBQ;
-                float* outbase = xb + ((size_t)hf * 2 + (step & 1)) * nub * inbox_elems;
-                for (int t2 = tid; t2 < ntiles; t2 += LSTM_CTHREADS) {
-                    const int kq2 = t2 % NKQ;
-                    const int bq2 = t2 / NKQ;
-                    float a[4][8];
+        }
+        named_bar_sync(3 + g, LSTM_GTHREADS);              // the dG tile of this step is complete
+        if (step + 1 < T) {
+            // partial[b][k] = sum_c dGs[c][b] * Wr[c][k]; thread tiles of 4 rows x (2 strided float4 of k)
+            const int NKQ = H / 8;
+            const int ntiles = NKQ * NBQ;
+            float* outbase = xb + ((size_t)g * 2 + (step & 1)) * nub * inbox_elems;
+            for (int t2 = gt; t2 < ntiles; t2 += LSTM_GTHREADS) {
+                const int kq2 = t2 % NKQ;
+                const int bq2 = t2 / NKQ;
+                float a[4][8];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
+                for (int i = 0; i < 4; ++i)
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) a[i][j] = 0.f;
-                    const int C = 4 * UB;
-                    const float* wbase = Wr + kq2 * 4;
-                    float4 d4 = *reinterpret_cast<const float4*>(dgs + bq2 * 4);
-                    float4 wa = *reinterpret_cast<const float4*>(wbase);
-                    float4 wb = *reinterpret_cast<const float4*>(wbase + (H >> 1));
+                    for (int j = 0; j < 8; ++j) a[i][j] = 0.f;
+                const int C = 4 * UB;
+                const float* wbase = Wr + kq2 * 4;
+                float4 d4 = *reinterpret_cast<const float4*>(dgs + bq2 * 4);
+                float4 wa = *reinterpret_cast<const float4*>(wbase);
+                float4 wb = *reinterpret_cast<const float4*>(wbase + (H >> 1));
 #pragma unroll 4
-                    for (int c = 0; c < C; ++c) {
-                        const int cn = (c + 1 < C) ? c + 1 : c;
-                        const float4 d4n = *reinterpret_cast<const float4*>(dgs + (size_t)cn * Bh + bq2 * 4);
-                        const float4 wan = *reinterpret_cast<const float4*>(wbase + (size_t)cn * H);
-                        const float4 wbn = *reinterpret_cast<const float4*>(wbase + (size_t)cn * H + (H >> 1));
-                        const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+                for (int c = 0; c < C; ++c) {
+                    const int cn = (c + 1 < C) ? c + 1 : c;
+                    const float4 d4n = *reinterpret_cast<const float4*>(dgs + (size_t)cn * Bh + bq2 * 4);
+                    const float4 wan = *reinterpret_cast<const float4*>(wbase + (size_t)cn * H);
+                    const float4 wbn = *reinterpret_cast<const float4*>(wbase + (size_t)cn * H + (H >> 1));
+                    const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            a[i][0] = fmaf(dv[i], wa.x, a[i][0]); a[i][1] = fmaf(dv[i], wa.y, a[i][1]);
-                            a[i][2] = fmaf(dv[i], wa.z, a[i][2]); a[i][3] = fmaf(dv[i], wa.w, a[i][3]);
-                            a[i][4] = fmaf(dv[i], wb.x, a[i][4]); a[i][5] = fmaf(dv[i], wb.y, a[i][5]);
-                            a[i][6] = fmaf(dv[i], wb.z, a[i][6]); a[i][7] = fmaf(dv[i], wb.w, a[i][7]);
-                        }
-                        d4 = d4n; wa = wan; wb = wbn;
+                    for (int i = 0; i < 4; ++i) {
+                        a[i][0] = fmaf(dv[i], wa.x, a[i][0]); a[i][1] = fmaf(dv[i], wa.y, a[i][1]);
+                        a[i][2] = fmaf(dv[i], wa.z, a[i][2]); a[i][3] = fmaf(dv[i], wa.w, a[i][3]);
+                        a[i][4] = fmaf(dv[i], wb.x, a[i][4]); a[i][5] = fmaf(dv[i], wb.y, a[i][5]);
+                        a[i][6] = fmaf(dv[i], wb.z, a[i][6]); a[i][7] = fmaf(dv[i], wb.w, a[i][7]);
                     }
-                    // scatter to the destination inboxes: element (dst, src=ub, row, u')
+                    d4 = d4n; wa = wan; wb = wbn;
+                }
+                // scatter to the destination inboxes: element (dst, src=ub, row, u')
 #pragma unroll
-                    for (int r = 0; r < 2; ++r) {
-                        const int k0 = r * (H >> 1) + kq2 * 4;
+                for (int r = 0; r < 2; ++r) {
+                    const int k0 = r * (H >> 1) + kq2 * 4;
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int rowl = bq2 * 4 + i;
-                            if (vec_ok) {
-                                const int dst = k0 / UB, uu = k0 - dst * UB;
-                                float* o = outbase + (((size_t)dst * nub + ub) * Bh + rowl) * UB + uu;
-                                *reinterpret_cast<float4*>(o) =
-                                    make_float4(a[i][r * 4], a[i][r * 4 + 1], a[i][r * 4 + 2], a[i][r * 4 + 3]);
-                            } else {
+                    for (int i = 0; i < 4; ++i) {
+                        const int rowl = bq2 * 4 + i;
+                        if (vec_ok) {
+                            const int dst = k0 / UB, uu = k0 - dst * UB;
+                            float* o = outbase + (((size_t)dst * nub + ub) * Bh + rowl) * UB + uu;
+                            *reinterpret_cast<float4*>(o) =
+                                make_float4(a[i][r * 4], a[i][r * 4 + 1], a[i][r * 4 + 2], a[i][r * 4 + 3]);
+                        } else {
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    const int k = k0 + j;
-                                    const int dst = k / UB, uu = k - dst * UB;
-                                    outbase[(((size_t)dst * nub + ub) * Bh + rowl) * UB + uu] = a[i][r * 4 + j];
-                                }
+                            for (int j = 0; j < 4; ++j) {
+                                const int k = k0 + j;
+                                const int dst = k / UB, uu = k - dst * UB;
+                                outbase[(((size_t)dst * nub + ub) * Bh + rowl) * UB + uu] = a[i][r * 4 + j];
                             }
                         }
                     }
                 }
-                __syncwarp();
-                if (lane == 0) {
-                    __threadfence();
-                    red_release_add_u32(ctr + hf, 1u);
-                }
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&done[g]);
         }
     }
 }
@@ -488,11 +522,11 @@ struct Plan {
 
 static int halves_for(int Bc) { return (Bc % 8 == 0) ? 2 : 1; }
 static size_t smem_fwd_bytes(int H, int UB, int Bc) {
-    return (size_t)H * UB * 16 + (size_t)H * Bc * 4 + (2 * LSTM_NCHUNK + 2) * 8 + 128;
+    return (size_t)H * UB * 16 + (size_t)H * Bc * 4 + 2 * 8 * LSTM_GTHREADS * 4 + (2 * LSTM_NCHUNK + 2) * 8 + 128;
 }
 static size_t smem_bwd_bytes(int H, int UB, int Bc) {
-    const int Bh = Bc / halves_for(Bc);
-    return (size_t)4 * UB * H * 4 + (size_t)Bc * H * 4 + (size_t)2 * 4 * UB * Bh * 4 + (2 * LSTM_NCHUNK + 2) * 8 + 128;
+    return (size_t)4 * UB * H * 4 + (size_t)Bc * H * 4 + (size_t)4 * UB * Bc * 4 + 2 * 2 * LSTM_GTHREADS * 4 +
+           (2 * LSTM_NCHUNK + 2) * 8 + 128;
 }
 
 static int make_plan(int B, int H, int ndir, Plan* out) {
