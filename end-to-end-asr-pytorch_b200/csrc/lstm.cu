@@ -6,14 +6,17 @@
 // step loops and drift out of phase: while one group waits for its state exchange, the FMA pipes work for the other,
 // so the cross-SM latency is hidden behind compute.
 //
-//   group g (4 warps): 64 register tiles (4 gates x 4 rows), K split over the two warp pairs (each waits only for
-//              its own two bulk-copy chunks), software-pipelined LDS->FMA loop, partner rows exchanged through
-//              shared memory, then every thread finishes the pointwise cell update of two rows.
+//   group g (4 warps): 32 register tiles of 4 gates x 8 rows (one W float4 feeds 32 FMAs - the loop is bound by
+//              shared-memory wavefronts otherwise); the K dimension of a tile is split over 4 lanes, one per
+//              bulk-copy chunk (a lane waits only for its own chunk; chunks are padded apart in shared memory so the 4
+//              lanes hit different banks), software-pipelined LDS->FMA loop, two warp shuffles reduce the K-chunks,
+//              then each of the 4 lanes finishes the pointwise cell update of two rows.
 //   control warp g (1 lane): waits on the group's "done" mbarrier, issues ONE fence + release for the whole group
 //              (off the compute warps' critical path), spins on the peers' counter, then pulls the next [H,Bh] state
 //              block (fwd) / [nub,Bh,UB] inbox of partial products (bwd) from L2 with 1-D bulk async copies (TMA)
 //              that complete on per-chunk "full" mbarriers.
-// There is no CTA-wide or grid-wide barrier in the step loops, only 128-thread named barriers inside a group.
+// There is no CTA-wide or grid-wide barrier in the step loops; the backward has one 128-thread named barrier per step
+// (the dG tile of a group feeds all of its GEMM tiles).
 //
 //   fwd step : gates[b, 4UB] = Gx[b,t] + h_{t-1}[b,:] . Wslice^T ; pointwise ; publish h_t slice
 //   bwd step : dh = dOut[b,t] + sum_src partial_src[b, my units] ; pointwise -> dG[b,4UB] ;
@@ -32,7 +35,8 @@ namespace b200asr {
 constexpr int LSTM_GTHREADS = 128;                  // compute threads per group (one group per batch half)
 constexpr int LSTM_THREADS = 2 * LSTM_GTHREADS + 64;  // two groups + two control warps
 constexpr int LSTM_NCHUNK = 4;
-constexpr int LSTM_MAX_TILES = 64;                  // register tiles per half
+constexpr int LSTM_MAX_TILES = 32;                  // register tiles (4 gates x R rows) per group
+constexpr int LSTM_CHUNK_PAD = 4;                   // floats between the K-chunks of the state block in smem
 constexpr int LSTM_COUNTER_BYTES = 4096;
 
 struct LstmParams {
@@ -43,8 +47,12 @@ struct LstmParams {
     float* xbuf;         // exchange buffers
     unsigned* counters;  // [ndir][nbg][NH]
     int* err_flag;
-    int B, T, H, ndir, UB, Bc, nub, nbg, NH;
+    long long* trace;    // optional [T][16] clock64 stamps of CTA 0 / group 0 (debug; NULL in production)
+    int B, T, H, ndir, UB, Bc, nub, nbg, NH, R;
 };
+
+#define LSTM_TRACE(slot) \
+    do { if (p.trace && blockIdx.x == 0) p.trace[(size_t)step * 16 + (slot)] = clock64(); } while (0)
 
 __device__ __forceinline__ void spin_until(const unsigned* ctr, unsigned target, int* err_flag) {
     const long long t0 = clock64();
@@ -94,46 +102,175 @@ __global__ void lstm_pack_kernel(const float* __restrict__ w, float* __restrict_
     }
 }
 
-#define FMA16(hv, wv)                                                                                 \
-    acc[0][0] = fmaf(hv.x, wv.x, acc[0][0]); acc[0][1] = fmaf(hv.x, wv.y, acc[0][1]);                 \
-    acc[0][2] = fmaf(hv.x, wv.z, acc[0][2]); acc[0][3] = fmaf(hv.x, wv.w, acc[0][3]);                 \
-    acc[1][0] = fmaf(hv.y, wv.x, acc[1][0]); acc[1][1] = fmaf(hv.y, wv.y, acc[1][1]);                 \
-    acc[1][2] = fmaf(hv.y, wv.z, acc[1][2]); acc[1][3] = fmaf(hv.y, wv.w, acc[1][3]);                 \
-    acc[2][0] = fmaf(hv.z, wv.x, acc[2][0]); acc[2][1] = fmaf(hv.z, wv.y, acc[2][1]);                 \
-    acc[2][2] = fmaf(hv.z, wv.z, acc[2][2]); acc[2][3] = fmaf(hv.z, wv.w, acc[2][3]);                 \
-    acc[3][0] = fmaf(hv.w, wv.x, acc[3][0]); acc[3][1] = fmaf(hv.w, wv.y, acc[3][1]);                 \
-    acc[3][2] = fmaf(hv.w, wv.z, acc[3][2]); acc[3][3] = fmaf(hv.w, wv.w, acc[3][3]);
-
 // Control lane of one group: publishes the group's step (one fence + one release per CTA-group and step, off the
 // compute warps' critical path), waits for the peers, then pulls the next step's block into shared memory.
 __device__ __forceinline__ void control_loop(const LstmParams& p, int T, unsigned nub, uint64_t* done, uint64_t* full,
                                              unsigned* ctr, const float* src_even, const float* src_odd, float* dst,
-                                             const uint32_t* chunk_off, const uint32_t* chunk_bytes) {
+                                             const uint32_t* src_off, const uint32_t* dst_off,
+                                             const uint32_t* chunk_bytes, bool trace_me) {
     for (int step = 0; step + 1 < T; ++step) {
         mbar_wait(done, (uint32_t)(step & 1));          // every compute warp of the group finished `step`
+        if (trace_me) LSTM_TRACE(8);
         __threadfence();                                // their global stores (made visible to me through the
-        red_release_add_u32(ctr, 1u);                   // mbarrier) are ordered before the release
+        if (trace_me) LSTM_TRACE(9);                    // mbarrier) are ordered before the release
+        red_release_add_u32(ctr, 1u);
         spin_until(ctr, (unsigned)(step + 1) * nub, p.err_flag);
+        if (trace_me) LSTM_TRACE(10);
         fence_proxy_async();
         const float* src = (step & 1) ? src_odd : src_even;
         for (int c = 0; c < LSTM_NCHUNK; ++c) {
             mbar_expect_tx(&full[c], chunk_bytes[c]);
-            if (chunk_bytes[c]) bulk_g2s(dst + chunk_off[c], src + chunk_off[c], chunk_bytes[c], &full[c]);
+            if (chunk_bytes[c]) bulk_g2s(dst + dst_off[c], src + src_off[c], chunk_bytes[c], &full[c]);
+        }
+        if (trace_me) LSTM_TRACE(11);
+    }
+}
+
+// pick the RL consecutive rows [kq*RL, kq*RL + RL) of an R-row accumulator tile (RL = R/4) without dynamic indexing
+template <int R>
+__device__ __forceinline__ float pick_row(const float (&acc)[R][4], int kq, int i, int q) {
+    constexpr int RL = R / 4;
+    float v = acc[i][q];
+    if (kq == 1) v = acc[RL + i][q];
+    if (kq == 2) v = acc[2 * RL + i][q];
+    if (kq == 3) v = acc[3 * RL + i][q];
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// Forward compute group: 128 threads = 32 register tiles (4 gates x R rows) x 4 K-chunks.  lane = kq*8 + tile%8.
+template <int R>
+__device__ __forceinline__ void fwd_group(const LstmParams& p, int g, int gt, int dir, int bg, int ub, const float4* Ws,
+                                          const float* hsg, uint64_t* full, uint64_t* done, float* xbg) {
+    constexpr int RL = R / 4;                 // rows each lane finishes
+    const int H = p.H, UB = p.UB, T = p.T;
+    const int Bh = p.Bc / p.NH;
+    const int NBO = Bh / R;                   // row blocks per half
+    const int KC = H / LSTM_NCHUNK;
+    const int lane = gt & 31;
+    const int kq = lane >> 3;
+    const int tile = (gt >> 5) * 8 + (lane & 7);
+    const int NT = UB * NBO;
+    const bool has_tile = tile < NT;
+    const int u = has_tile ? tile % UB : 0;
+    const int bo = has_tile ? tile / UB : 0;
+    const int ug = ub * UB + u;
+    const int bl0 = bo * R + kq * RL;         // my RL rows within the half
+    const int bglob0 = bg * p.Bc + g * Bh + bl0;
+    const size_t half_elems = (size_t)H * Bh;
+    const int chunk_stride = KC * Bh + LSTM_CHUNK_PAD;   // padded so the 4 chunks start in different banks
+    const bool trc = (g == 0 && gt == 0);
+    float c_reg[RL];
+#pragma unroll
+    for (int i = 0; i < RL; ++i) c_reg[i] = 0.f;
+
+    for (int step = 0; step < T; ++step) {
+        const int tt = dir ? (T - 1 - step) : step;
+        if (trc) LSTM_TRACE(0);
+        float4 gx[RL];
+#pragma unroll
+        for (int i = 0; i < RL; ++i) {
+            gx[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int b = bglob0 + i;
+            if (has_tile && b < p.B)
+                gx[i] = *reinterpret_cast<const float4*>(p.gates + ((((size_t)dir * p.B + b) * T + tt) * H + ug) * 4);
+        }
+        float acc[R][4];
+#pragma unroll
+        for (int i = 0; i < R; ++i)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[i][q] = 0.f;
+
+        if (step > 0) {
+            mbar_wait(&full[kq], (uint32_t)((step - 1) & 1));
+            if (trc) LSTM_TRACE(1);
+            if (has_tile) {
+                const float4* hp = reinterpret_cast<const float4*>(hsg + (size_t)kq * chunk_stride + bo * R);
+                const float4* wp = Ws + (size_t)kq * KC * UB + u;
+                const int hstride = Bh >> 2;  // float4 per k row
+                float4 hv[RL], wv = wp[0];
+#pragma unroll
+                for (int j = 0; j < RL; ++j) hv[j] = hp[j];
+#pragma unroll 2
+                for (int kk = 0; kk < KC; ++kk) {
+                    // software pipelined: the loads of k+1 are in flight while the FMAs of k issue
+                    const int kn = (kk + 1 < KC) ? kk + 1 : kk;
+                    float4 hn[RL];
+                    const float4 wn = wp[(size_t)kn * UB];
+#pragma unroll
+                    for (int j = 0; j < RL; ++j) hn[j] = hp[(size_t)kn * hstride + j];
+#pragma unroll
+                    for (int j = 0; j < RL; ++j) {
+                        const float hr[4] = {hv[j].x, hv[j].y, hv[j].z, hv[j].w};
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            acc[j * 4 + r][0] = fmaf(hr[r], wv.x, acc[j * 4 + r][0]);
+                            acc[j * 4 + r][1] = fmaf(hr[r], wv.y, acc[j * 4 + r][1]);
+                            acc[j * 4 + r][2] = fmaf(hr[r], wv.z, acc[j * 4 + r][2]);
+                            acc[j * 4 + r][3] = fmaf(hr[r], wv.w, acc[j * 4 + r][3]);
+                        }
+                    }
+                    wv = wn;
+#pragma unroll
+                    for (int j = 0; j < RL; ++j) hv[j] = hn[j];
+                }
+            }
+            if (trc) LSTM_TRACE(3);
+            // reduce the 4 K-chunks held by lanes l, l^8, l^16, l^24
+#pragma unroll
+            for (int i = 0; i < R; ++i)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float v = acc[i][q];
+                    v += __shfl_xor_sync(0xffffffffu, v, 8);
+                    v += __shfl_xor_sync(0xffffffffu, v, 16);
+                    acc[i][q] = v;
+                }
+            if (trc) LSTM_TRACE(4);
+        }
+        float hq[RL];
+#pragma unroll
+        for (int i = 0; i < RL; ++i) {
+            hq[i] = 0.f;
+            const int b = bglob0 + i;
+            if (has_tile && b < p.B) {
+                const float ig = sigmoidf_(gx[i].x + pick_row<R>(acc, kq, i, 0));
+                const float fg = sigmoidf_(gx[i].y + pick_row<R>(acc, kq, i, 1));
+                const float gg = tanhf(gx[i].z + pick_row<R>(acc, kq, i, 2));
+                const float og = sigmoidf_(gx[i].w + pick_row<R>(acc, kq, i, 3));
+                const float c = fmaf(fg, c_reg[i], ig * gg);
+                c_reg[i] = c;
+                const float h = og * tanhf(c);
+                hq[i] = h;
+                const size_t row = ((size_t)dir * p.B + b) * T + tt;
+                *reinterpret_cast<float4*>(p.gates + (row * H + ug) * 4) = make_float4(ig, fg, gg, og);
+                p.cst[row * H + ug] = c;
+                p.out[((size_t)b * T + tt) * (p.ndir * H) + (size_t)dir * H + ug] = h;
+            }
+        }
+        if (step + 1 < T) {
+            if (has_tile) {
+                float* dstp = xbg + (size_t)(step & 1) * half_elems + (size_t)ug * Bh + bl0;
+#pragma unroll
+                for (int i = 0; i < RL; ++i) dstp[i] = hq[i];
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(done);
+            if (trc) LSTM_TRACE(5);
         }
     }
 }
 
-// ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(LSTM_THREADS, 1) bilstm_fwd_kernel(LstmParams p) {
     extern __shared__ __align__(128) unsigned char s_raw[];
     const int H = p.H, UB = p.UB, Bc = p.Bc, T = p.T, NH = p.NH;
     const int Bh = Bc / NH;
-    const int NBQ = Bh >> 2;                 // batch quads per half
     const int KC = H / LSTM_NCHUNK;
+    const int chunk_stride = KC * Bh + LSTM_CHUNK_PAD;
+    const size_t hs_half = (size_t)LSTM_NCHUNK * chunk_stride;                   // padded floats per half
     float4* Ws = reinterpret_cast<float4*>(s_raw);                               // [H][UB] float4 (4 gates)
-    float* hs = reinterpret_cast<float*>(Ws + (size_t)H * UB);                   // [NH][H*Bh]
-    float* red = hs + (size_t)H * Bc;                                            // [2][8][128]
-    uint64_t* full = reinterpret_cast<uint64_t*>(red + 2 * 8 * LSTM_GTHREADS);   // [2][NCHUNK]
+    float* hs = reinterpret_cast<float*>(Ws + (size_t)H * UB);                   // [NH][4 chunks, padded]
+    uint64_t* full = reinterpret_cast<uint64_t*>(hs + 2 * ((size_t)LSTM_NCHUNK * (KC * (Bc / NH) + LSTM_CHUNK_PAD)));
     uint64_t* done = full + 2 * LSTM_NCHUNK;                                     // [2]
 
     const int tid = threadIdx.x;
@@ -162,132 +299,210 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) bilstm_fwd_kernel(LstmParams 
         // ===== control warps: warp 8 -> group 0, warp 9 -> group 1 =====
         const int g = warp - 2 * (LSTM_GTHREADS / 32);
         if (lane == 0 && g < NH) {
-            uint32_t off[LSTM_NCHUNK], bytes[LSTM_NCHUNK];
+            uint32_t soff[LSTM_NCHUNK], doff[LSTM_NCHUNK], bytes[LSTM_NCHUNK];
             for (int c = 0; c < LSTM_NCHUNK; ++c) {
-                off[c] = (uint32_t)((size_t)c * KC * Bh);
+                soff[c] = (uint32_t)((size_t)c * KC * Bh);
+                doff[c] = (uint32_t)((size_t)c * chunk_stride);
                 bytes[c] = (uint32_t)((size_t)KC * Bh * sizeof(float));
             }
             control_loop(p, T, (unsigned)p.nub, &done[g], &full[g * LSTM_NCHUNK], ctr0 + g,
                          xb + ((size_t)g * 2 + 0) * half_elems, xb + ((size_t)g * 2 + 1) * half_elems,
-                         hs + (size_t)g * half_elems, off, bytes);
+                         hs + (size_t)g * hs_half, soff, doff, bytes, g == 0);
         }
         return;
     }
-
-    // ===== compute groups: threads [0,128) -> batch half 0, [128,256) -> batch half 1 =====
     const int g = tid / LSTM_GTHREADS;
     if (g >= NH) return;
     const int gt = tid - g * LSTM_GTHREADS;
-    const int kh = gt >> 6;                   // K half of this thread
-    const int pidx = gt & 63;
-    const int NT = UB * NBQ;
-    const bool has_tile = pidx < NT;
-    const int u = has_tile ? pidx % UB : 0;
-    const int bq = has_tile ? pidx / UB : 0;
+    if (p.R == 8)
+        fwd_group<8>(p, g, gt, dir, bg, ub, Ws, hs + (size_t)g * hs_half, &full[g * LSTM_NCHUNK], &done[g],
+                     xb + (size_t)g * 2 * half_elems);
+    else
+        fwd_group<4>(p, g, gt, dir, bg, ub, Ws, hs + (size_t)g * hs_half, &full[g * LSTM_NCHUNK], &done[g],
+                     xb + (size_t)g * 2 * half_elems);
+}
+
+// ------------------------------------------------------------------------------------------
+// Backward compute group.
+template <int R>
+__device__ __forceinline__ void bwd_group(const LstmParams& p, int g, int gt, int dir, int bg, int ub, const float* Wr,
+                                          const float* inb, float* dgs, uint64_t* full, uint64_t* done, float* xbg) {
+    constexpr int RL = R / 4;
+    const int H = p.H, UB = p.UB, T = p.T, nub = p.nub;
+    const int Bh = p.Bc / p.NH;
+    const int NBO = Bh / R;
+    const int lane = gt & 31;
+    const int kq = lane >> 3;
+    const int tile = (gt >> 5) * 8 + (lane & 7);
+    const int NT = UB * NBO;
+    const bool has_tile = tile < NT;
+    const int u = has_tile ? tile % UB : 0;
+    const int bo = has_tile ? tile / UB : 0;
     const int ug = ub * UB + u;
-    const int bl0 = bq * 4 + 2 * kh;          // my two rows within the half: bl0, bl0+1
-    const int bglob0 = bg * Bc + g * Bh + bl0;
-    float* redg = red + (size_t)g * 8 * LSTM_GTHREADS;
-    const float* hsg = hs + (size_t)g * half_elems;
-    float c_reg[2] = {0.f, 0.f};
+    const int bl0 = bo * R + kq * RL;
+    const int bglob0 = bg * p.Bc + g * Bh + bl0;
+    const size_t inbox_elems = (size_t)Bh * H;
+    const int SC = (nub + LSTM_NCHUNK - 1) / LSTM_NCHUNK;        // sources per chunk
+    const bool vec_ok = (UB % 4) == 0;
+    float dc_reg[RL];
+#pragma unroll
+    for (int i = 0; i < RL; ++i) dc_reg[i] = 0.f;
 
     for (int step = 0; step < T; ++step) {
-        const int tt = dir ? (T - 1 - step) : step;
-        float4 gx[2];
+        const int fstep = T - 1 - step;                    // forward step index being differentiated
+        const int tt = dir ? (T - 1 - fstep) : fstep;      // its time index
+        const int tt_prev = dir ? tt + 1 : tt - 1;         // time index of the previous forward step
+        float4 gtv[RL];
+        float ct[RL], cp[RL], dh[RL];
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            gx[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            const int b = bglob0 + i;
-            if (has_tile && b < p.B)
-                gx[i] = *reinterpret_cast<const float4*>(p.gates + ((((size_t)dir * p.B + b) * T + tt) * H + ug) * 4);
-        }
-        float acc[4][4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int q = 0; q < 4; ++q) acc[i][q] = 0.f;
-
-        if (step > 0) {
-            if (has_tile) {
-#pragma unroll 1
-                for (int cc = 0; cc < LSTM_NCHUNK / 2; ++cc) {
-                    const int c = kh * (LSTM_NCHUNK / 2) + cc;
-                    mbar_wait(&full[g * LSTM_NCHUNK + c], (uint32_t)((step - 1) & 1));
-                    const float4* hp = reinterpret_cast<const float4*>(hsg + (size_t)c * KC * Bh) + bq;
-                    const float4* wp = Ws + (size_t)c * KC * UB + u;
-                    // software pipelined: the loads of k+1 are in flight while the 16 FMAs of k issue
-                    float4 h0 = hp[0], w0 = wp[0];
-#pragma unroll 4
-                    for (int kk = 1; kk < KC; ++kk) {
-                        const float4 h1 = hp[(size_t)kk * NBQ];
-                        const float4 w1 = wp[(size_t)kk * UB];
-                        FMA16(h0, w0)
-                        h0 = h1;
-                        w0 = w1;
-                    }
-                    FMA16(h0, w0)
-                }
-            }
-            // exchange the two rows the partner K-half finishes
-#pragma unroll
-            for (int i = 0; i < 2; ++i)
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    redg[(i * 4 + q) * LSTM_GTHREADS + gt] = kh ? acc[i][q] : acc[2 + i][q];
-            named_bar_sync(1 + g, LSTM_GTHREADS);
-#pragma unroll
-            for (int i = 0; i < 2; ++i)
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float o = redg[(i * 4 + q) * LSTM_GTHREADS + (gt ^ 64)];
-                    if (kh) acc[2 + i][q] += o; else acc[i][q] += o;
-                }
-        }
-        float hq[2] = {0.f, 0.f};
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < RL; ++i) {
+            gtv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            ct[i] = cp[i] = dh[i] = 0.f;
             const int b = bglob0 + i;
             if (has_tile && b < p.B) {
-                const float a0 = kh ? acc[2 + i][0] : acc[i][0];
-                const float a1 = kh ? acc[2 + i][1] : acc[i][1];
-                const float a2 = kh ? acc[2 + i][2] : acc[i][2];
-                const float a3 = kh ? acc[2 + i][3] : acc[i][3];
-                const float ig = sigmoidf_(gx[i].x + a0);
-                const float fg = sigmoidf_(gx[i].y + a1);
-                const float gg = tanhf(gx[i].z + a2);
-                const float og = sigmoidf_(gx[i].w + a3);
-                const float c = fmaf(fg, c_reg[i], ig * gg);
-                c_reg[i] = c;
-                const float h = og * tanhf(c);
-                hq[i] = h;
                 const size_t row = ((size_t)dir * p.B + b) * T + tt;
-                *reinterpret_cast<float4*>(p.gates + (row * H + ug) * 4) = make_float4(ig, fg, gg, og);
-                p.cst[row * H + ug] = c;
-                p.out[((size_t)b * T + tt) * (p.ndir * H) + (size_t)dir * H + ug] = h;
+                gtv[i] = *reinterpret_cast<const float4*>(p.gates + (row * H + ug) * 4);
+                ct[i] = p.cst[row * H + ug];
+                if (fstep > 0) cp[i] = p.cst[(((size_t)dir * p.B + b) * T + tt_prev) * H + ug];
+                dh[i] = p.out[((size_t)b * T + tt) * (p.ndir * H) + (size_t)dir * H + ug];
             }
         }
+        if (step > 0) {
+            // my K-chunk of the sources for all R rows of the tile, then reduce over the 4 chunk lanes
+            float part[R];
+#pragma unroll
+            for (int i = 0; i < R; ++i) part[i] = 0.f;
+            mbar_wait(&full[kq], (uint32_t)((step - 1) & 1));
+            const int s0 = min(nub, kq * SC), s1 = min(nub, s0 + SC);
+            if (has_tile) {
+                for (int s = s0; s < s1; ++s) {
+                    const float* ib = inb + ((size_t)s * Bh + bo * R) * UB + u;
+#pragma unroll
+                    for (int i = 0; i < R; ++i) part[i] += ib[i * UB];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                float v = part[i];
+                v += __shfl_xor_sync(0xffffffffu, v, 8);
+                v += __shfl_xor_sync(0xffffffffu, v, 16);
+                part[i] = v;
+            }
+#pragma unroll
+            for (int i = 0; i < RL; ++i) {
+                float v = part[i];
+                if (kq == 1) v = part[RL + i];
+                if (kq == 2) v = part[2 * RL + i];
+                if (kq == 3) v = part[3 * RL + i];
+                dh[i] += v;
+            }
+        }
+        // pointwise backward of the cell for my rows
+#pragma unroll
+        for (int i = 0; i < RL; ++i) {
+            const int b = bglob0 + i;
+            float4 dg = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (has_tile && b < p.B) {
+                const float ig = gtv[i].x, fg = gtv[i].y, gg = gtv[i].z, og = gtv[i].w;
+                const float tc = tanhf(ct[i]);
+                const float dc = dc_reg[i] + dh[i] * og * (1.f - tc * tc);
+                dg.x = dc * gg * ig * (1.f - ig);
+                dg.y = dc * cp[i] * fg * (1.f - fg);
+                dg.z = dc * ig * (1.f - gg * gg);
+                dg.w = dh[i] * tc * og * (1.f - og);
+                dc_reg[i] = dc * fg;
+                const size_t row = ((size_t)dir * p.B + b) * T + tt;
+                *reinterpret_cast<float4*>(p.gates + (row * H + ug) * 4) = dg;
+            }
+            if (has_tile) {
+                float* d = dgs + (size_t)(u * 4) * Bh + bl0 + i;
+                d[0] = dg.x; d[Bh] = dg.y; d[2 * Bh] = dg.z; d[3 * Bh] = dg.w;
+            }
+        }
+        named_bar_sync(1 + g, LSTM_GTHREADS);              // the dG tile of this step is complete
         if (step + 1 < T) {
-            if (has_tile)
-                *reinterpret_cast<float2*>(xb + ((size_t)g * 2 + (step & 1)) * half_elems + (size_t)ug * Bh + bl0) =
-                    make_float2(hq[0], hq[1]);
+            // partial[b][k] = sum_c dGs[c][b] * Wr[c][k]; thread tiles of R rows x (2 strided float4 of k)
+            const int NKQ = H / 8;
+            const int ntiles = NKQ * NBO;
+            float* outbase = xbg + (size_t)(step & 1) * nub * inbox_elems;
+            for (int t2 = gt; t2 < ntiles; t2 += LSTM_GTHREADS) {
+                const int kq2 = t2 % NKQ;
+                const int bo2 = t2 / NKQ;
+                float a[R][8];
+#pragma unroll
+                for (int i = 0; i < R; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) a[i][j] = 0.f;
+                const int C = 4 * UB;
+                const float* wbase = Wr + kq2 * 4;
+                const float* dbase = dgs + bo2 * R;
+                float4 dcur[RL];
+#pragma unroll
+                for (int j = 0; j < RL; ++j) dcur[j] = *reinterpret_cast<const float4*>(dbase + j * 4);
+                float4 wa = *reinterpret_cast<const float4*>(wbase);
+                float4 wb = *reinterpret_cast<const float4*>(wbase + (H >> 1));
+#pragma unroll 2
+                for (int c = 0; c < C; ++c) {
+                    const int cn = (c + 1 < C) ? c + 1 : c;
+                    float4 dnext[RL];
+#pragma unroll
+                    for (int j = 0; j < RL; ++j) dnext[j] = *reinterpret_cast<const float4*>(dbase + (size_t)cn * Bh + j * 4);
+                    const float4 wan = *reinterpret_cast<const float4*>(wbase + (size_t)cn * H);
+                    const float4 wbn = *reinterpret_cast<const float4*>(wbase + (size_t)cn * H + (H >> 1));
+#pragma unroll
+                    for (int j = 0; j < RL; ++j) {
+                        const float dv[4] = {dcur[j].x, dcur[j].y, dcur[j].z, dcur[j].w};
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            float* ar = a[j * 4 + r];
+                            ar[0] = fmaf(dv[r], wa.x, ar[0]); ar[1] = fmaf(dv[r], wa.y, ar[1]);
+                            ar[2] = fmaf(dv[r], wa.z, ar[2]); ar[3] = fmaf(dv[r], wa.w, ar[3]);
+                            ar[4] = fmaf(dv[r], wb.x, ar[4]); ar[5] = fmaf(dv[r], wb.y, ar[5]);
+                            ar[6] = fmaf(dv[r], wb.z, ar[6]); ar[7] = fmaf(dv[r], wb.w, ar[7]);
+                        }
+                    }
+                    wa = wan; wb = wbn;
+#pragma unroll
+                    for (int j = 0; j < RL; ++j) dcur[j] = dnext[j];
+                }
+                // scatter to the destination inboxes: element (dst, src=ub, row, u')
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const int k0 = r * (H >> 1) + kq2 * 4;
+#pragma unroll
+                    for (int i = 0; i < R; ++i) {
+                        const int rowl = bo2 * R + i;
+                        if (vec_ok) {
+                            const int dst = k0 / UB, uu = k0 - dst * UB;
+                            float* o = outbase + (((size_t)dst * nub + ub) * Bh + rowl) * UB + uu;
+                            *reinterpret_cast<float4*>(o) =
+                                make_float4(a[i][r * 4], a[i][r * 4 + 1], a[i][r * 4 + 2], a[i][r * 4 + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int k = k0 + j;
+                                const int dst = k / UB, uu = k - dst * UB;
+                                outbase[(((size_t)dst * nub + ub) * Bh + rowl) * UB + uu] = a[i][r * 4 + j];
+                            }
+                        }
+                    }
+                }
+            }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&done[g]);
+            if (lane == 0) mbar_arrive(done);
         }
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// Backward. Shared memory: Wr[4UB][H] | inbox[NH][nub*Bh*UB] | dGs[NH][4UB*Bh] | red[2][2][128] | barriers
+// Shared memory: Wr[4UB][H] | inbox[NH][nub*Bh*UB] | dGs[NH][4UB*Bh] | barriers
 __global__ void __launch_bounds__(LSTM_THREADS, 1) bilstm_bwd_kernel(LstmParams p) {
     extern __shared__ __align__(128) unsigned char s_raw[];
     const int H = p.H, UB = p.UB, Bc = p.Bc, T = p.T, nub = p.nub, NH = p.NH;
     const int Bh = Bc / NH;
-    const int NBQ = Bh >> 2;
     float* Wr = reinterpret_cast<float*>(s_raw);                 // [4UB][H]
     float* inbox = Wr + (size_t)4 * UB * H;                      // [NH][nub*Bh*UB]  (= Bc*H floats)
     float* dGs = inbox + (size_t)Bc * H;                         // [NH][4UB*Bh]
-    float* red = dGs + (size_t)4 * UB * Bc;                      // [2][2][128]
-    uint64_t* full = reinterpret_cast<uint64_t*>(red + 2 * 2 * LSTM_GTHREADS);
+    uint64_t* full = reinterpret_cast<uint64_t*>(dGs + (size_t)4 * UB * Bc);
     uint64_t* done = full + 2 * LSTM_NCHUNK;
 
     const int tid = threadIdx.x;
@@ -313,7 +528,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) bilstm_bwd_kernel(LstmParams 
     const size_t inbox_elems = (size_t)Bh * H;                   // floats one destination receives per step
     float* xb = p.xbuf + ((size_t)dir * p.nbg + bg) * NH * 2 * (size_t)nub * inbox_elems;
     unsigned* ctr0 = p.counters + ((size_t)dir * p.nbg + bg) * NH;
-    const int SC = (nub + LSTM_NCHUNK - 1) / LSTM_NCHUNK;        // sources per chunk
+    const int SC = (nub + LSTM_NCHUNK - 1) / LSTM_NCHUNK;
 
     if (warp >= 2 * (LSTM_GTHREADS / 32)) {
         const int g = warp - 2 * (LSTM_GTHREADS / 32);
@@ -326,155 +541,20 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) bilstm_bwd_kernel(LstmParams 
             }
             control_loop(p, T, (unsigned)nub, &done[g], &full[g * LSTM_NCHUNK], ctr0 + g,
                          xb + (((size_t)g * 2 + 0) * nub + ub) * inbox_elems,
-                         xb + (((size_t)g * 2 + 1) * nub + ub) * inbox_elems, inbox + (size_t)g * inbox_elems, off,
-                         bytes);
+                         xb + (((size_t)g * 2 + 1) * nub + ub) * inbox_elems, inbox + (size_t)g * inbox_elems, off, off,
+                         bytes, false);
         }
         return;
     }
-
     const int g = tid / LSTM_GTHREADS;
     if (g >= NH) return;
     const int gt = tid - g * LSTM_GTHREADS;
-    const int kh = gt >> 6;
-    const int pidx = gt & 63;
-    const int NT = UB * NBQ;
-    const bool has_tile = pidx < NT;
-    const int u = has_tile ? pidx % UB : 0;
-    const int bq = has_tile ? pidx / UB : 0;
-    const int ug = ub * UB + u;
-    const int bl0 = bq * 4 + 2 * kh;
-    const int bglob0 = bg * Bc + g * Bh + bl0;
-    const bool vec_ok = (UB % 4) == 0;
-    float* redg = red + (size_t)g * 2 * LSTM_GTHREADS;
-    const float* inb = inbox + (size_t)g * inbox_elems;
-    float* dgs = dGs + (size_t)g * 4 * UB * Bh;
-    float dc_reg[2] = {0.f, 0.f};
-
-    for (int step = 0; step < T; ++step) {
-        const int fstep = T - 1 - step;                    // forward step index being differentiated
-        const int tt = dir ? (T - 1 - fstep) : fstep;      // its time index
-        const int tt_prev = dir ? tt + 1 : tt - 1;         // time index of the previous forward step
-        float4 gtv[2];
-        float ct[2], cp[2], dh[2];
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            gtv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            ct[i] = cp[i] = dh[i] = 0.f;
-            const int b = bglob0 + i;
-            if (has_tile && b < p.B) {
-                const size_t row = ((size_t)dir * p.B + b) * T + tt;
-                gtv[i] = *reinterpret_cast<const float4*>(p.gates + (row * H + ug) * 4);
-                ct[i] = p.cst[row * H + ug];
-                if (fstep > 0) cp[i] = p.cst[(((size_t)dir * p.B + b) * T + tt_prev) * H + ug];
-                dh[i] = p.out[((size_t)b * T + tt) * (p.ndir * H) + (size_t)dir * H + ug];
-            }
-        }
-        if (step > 0) {
-            // sum the partial products of my K-half of the sources for all 4 rows of the tile
-            float part[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-            for (int cc = 0; cc < LSTM_NCHUNK / 2; ++cc) {
-                const int c = kh * (LSTM_NCHUNK / 2) + cc;
-                mbar_wait(&full[g * LSTM_NCHUNK + c], (uint32_t)((step - 1) & 1));
-                const int s0 = min(nub, c * SC), s1 = min(nub, s0 + SC);
-                if (has_tile) {
-                    for (int s = s0; s < s1; ++s) {
-                        const float* ib = inb + ((size_t)s * Bh + bq * 4) * UB + u;
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) part[i] += ib[i * UB];
-                    }
-                }
-            }
-            redg[0 * LSTM_GTHREADS + gt] = kh ? part[0] : part[2];
-            redg[1 * LSTM_GTHREADS + gt] = kh ? part[1] : part[3];
-            named_bar_sync(1 + g, LSTM_GTHREADS);
-            dh[0] += (kh ? part[2] : part[0]) + redg[0 * LSTM_GTHREADS + (gt ^ 64)];
-            dh[1] += (kh ? part[3] : part[1]) + redg[1 * LSTM_GTHREADS + (gt ^ 64)];
-        }
-        // pointwise backward of the cell for my two rows
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int b = bglob0 + i;
-            float4 dg = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (has_tile && b < p.B) {
-                const float ig = gtv[i].x, fg = gtv[i].y, gg = gtv[i].z, og = gtv[i].w;
-                const float tc = tanhf(ct[i]);
-                const float dc = dc_reg[i] + dh[i] * og * (1.f - tc * tc);
-                dg.x = dc * gg * ig * (1.f - ig);
-                dg.y = dc * cp[i] * fg * (1.f - fg);
-                dg.z = dc * ig * (1.f - gg * gg);
-                dg.w = dh[i] * tc * og * (1.f - og);
-                dc_reg[i] = dc * fg;
-                const size_t row = ((size_t)dir * p.B + b) * T + tt;
-                *reinterpret_cast<float4*>(p.gates + (row * H + ug) * 4) = dg;
-            }
-            if (has_tile) {
-                float* d = dgs + (size_t)(u * 4) * Bh + bl0 + i;
-                d[0] = dg.x; d[Bh] = dg.y; d[2 * Bh] = dg.z; d[3 * Bh] = dg.w;
-            }
-        }
-        named_bar_sync(3 + g, LSTM_GTHREADS);              // the dG tile of this step is complete
-        if (step + 1 < T) {
-            // partial[b][k] = sum_c dGs[c][b] * Wr[c][k]; thread tiles of 4 rows x (2 strided float4 of k)
-            const int NKQ = H / 8;
-            const int ntiles = NKQ * NBQ;
-            float* outbase = xb + ((size_t)g * 2 + (step & 1)) * nub * inbox_elems;
-            for (int t2 = gt; t2 < ntiles; t2 += LSTM_GTHREADS) {
-                const int kq2 = t2 % NKQ;
-                const int bq2 = t2 / NKQ;
-                float a[4][8];
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) a[i][j] = 0.f;
-                const int C = 4 * UB;
-                const float* wbase = Wr + kq2 * 4;
-                float4 d4 = *reinterpret_cast<const float4*>(dgs + bq2 * 4);
-                float4 wa = *reinterpret_cast<const float4*>(wbase);
-                float4 wb = *reinterpret_cast<const float4*>(wbase + (H >> 1));
-#pragma unroll 4
-                for (int c = 0; c < C; ++c) {
-                    const int cn = (c + 1 < C) ? c + 1 : c;
-                    const float4 d4n = *reinterpret_cast<const float4*>(dgs + (size_t)cn * Bh + bq2 * 4);
-                    const float4 wan = *reinterpret_cast<const float4*>(wbase + (size_t)cn * H);
-                    const float4 wbn = *reinterpret_cast<const float4*>(wbase + (size_t)cn * H + (H >> 1));
-                    const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        a[i][0] = fmaf(dv[i], wa.x, a[i][0]); a[i][1] = fmaf(dv[i], wa.y, a[i][1]);
-                        a[i][2] = fmaf(dv[i], wa.z, a[i][2]); a[i][3] = fmaf(dv[i], wa.w, a[i][3]);
-                        a[i][4] = fmaf(dv[i], wb.x, a[i][4]); a[i][5] = fmaf(dv[i], wb.y, a[i][5]);
-                        a[i][6] = fmaf(dv[i], wb.z, a[i][6]); a[i][7] = fmaf(dv[i], wb.w, a[i][7]);
-                    }
-                    d4 = d4n; wa = wan; wb = wbn;
-                }
-                // scatter to the destination inboxes: element (dst, src=ub, row, u')
-#pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    const int k0 = r * (H >> 1) + kq2 * 4;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int rowl = bq2 * 4 + i;
-                        if (vec_ok) {
-                            const int dst = k0 / UB, uu = k0 - dst * UB;
-                            float* o = outbase + (((size_t)dst * nub + ub) * Bh + rowl) * UB + uu;
-                            *reinterpret_cast<float4*>(o) =
-                                make_float4(a[i][r * 4], a[i][r * 4 + 1], a[i][r * 4 + 2], a[i][r * 4 + 3]);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const int k = k0 + j;
-                                const int dst = k / UB, uu = k - dst * UB;
-                                outbase[(((size_t)dst * nub + ub) * Bh + rowl) * UB + uu] = a[i][r * 4 + j];
-                            }
-                        }
-                    }
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&done[g]);
-        }
-    }
+    if (p.R == 8)
+        bwd_group<8>(p, g, gt, dir, bg, ub, Wr, inbox + (size_t)g * inbox_elems, dGs + (size_t)g * 4 * UB * Bh,
+                     &full[g * LSTM_NCHUNK], &done[g], xb + (size_t)g * 2 * nub * inbox_elems);
+    else
+        bwd_group<4>(p, g, gt, dir, bg, ub, Wr, inbox + (size_t)g * inbox_elems, dGs + (size_t)g * 4 * UB * Bh,
+                     &full[g * LSTM_NCHUNK], &done[g], xb + (size_t)g * 2 * nub * inbox_elems);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -516,17 +596,18 @@ __global__ void lstm_cell_bwd_kernel(const float* __restrict__ gates, const floa
 
 // ------------------------------------------------------------------------------------------
 struct Plan {
-    int UB, Bc, nub, nbg, ctas, NH;
+    int UB, Bc, nub, nbg, ctas, NH, R;
     size_t smem_fwd, smem_bwd, pack_bytes, xbuf_fwd_bytes, xbuf_bwd_bytes;
 };
 
 static int halves_for(int Bc) { return (Bc % 8 == 0) ? 2 : 1; }
+static int rows_for(int Bc) { return ((Bc / halves_for(Bc)) % 8 == 0) ? 8 : 4; }
 static size_t smem_fwd_bytes(int H, int UB, int Bc) {
-    return (size_t)H * UB * 16 + (size_t)H * Bc * 4 + 2 * 8 * LSTM_GTHREADS * 4 + (2 * LSTM_NCHUNK + 2) * 8 + 128;
+    const int Bh = Bc / halves_for(Bc);
+    return (size_t)H * UB * 16 + 2 * ((size_t)H * Bh + LSTM_NCHUNK * LSTM_CHUNK_PAD) * 4 + (2 * LSTM_NCHUNK + 2) * 8 + 128;
 }
 static size_t smem_bwd_bytes(int H, int UB, int Bc) {
-    return (size_t)4 * UB * H * 4 + (size_t)Bc * H * 4 + (size_t)4 * UB * Bc * 4 + 2 * 2 * LSTM_GTHREADS * 4 +
-           (2 * LSTM_NCHUNK + 2) * 8 + 128;
+    return (size_t)4 * UB * H * 4 + (size_t)Bc * H * 4 + (size_t)4 * UB * Bc * 4 + (2 * LSTM_NCHUNK + 2) * 8 + 128;
 }
 
 static int make_plan(int B, int H, int ndir, Plan* out) {
@@ -539,7 +620,8 @@ static int make_plan(int B, int H, int ndir, Plan* out) {
         if (H % UB) continue;
         for (int Bc = 4; Bc <= 64; Bc += 4) {
             const int NH = halves_for(Bc);
-            if (UB * (Bc / NH / 4) > LSTM_MAX_TILES) continue;   // register tiles per half
+            const int R = rows_for(Bc);
+            if (UB * (Bc / NH / R) > LSTM_MAX_TILES) continue;   // register tiles per group
             const int nbg = (B + Bc - 1) / Bc;
             const int nub = H / UB;
             const int ctas = ndir * nbg * nub;
@@ -554,7 +636,7 @@ static int make_plan(int B, int H, int ndir, Plan* out) {
             const long long cost = (long long)UB * Bc * 1000 + Bc;
             if (best_cost < 0 || cost < best_cost) {
                 best_cost = cost;
-                best.UB = UB; best.Bc = Bc; best.nub = nub; best.nbg = nbg; best.ctas = ctas; best.NH = NH;
+                best.UB = UB; best.Bc = Bc; best.nub = nub; best.nbg = nbg; best.ctas = ctas; best.NH = NH; best.R = R;
                 best.smem_fwd = sf; best.smem_bwd = sb;
             }
         }
@@ -568,6 +650,7 @@ static int make_plan(int B, int H, int ndir, Plan* out) {
 }
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static long long* g_trace = nullptr;   // debug only: set through b200asr_debug_set_lstm_trace
 
 }  // namespace b200asr
 
@@ -620,7 +703,7 @@ static int bilstm_run(bool bwd, float* gates, const float* w_hh, float* cstate, 
     LstmParams p;
     p.gates = gates; p.whh = packed; p.cst = cstate; p.out = out_or_dout; p.xbuf = xbuf; p.counters = counters;
     p.err_flag = err_flag; p.B = B; p.T = T; p.H = H; p.ndir = ndir; p.UB = pl.UB; p.Bc = pl.Bc; p.nub = pl.nub;
-    p.nbg = pl.nbg; p.NH = pl.NH;
+    p.nbg = pl.nbg; p.NH = pl.NH; p.R = pl.R; p.trace = bwd ? nullptr : g_trace;
     const void* fn = bwd ? (const void*)bilstm_bwd_kernel : (const void*)bilstm_fwd_kernel;
     const size_t smem = bwd ? pl.smem_bwd : pl.smem_fwd;
     B200_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -633,6 +716,8 @@ static int bilstm_run(bool bwd, float* gates, const float* w_hh, float* cstate, 
     count_launch();
     return B200_OK;
 }
+
+extern "C" void b200asr_debug_set_lstm_trace(long long* device_buffer) { g_trace = device_buffer; }
 
 extern "C" int b200asr_bilstm_fwd(float* gates, const float* w_hh, float* cstate, float* out, int B, int T, int H,
                                   int ndir, void* workspace, size_t workspace_bytes, b200asr_stream stream) {

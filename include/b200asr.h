@@ -98,6 +98,9 @@ B200ASR_API int b200asr_bilstm_fwd(float* gates, const float* w_hh, float* cstat
 B200ASR_API int b200asr_bilstm_bwd(float* gates, const float* w_hh, const float* cstate, const float* dout, int B, int T,
                        int H, int ndir, void* workspace, size_t workspace_bytes, b200asr_stream stream);
 
+/* debug: when non-NULL, CTA 0 of the next b200asr_bilstm_fwd calls records clock64 stamps into [T][16] int64 */
+B200ASR_API void b200asr_debug_set_lstm_trace(long long* device_buffer);
+
 /* ---- K13: one LSTM cell step (decoder, src/asr.py:214-221) -------------------------------------------------
  * preact [B, 4H] gate-major (i,f,g,o) = x.W_ih^T + h.W_hh^T + biases; gates [B,4H] activated (stash).        */
 B200ASR_API int b200asr_lstm_cell_fwd(const float* preact, const float* c_prev, float* gates, float* c, float* h, int B,
