@@ -182,7 +182,11 @@ __device__ __forceinline__ void fwd_group(const LstmParams& p, int g, int gt, in
             for (int q = 0; q < 4; ++q) acc[i][q] = 0.f;
 
         if (step > 0) {
-            mbar_wait(&full[kq], (uint32_t)((step - 1) & 1));
+            // warp-uniform wait: the 4 K-chunk lanes of a warp need all 4 chunks (a per-lane wait would diverge the
+            // warp and serialise the four K-chunk loops)
+#pragma unroll
+            for (int c = 0; c < LSTM_NCHUNK; ++c) mbar_wait(&full[c], (uint32_t)((step - 1) & 1));
+            __syncwarp();
             if (trc) LSTM_TRACE(1);
             if (has_tile) {
                 const float4* hp = reinterpret_cast<const float4*>(hsg + (size_t)kq * chunk_stride + bo * R);
@@ -372,7 +376,9 @@ __device__ __forceinline__ void bwd_group(const LstmParams& p, int g, int gt, in
             float part[R];
 #pragma unroll
             for (int i = 0; i < R; ++i) part[i] = 0.f;
-            mbar_wait(&full[kq], (uint32_t)((step - 1) & 1));
+#pragma unroll
+            for (int c = 0; c < LSTM_NCHUNK; ++c) mbar_wait(&full[c], (uint32_t)((step - 1) & 1));
+            __syncwarp();
             const int s0 = min(nub, kq * SC), s1 = min(nub, s0 + SC);
             if (has_tile) {
                 for (int s = s0; s < s1; ++s) {
