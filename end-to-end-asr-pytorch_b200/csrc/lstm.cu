@@ -126,6 +126,24 @@ __device__ __forceinline__ void control_loop(const LstmParams& p, int T, unsigne
     }
 }
 
+// Packed fp32 FMA (Blackwell FFMA2): d.{lo,hi} = a.{lo,hi} * b + c.{lo,hi} with a scalar multiplier that ptxas
+// folds into the instruction's broadcast operand form - two FMAs per issue slot, which leaves issue bandwidth for
+// the shared-memory loads of the recurrence loops.
+__device__ __forceinline__ unsigned long long ffma2_vs(unsigned long long a, float b, unsigned long long c) {
+    unsigned long long bb, d;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(bb) : "f"(b));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(bb), "l"(c));
+    return d;
+}
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+    return d;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+
 // pick the RL consecutive rows [kq*RL, kq*RL + RL) of an R-row accumulator tile (RL = R/4) without dynamic indexing
 template <int R>
 __device__ __forceinline__ float pick_row(const float (&acc)[R][4], int kq, int i, int q) {
@@ -192,32 +210,48 @@ __device__ __forceinline__ void fwd_group(const LstmParams& p, int g, int gt, in
                 const float4* hp = reinterpret_cast<const float4*>(hsg + (size_t)kq * chunk_stride + bo * R);
                 const float4* wp = Ws + (size_t)kq * KC * UB + u;
                 const int hstride = Bh >> 2;  // float4 per k row
+                // accumulators as row pairs: accp[rp][q] = (acc[2rp][q], acc[2rp+1][q])
+                unsigned long long accp[R / 2][4];
+#pragma unroll
+                for (int rp = 0; rp < R / 2; ++rp)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) accp[rp][q] = 0ull;
                 float4 hv[RL], wv = wp[0];
 #pragma unroll
                 for (int j = 0; j < RL; ++j) hv[j] = hp[j];
-#pragma unroll 2
-                for (int kk = 0; kk < KC; ++kk) {
-                    // software pipelined: the loads of k+1 are in flight while the FMAs of k issue
-                    const int kn = (kk + 1 < KC) ? kk + 1 : kk;
-                    float4 hn[RL];
-                    const float4 wn = wp[(size_t)kn * UB];
+                // software pipelined: the loads of k+1 are in flight while the packed FMAs of k issue
+#pragma unroll 4
+                for (int kk = 1; kk <= KC; ++kk) {
+                    float4 hn[RL], wn;
+                    if (kk < KC) {
+                        hp += hstride;
+                        wp += UB;
+                        wn = wp[0];
 #pragma unroll
-                    for (int j = 0; j < RL; ++j) hn[j] = hp[(size_t)kn * hstride + j];
+                        for (int j = 0; j < RL; ++j) hn[j] = hp[j];
+                    }
 #pragma unroll
                     for (int j = 0; j < RL; ++j) {
-                        const float hr[4] = {hv[j].x, hv[j].y, hv[j].z, hv[j].w};
-#pragma unroll
-                        for (int r = 0; r < 4; ++r) {
-                            acc[j * 4 + r][0] = fmaf(hr[r], wv.x, acc[j * 4 + r][0]);
-                            acc[j * 4 + r][1] = fmaf(hr[r], wv.y, acc[j * 4 + r][1]);
-                            acc[j * 4 + r][2] = fmaf(hr[r], wv.z, acc[j * 4 + r][2]);
-                            acc[j * 4 + r][3] = fmaf(hr[r], wv.w, acc[j * 4 + r][3]);
-                        }
+                        const unsigned long long h01 = pack2(hv[j].x, hv[j].y), h23 = pack2(hv[j].z, hv[j].w);
+                        accp[2 * j][0] = ffma2_vs(h01, wv.x, accp[2 * j][0]);
+                        accp[2 * j][1] = ffma2_vs(h01, wv.y, accp[2 * j][1]);
+                        accp[2 * j][2] = ffma2_vs(h01, wv.z, accp[2 * j][2]);
+                        accp[2 * j][3] = ffma2_vs(h01, wv.w, accp[2 * j][3]);
+                        accp[2 * j + 1][0] = ffma2_vs(h23, wv.x, accp[2 * j + 1][0]);
+                        accp[2 * j + 1][1] = ffma2_vs(h23, wv.y, accp[2 * j + 1][1]);
+                        accp[2 * j + 1][2] = ffma2_vs(h23, wv.z, accp[2 * j + 1][2]);
+                        accp[2 * j + 1][3] = ffma2_vs(h23, wv.w, accp[2 * j + 1][3]);
                     }
-                    wv = wn;
+                    if (kk < KC) {
+                        wv = wn;
 #pragma unroll
-                    for (int j = 0; j < RL; ++j) hv[j] = hn[j];
+                        for (int j = 0; j < RL; ++j) hv[j] = hn[j];
+                    }
                 }
+#pragma unroll
+                for (int rp = 0; rp < R / 2; ++rp)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) unpack2(accp[rp][q], acc[2 * rp][q], acc[2 * rp + 1][q]);
             }
             if (trc) LSTM_TRACE(3);
             // reduce the 4 K-chunks held by lanes l, l^8, l^16, l^24
@@ -434,43 +468,55 @@ __device__ __forceinline__ void bwd_group(const LstmParams& p, int g, int gt, in
             for (int t2 = gt; t2 < ntiles; t2 += LSTM_GTHREADS) {
                 const int kq2 = t2 % NKQ;
                 const int bo2 = t2 / NKQ;
-                float a[R][8];
+                // packed accumulators: a2[i][j] = (partial[row i][k0 + 2j], partial[row i][k0 + 2j + 1])
+                unsigned long long a2[R][4];
 #pragma unroll
                 for (int i = 0; i < R; ++i)
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) a[i][j] = 0.f;
+                    for (int j = 0; j < 4; ++j) a2[i][j] = 0ull;
                 const int C = 4 * UB;
-                const float* wbase = Wr + kq2 * 4;
-                const float* dbase = dgs + bo2 * R;
+                const float* wptr = Wr + kq2 * 4;
+                const float* dptr = dgs + bo2 * R;
                 float4 dcur[RL];
 #pragma unroll
-                for (int j = 0; j < RL; ++j) dcur[j] = *reinterpret_cast<const float4*>(dbase + j * 4);
-                float4 wa = *reinterpret_cast<const float4*>(wbase);
-                float4 wb = *reinterpret_cast<const float4*>(wbase + (H >> 1));
+                for (int j = 0; j < RL; ++j) dcur[j] = *reinterpret_cast<const float4*>(dptr + j * 4);
+                float4 wa = *reinterpret_cast<const float4*>(wptr);
+                float4 wb = *reinterpret_cast<const float4*>(wptr + (H >> 1));
 #pragma unroll 2
-                for (int c = 0; c < C; ++c) {
-                    const int cn = (c + 1 < C) ? c + 1 : c;
-                    float4 dnext[RL];
+                for (int c = 1; c <= C; ++c) {
+                    float4 dnext[RL], wan, wbn;
+                    if (c < C) {
+                        dptr += Bh;
+                        wptr += H;
 #pragma unroll
-                    for (int j = 0; j < RL; ++j) dnext[j] = *reinterpret_cast<const float4*>(dbase + (size_t)cn * Bh + j * 4);
-                    const float4 wan = *reinterpret_cast<const float4*>(wbase + (size_t)cn * H);
-                    const float4 wbn = *reinterpret_cast<const float4*>(wbase + (size_t)cn * H + (H >> 1));
+                        for (int j = 0; j < RL; ++j) dnext[j] = *reinterpret_cast<const float4*>(dptr + j * 4);
+                        wan = *reinterpret_cast<const float4*>(wptr);
+                        wbn = *reinterpret_cast<const float4*>(wptr + (H >> 1));
+                    }
+                    const unsigned long long w01 = pack2(wa.x, wa.y), w23 = pack2(wa.z, wa.w);
+                    const unsigned long long w45 = pack2(wb.x, wb.y), w67 = pack2(wb.z, wb.w);
 #pragma unroll
                     for (int j = 0; j < RL; ++j) {
                         const float dv[4] = {dcur[j].x, dcur[j].y, dcur[j].z, dcur[j].w};
 #pragma unroll
                         for (int r = 0; r < 4; ++r) {
-                            float* ar = a[j * 4 + r];
-                            ar[0] = fmaf(dv[r], wa.x, ar[0]); ar[1] = fmaf(dv[r], wa.y, ar[1]);
-                            ar[2] = fmaf(dv[r], wa.z, ar[2]); ar[3] = fmaf(dv[r], wa.w, ar[3]);
-                            ar[4] = fmaf(dv[r], wb.x, ar[4]); ar[5] = fmaf(dv[r], wb.y, ar[5]);
-                            ar[6] = fmaf(dv[r], wb.z, ar[6]); ar[7] = fmaf(dv[r], wb.w, ar[7]);
+                            a2[j * 4 + r][0] = ffma2_vs(w01, dv[r], a2[j * 4 + r][0]);
+                            a2[j * 4 + r][1] = ffma2_vs(w23, dv[r], a2[j * 4 + r][1]);
+                            a2[j * 4 + r][2] = ffma2_vs(w45, dv[r], a2[j * 4 + r][2]);
+                            a2[j * 4 + r][3] = ffma2_vs(w67, dv[r], a2[j * 4 + r][3]);
                         }
                     }
-                    wa = wan; wb = wbn;
+                    if (c < C) {
+                        wa = wan; wb = wbn;
 #pragma unroll
-                    for (int j = 0; j < RL; ++j) dcur[j] = dnext[j];
+                        for (int j = 0; j < RL; ++j) dcur[j] = dnext[j];
+                    }
                 }
+                float a[R][8];
+#pragma unroll
+                for (int i = 0; i < R; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) unpack2(a2[i][j], a[i][2 * j], a[i][2 * j + 1]);
                 // scatter to the destination inboxes: element (dst, src=ub, row, u')
 #pragma unroll
                 for (int r = 0; r < 2; ++r) {
