@@ -159,7 +159,8 @@ __device__ __forceinline__ float pick_row(const float (&acc)[R][4], int kq, int 
 // Forward compute group: 128 threads = 32 register tiles (4 gates x R rows) x 4 K-chunks.  lane = kq*8 + tile%8.
 template <int R>
 __device__ __forceinline__ void fwd_group(const LstmParams& p, int g, int gt, int dir, int bg, int ub, const float4* Ws,
-                                          const float* hsg, uint64_t* full, uint64_t* done, float* xbg) {
+                                          const float* hsg, uint64_t* full, uint64_t* done, float* xbg,
+                                          uint64_t* stagger) {
     constexpr int RL = R / 4;                 // rows each lane finishes
     const int H = p.H, UB = p.UB, T = p.T;
     const int Bh = p.Bc / p.NH;
@@ -200,6 +201,10 @@ __device__ __forceinline__ void fwd_group(const LstmParams& p, int g, int gt, in
             for (int q = 0; q < 4; ++q) acc[i][q] = 0.f;
 
         if (step > 0) {
+            // one-time stagger: group 1 enters its first K loop only after group 0 has left its own, so that the two
+            // groups run in anti-phase (one loops on the FMA pipes while the other exchanges state) instead of both
+            // waiting and both looping at the same time
+            if (step == 1 && g == 1 && p.NH == 2) mbar_wait(stagger, 0u);
             // warp-uniform wait: the 4 K-chunk lanes of a warp need all 4 chunks (a per-lane wait would diverge the
             // warp and serialise the four K-chunk loops)
 #pragma unroll
@@ -254,6 +259,10 @@ __device__ __forceinline__ void fwd_group(const LstmParams& p, int g, int gt, in
                     for (int q = 0; q < 4; ++q) unpack2(accp[rp][q], acc[2 * rp][q], acc[2 * rp + 1][q]);
             }
             if (trc) LSTM_TRACE(3);
+            if (step == 1 && g == 0) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(stagger);
+            }
             // reduce the 4 K-chunks held by lanes l, l^8, l^16, l^24
 #pragma unroll
             for (int i = 0; i < R; ++i)
@@ -310,6 +319,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) bilstm_fwd_kernel(LstmParams 
     float* hs = reinterpret_cast<float*>(Ws + (size_t)H * UB);                   // [NH][4 chunks, padded]
     uint64_t* full = reinterpret_cast<uint64_t*>(hs + 2 * ((size_t)LSTM_NCHUNK * (KC * (Bc / NH) + LSTM_CHUNK_PAD)));
     uint64_t* done = full + 2 * LSTM_NCHUNK;                                     // [2]
+    uint64_t* stagger = done + 2;                                                // [1]
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -325,6 +335,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) bilstm_fwd_kernel(LstmParams 
     if (tid == 0) {
         for (int i = 0; i < 2 * LSTM_NCHUNK; ++i) mbar_init(&full[i], 1);
         for (int i = 0; i < 2; ++i) mbar_init(&done[i], LSTM_GTHREADS / 32);
+        mbar_init(stagger, LSTM_GTHREADS / 32);
         mbar_fence_init();
     }
     __syncthreads();
@@ -354,10 +365,10 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) bilstm_fwd_kernel(LstmParams 
     const int gt = tid - g * LSTM_GTHREADS;
     if (p.R == 8)
         fwd_group<8>(p, g, gt, dir, bg, ub, Ws, hs + (size_t)g * hs_half, &full[g * LSTM_NCHUNK], &done[g],
-                     xb + (size_t)g * 2 * half_elems);
+                     xb + (size_t)g * 2 * half_elems, stagger);
     else
         fwd_group<4>(p, g, gt, dir, bg, ub, Ws, hs + (size_t)g * hs_half, &full[g * LSTM_NCHUNK], &done[g],
-                     xb + (size_t)g * 2 * half_elems);
+                     xb + (size_t)g * 2 * half_elems, stagger);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -656,7 +667,7 @@ static int halves_for(int Bc) { return (Bc % 8 == 0) ? 2 : 1; }
 static int rows_for(int Bc) { return ((Bc / halves_for(Bc)) % 8 == 0) ? 8 : 4; }
 static size_t smem_fwd_bytes(int H, int UB, int Bc) {
     const int Bh = Bc / halves_for(Bc);
-    return (size_t)H * UB * 16 + 2 * ((size_t)H * Bh + LSTM_NCHUNK * LSTM_CHUNK_PAD) * 4 + (2 * LSTM_NCHUNK + 2) * 8 + 128;
+    return (size_t)H * UB * 16 + 2 * ((size_t)H * Bh + LSTM_NCHUNK * LSTM_CHUNK_PAD) * 4 + (2 * LSTM_NCHUNK + 3) * 8 + 128;
 }
 static size_t smem_bwd_bytes(int H, int UB, int Bc) {
     return (size_t)4 * UB * H * 4 + (size_t)Bc * H * 4 + (size_t)4 * UB * Bc * 4 + (2 * LSTM_NCHUNK + 2) * 8 + 128;
