@@ -221,38 +221,39 @@ __device__ __forceinline__ void fwd_group(const LstmParams& p, int g, int gt, in
                 for (int rp = 0; rp < R / 2; ++rp)
 #pragma unroll
                     for (int q = 0; q < 4; ++q) accp[rp][q] = 0ull;
-                float4 hv[RL], wv = wp[0];
-#pragma unroll
-                for (int j = 0; j < RL; ++j) hv[j] = hp[j];
-                // software pipelined: the loads of k+1 are in flight while the packed FMAs of k issue
-#pragma unroll 4
-                for (int kk = 1; kk <= KC; ++kk) {
-                    float4 hn[RL], wn;
-                    if (kk < KC) {
-                        hp += hstride;
-                        wp += UB;
-                        wn = wp[0];
-#pragma unroll
-                        for (int j = 0; j < RL; ++j) hn[j] = hp[j];
-                    }
-#pragma unroll
-                    for (int j = 0; j < RL; ++j) {
-                        const unsigned long long h01 = pack2(hv[j].x, hv[j].y), h23 = pack2(hv[j].z, hv[j].w);
-                        accp[2 * j][0] = ffma2_vs(h01, wv.x, accp[2 * j][0]);
-                        accp[2 * j][1] = ffma2_vs(h01, wv.y, accp[2 * j][1]);
-                        accp[2 * j][2] = ffma2_vs(h01, wv.z, accp[2 * j][2]);
-                        accp[2 * j][3] = ffma2_vs(h01, wv.w, accp[2 * j][3]);
-                        accp[2 * j + 1][0] = ffma2_vs(h23, wv.x, accp[2 * j + 1][0]);
-                        accp[2 * j + 1][1] = ffma2_vs(h23, wv.y, accp[2 * j + 1][1]);
-                        accp[2 * j + 1][2] = ffma2_vs(h23, wv.z, accp[2 * j + 1][2]);
-                        accp[2 * j + 1][3] = ffma2_vs(h23, wv.w, accp[2 * j + 1][3]);
-                    }
-                    if (kk < KC) {
-                        wv = wn;
-#pragma unroll
-                        for (int j = 0; j < RL; ++j) hv[j] = hn[j];
-                    }
+                // explicit register double buffering (A/B) over pairs of k, last pair peeled: every load is
+                // unconditional and is issued one full FMA block (16 packed FMAs) ahead of its first use
+#define LSTM_FWD_LOAD(hreg, wreg, k_)                                              \
+    {                                                                              \
+        wreg = wp[(size_t)(k_) * UB];                                              \
+        _Pragma("unroll") for (int j = 0; j < RL; ++j) hreg[j] = hp[(size_t)(k_) * hstride + j]; \
+    }
+#define LSTM_FWD_FMA(hreg, wreg)                                                   \
+    _Pragma("unroll") for (int j = 0; j < RL; ++j) {                               \
+        const unsigned long long h01 = pack2(hreg[j].x, hreg[j].y), h23 = pack2(hreg[j].z, hreg[j].w); \
+        accp[2 * j][0] = ffma2_vs(h01, wreg.x, accp[2 * j][0]);                    \
+        accp[2 * j][1] = ffma2_vs(h01, wreg.y, accp[2 * j][1]);                    \
+        accp[2 * j][2] = ffma2_vs(h01, wreg.z, accp[2 * j][2]);                    \
+        accp[2 * j][3] = ffma2_vs(h01, wreg.w, accp[2 * j][3]);                    \
+        accp[2 * j + 1][0] = ffma2_vs(h23, wreg.x, accp[2 * j + 1][0]);            \
+        accp[2 * j + 1][1] = ffma2_vs(h23, wreg.y, accp[2 * j + 1][1]);            \
+        accp[2 * j + 1][2] = ffma2_vs(h23, wreg.z, accp[2 * j + 1][2]);            \
+        accp[2 * j + 1][3] = ffma2_vs(h23, wreg.w, accp[2 * j + 1][3]);            \
+    }
+                float4 hA[RL], hB[RL], wA, wB;
+                LSTM_FWD_LOAD(hA, wA, 0)
+#pragma unroll 2
+                for (int kk = 0; kk < KC - 2; kk += 2) {
+                    LSTM_FWD_LOAD(hB, wB, kk + 1)
+                    LSTM_FWD_FMA(hA, wA)
+                    LSTM_FWD_LOAD(hA, wA, kk + 2)
+                    LSTM_FWD_FMA(hB, wB)
                 }
+                LSTM_FWD_LOAD(hB, wB, KC - 1)
+                LSTM_FWD_FMA(hA, wA)
+                LSTM_FWD_FMA(hB, wB)
+#undef LSTM_FWD_LOAD
+#undef LSTM_FWD_FMA
 #pragma unroll
                 for (int rp = 0; rp < R / 2; ++rp)
 #pragma unroll
@@ -488,41 +489,41 @@ __device__ __forceinline__ void bwd_group(const LstmParams& p, int g, int gt, in
                 const int C = 4 * UB;
                 const float* wptr = Wr + kq2 * 4;
                 const float* dptr = dgs + bo2 * R;
-                float4 dcur[RL];
-#pragma unroll
-                for (int j = 0; j < RL; ++j) dcur[j] = *reinterpret_cast<const float4*>(dptr + j * 4);
-                float4 wa = *reinterpret_cast<const float4*>(wptr);
-                float4 wb = *reinterpret_cast<const float4*>(wptr + (H >> 1));
-#pragma unroll 2
-                for (int c = 1; c <= C; ++c) {
-                    float4 dnext[RL], wan, wbn;
-                    if (c < C) {
-                        dptr += Bh;
-                        wptr += H;
-#pragma unroll
-                        for (int j = 0; j < RL; ++j) dnext[j] = *reinterpret_cast<const float4*>(dptr + j * 4);
-                        wan = *reinterpret_cast<const float4*>(wptr);
-                        wbn = *reinterpret_cast<const float4*>(wptr + (H >> 1));
-                    }
-                    const unsigned long long w01 = pack2(wa.x, wa.y), w23 = pack2(wa.z, wa.w);
-                    const unsigned long long w45 = pack2(wb.x, wb.y), w67 = pack2(wb.z, wb.w);
-#pragma unroll
-                    for (int j = 0; j < RL; ++j) {
-                        const float dv[4] = {dcur[j].x, dcur[j].y, dcur[j].z, dcur[j].w};
-#pragma unroll
-                        for (int r = 0; r < 4; ++r) {
-                            a2[j * 4 + r][0] = ffma2_vs(w01, dv[r], a2[j * 4 + r][0]);
-                            a2[j * 4 + r][1] = ffma2_vs(w23, dv[r], a2[j * 4 + r][1]);
-                            a2[j * 4 + r][2] = ffma2_vs(w45, dv[r], a2[j * 4 + r][2]);
-                            a2[j * 4 + r][3] = ffma2_vs(w67, dv[r], a2[j * 4 + r][3]);
-                        }
-                    }
-                    if (c < C) {
-                        wa = wan; wb = wbn;
-#pragma unroll
-                        for (int j = 0; j < RL; ++j) dcur[j] = dnext[j];
-                    }
+#define LSTM_BWD_LOAD(dreg, wareg, wbreg, c_)                                       \
+    {                                                                              \
+        wareg = *reinterpret_cast<const float4*>(wptr + (size_t)(c_) * H);         \
+        wbreg = *reinterpret_cast<const float4*>(wptr + (size_t)(c_) * H + (H >> 1)); \
+        _Pragma("unroll") for (int j = 0; j < RL; ++j)                             \
+            dreg[j] = *reinterpret_cast<const float4*>(dptr + (size_t)(c_) * Bh + j * 4); \
+    }
+#define LSTM_BWD_FMA(dreg, wareg, wbreg)                                           \
+    {                                                                              \
+        const unsigned long long w01 = pack2(wareg.x, wareg.y), w23 = pack2(wareg.z, wareg.w); \
+        const unsigned long long w45 = pack2(wbreg.x, wbreg.y), w67 = pack2(wbreg.z, wbreg.w); \
+        _Pragma("unroll") for (int j = 0; j < RL; ++j) {                           \
+            const float dv[4] = {dreg[j].x, dreg[j].y, dreg[j].z, dreg[j].w};      \
+            _Pragma("unroll") for (int r = 0; r < 4; ++r) {                        \
+                a2[j * 4 + r][0] = ffma2_vs(w01, dv[r], a2[j * 4 + r][0]);         \
+                a2[j * 4 + r][1] = ffma2_vs(w23, dv[r], a2[j * 4 + r][1]);         \
+                a2[j * 4 + r][2] = ffma2_vs(w45, dv[r], a2[j * 4 + r][2]);         \
+                a2[j * 4 + r][3] = ffma2_vs(w67, dv[r], a2[j * 4 + r][3]);         \
+            }                                                                      \
+        }                                                                          \
+    }
+                float4 dA[RL], dB[RL], waA, wbA, waB, wbB;
+                LSTM_BWD_LOAD(dA, waA, wbA, 0)
+#pragma unroll 1
+                for (int c = 0; c < C - 2; c += 2) {
+                    LSTM_BWD_LOAD(dB, waB, wbB, c + 1)
+                    LSTM_BWD_FMA(dA, waA, wbA)
+                    LSTM_BWD_LOAD(dA, waA, wbA, c + 2)
+                    LSTM_BWD_FMA(dB, waB, wbB)
                 }
+                LSTM_BWD_LOAD(dB, waB, wbB, C - 1)
+                LSTM_BWD_FMA(dA, waA, wbA)
+                LSTM_BWD_FMA(dB, waB, wbB)
+#undef LSTM_BWD_LOAD
+#undef LSTM_BWD_FMA
                 float a[R][8];
 #pragma unroll
                 for (int i = 0; i < R; ++i)
