@@ -159,10 +159,12 @@ class FbankFrontEnd(torch.nn.Module):
             feat = fb
         else:
             feat = torch.empty((B, t_max, self.feat_dim), device=wave.device, dtype=torch.float32)
+            ws_bytes = lib.b200asr_delta_cmvn_workspace_bytes(B, t_max, self.num_mel, self.delta_order)
+            ws = torch.empty(max(ws_bytes, 8), device=wave.device, dtype=torch.uint8)
             with L.timed("delta_cmvn_fwd", 4 * B * t_max * (self.num_mel + self.feat_dim)):
                 L.check(lib.b200asr_delta_cmvn_fwd(
                     L.ptr(fb), L.ptr(nfr), B, t_max, self.num_mel, self.delta_order, self.delta_window,
-                    int(self.apply_cmvn), 1e-10, L.ptr(feat), L.stream()), "delta_cmvn_fwd")
+                    int(self.apply_cmvn), 1e-10, L.ptr(feat), L.ptr(ws), ws_bytes, L.stream()), "delta_cmvn_fwd")
         if return_fbank:
             return feat, nfr.to(torch.int64), fb
         return feat, nfr.to(torch.int64)

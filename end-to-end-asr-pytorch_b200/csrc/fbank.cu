@@ -3,8 +3,9 @@
 //   fbank_kernel      : framing + DC removal + pre-emphasis + window + 512-pt real FFT (shared
 //                       memory Stockham radix-4 on the packed 256-pt complex signal) + power
 //                       spectrum + triangular mel filters + log  -> [B, t_max, n_mel]
-//   delta_cmvn_kernel : delta / delta-delta (zero padded per utterance) + per-utterance CMVN
-//                       (unbiased std) + channel-major interleave -> [B, t_max, n_mel*(order+1)]
+//   delta_stats_kernel / delta_norm_kernel : delta / delta-delta (zero padded per utterance) + per-utterance
+//                       CMVN (unbiased std, fp64 partial sums per 64-frame chunk, reduced in a fixed order) +
+//                       channel-major interleave -> [B, t_max, n_mel*(order+1)]; grid (T/64, B)
 //
 // Reference behaviour restated (not copied):  /root/reference/src/audio.py:25-27,51-77,85-89,101-109
 // and torchaudio/compliance/kaldi.py:44-83 (framing), 154-217 (window), 436-511 (mel), 591-646 (fbank).
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(FB_WARPS * 32) fbank_kernel(FbankParams p) {
 constexpr int DC_MAX_ORDER = 2;
 constexpr int DC_MAX_TAPS = 33;
 constexpr int DC_COLS = 128;   // n_mel*(order+1) padded column count handled per CTA pass
-constexpr int DC_ROWS = 4;     // row phases (blockDim = DC_COLS*DC_ROWS)
+constexpr int DC_ROWS = 2;     // row phases (blockDim = DC_COLS*DC_ROWS)
 
 struct DeltaParams {
     const float* fb;
@@ -220,59 +221,84 @@ __device__ __forceinline__ float delta_value(const DeltaParams& p, const float* 
     return acc;
 }
 
-__global__ void __launch_bounds__(DC_COLS* DC_ROWS) delta_cmvn_kernel(DeltaParams p) {
-    __shared__ double s_red[DC_ROWS][DC_COLS];
-    __shared__ float s_mean[DC_COLS], s_rstd[DC_COLS];
-    const int b = blockIdx.x;
+// Pass 1: per (utterance, time chunk) partial sums of x and x^2 (fp64) for every output column.
+// Pass 2: every CTA re-reduces the chunk partials of its utterance in a fixed order (deterministic), then
+// normalises and writes its own time chunk.  Both passes recompute the (cheap) delta taps from the L2-resident fbank.
+constexpr int DC_TCHUNK = 64;
+
+__global__ void __launch_bounds__(DC_COLS* DC_ROWS) delta_stats_kernel(DeltaParams p, double* __restrict__ partial,
+                                                                      int nchunk) {
+    __shared__ double s_red[2][DC_ROWS][DC_COLS];
+    const int b = blockIdx.y, ch = blockIdx.x;
     const int D = p.n_mel * (p.order + 1);
     const int m = p.n_frames[b];
     const float* fb = p.fb + (long long)b * p.t_max * p.n_mel;
-    float* out = p.out + (long long)b * p.t_max * D;
-    const int r = threadIdx.x / DC_COLS;
-    const int cl = threadIdx.x % DC_COLS;
-
+    const int r = threadIdx.x / DC_COLS, cl = threadIdx.x % DC_COLS;
+    const int t0 = ch * DC_TCHUNK, t1 = min(m, t0 + DC_TCHUNK);
     for (int c0 = 0; c0 < D; c0 += DC_COLS) {
         const int col = c0 + cl;
         const bool act = col < D;
         const int o = act ? col / p.n_mel : 0;
         const int bin = act ? col - o * p.n_mel : 0;
-        float mean = 0.f, denom = 1.f;
-        if (p.apply_cmvn) {
-            double s = 0.0;
-            if (act)
-                for (int t = r; t < m; t += DC_ROWS) s += (double)delta_value(p, fb, m, t, o, bin);
-            s_red[r][cl] = s;
-            __syncthreads();
-            if (r == 0) {
-                double tot = 0.0;
-                for (int q = 0; q < DC_ROWS; ++q) tot += s_red[q][cl];
-                s_mean[cl] = (float)(tot / (double)m);
+        double s = 0.0, ss = 0.0;
+        if (act)
+            for (int t = t0 + r; t < t1; t += DC_ROWS) {
+                const double v = (double)delta_value(p, fb, m, t, o, bin);
+                s += v;
+                ss += v * v;
             }
-            __syncthreads();
-            mean = s_mean[cl];
-            double ss = 0.0;
-            if (act)
-                for (int t = r; t < m; t += DC_ROWS) {
-                    const double d = (double)(delta_value(p, fb, m, t, o, bin) - mean);
-                    ss += d * d;
-                }
-            s_red[r][cl] = ss;
-            __syncthreads();
-            if (r == 0) {
-                double tot = 0.0;
-                for (int q = 0; q < DC_ROWS; ++q) tot += s_red[q][cl];
-                // unbiased std (torch.std default); m == 1 gives 0/0 = NaN exactly like torch
-                s_rstd[cl] = (float)sqrt(tot / (double)(m - 1));
-            }
-            __syncthreads();
-            denom = p.eps + s_rstd[cl];
+        s_red[0][r][cl] = s;
+        s_red[1][r][cl] = ss;
+        __syncthreads();
+        if (r == 0 && act) {
+            double ts = 0.0, tss = 0.0;
+            for (int q = 0; q < DC_ROWS; ++q) { ts += s_red[0][q][cl]; tss += s_red[1][q][cl]; }
+            double* dst = partial + (((long long)b * nchunk + ch) * D + col) * 2;
+            dst[0] = ts;
+            dst[1] = tss;
         }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(DC_COLS* DC_ROWS) delta_norm_kernel(DeltaParams p, const double* __restrict__ partial,
+                                                                     int nchunk) {
+    __shared__ float s_mean[DC_COLS], s_den[DC_COLS];
+    const int b = blockIdx.y, ch = blockIdx.x;
+    const int D = p.n_mel * (p.order + 1);
+    const int m = p.n_frames[b];
+    const float* fb = p.fb + (long long)b * p.t_max * p.n_mel;
+    float* out = p.out + (long long)b * p.t_max * D;
+    const int r = threadIdx.x / DC_COLS, cl = threadIdx.x % DC_COLS;
+    const int t0 = ch * DC_TCHUNK, t1 = min(p.t_max, t0 + DC_TCHUNK);
+    const int mchunks = (m + DC_TCHUNK - 1) / DC_TCHUNK;
+    for (int c0 = 0; c0 < D; c0 += DC_COLS) {
+        const int col = c0 + cl;
+        const bool act = col < D;
+        const int o = act ? col / p.n_mel : 0;
+        const int bin = act ? col - o * p.n_mel : 0;
+        if (p.apply_cmvn && r == 0 && act) {
+            double ts = 0.0, tss = 0.0;
+            for (int q = 0; q < mchunks; ++q) {
+                const double* src = partial + (((long long)b * nchunk + q) * D + col) * 2;
+                ts += src[0];
+                tss += src[1];
+            }
+            const double mean = ts / (double)m;
+            // unbiased variance (torch.std default); m == 1 gives 0/0 = NaN exactly like torch
+            const double var = (tss - ts * mean) / (double)(m - 1);
+            s_mean[cl] = (float)mean;
+            s_den[cl] = p.eps + (float)sqrt(var > 0.0 || !(var == var) ? var : 0.0);
+        }
+        __syncthreads();
         if (act) {
-            for (int t = r; t < p.t_max; t += DC_ROWS) {
+            const float mean = p.apply_cmvn ? s_mean[cl] : 0.f;
+            const float den = p.apply_cmvn ? s_den[cl] : 1.f;
+            for (int t = t0 + r; t < t1; t += DC_ROWS) {
                 float v = 0.f;
                 if (t < m) {
                     v = delta_value(p, fb, m, t, o, bin);
-                    if (p.apply_cmvn) v = (v - mean) / denom;
+                    if (p.apply_cmvn) v = (v - mean) / den;
                 }
                 out[(long long)t * D + col] = v;
             }
@@ -346,9 +372,14 @@ static int build_delta_filters(int order, int window, float filt[DC_MAX_ORDER + 
     return 0;
 }
 
+extern "C" size_t b200asr_delta_cmvn_workspace_bytes(int B, int t_max, int n_mel, int delta_order) {
+    const size_t nchunk = ((size_t)t_max + DC_TCHUNK - 1) / DC_TCHUNK;
+    return (size_t)B * (nchunk ? nchunk : 1) * n_mel * (delta_order + 1) * 2 * sizeof(double);
+}
+
 extern "C" int b200asr_delta_cmvn_fwd(const float* fbank, const int* n_frames, int B, int t_max, int n_mel,
                                       int delta_order, int delta_window, int apply_cmvn, float cmvn_eps,
-                                      float* feat, b200asr_stream stream) {
+                                      float* feat, void* workspace, size_t workspace_bytes, b200asr_stream stream) {
     B200_REQUIRE(fbank && n_frames && feat, "delta_cmvn: null pointer");
     B200_REQUIRE(B > 0 && t_max >= 0 && n_mel > 0, "delta_cmvn: bad sizes");
     DeltaParams p;
@@ -358,7 +389,15 @@ extern "C" int b200asr_delta_cmvn_fwd(const float* fbank, const int* n_frames, i
     p.fb = fbank; p.n_frames = n_frames; p.B = B; p.t_max = t_max; p.n_mel = n_mel; p.order = delta_order;
     p.taps = taps; p.pad = (taps - 1) / 2; p.apply_cmvn = apply_cmvn; p.eps = cmvn_eps; p.out = feat;
     if (t_max == 0) return B200_OK;
-    delta_cmvn_kernel<<<B, DC_COLS * DC_ROWS, 0, (cudaStream_t)stream>>>(p);
-    B200_LAUNCH_CHECK("delta_cmvn_kernel");
+    const int nchunk = (t_max + DC_TCHUNK - 1) / DC_TCHUNK;
+    double* partial = reinterpret_cast<double*>(workspace);
+    if (apply_cmvn) {
+        B200_REQUIRE(workspace && workspace_bytes >= b200asr_delta_cmvn_workspace_bytes(B, t_max, n_mel, delta_order),
+                     "delta_cmvn: workspace too small");
+        delta_stats_kernel<<<dim3(nchunk, B), DC_COLS * DC_ROWS, 0, (cudaStream_t)stream>>>(p, partial, nchunk);
+        B200_LAUNCH_CHECK("delta_stats_kernel");
+    }
+    delta_norm_kernel<<<dim3(nchunk, B), DC_COLS * DC_ROWS, 0, (cudaStream_t)stream>>>(p, partial, nchunk);
+    B200_LAUNCH_CHECK("delta_norm_kernel");
     return B200_OK;
 }

@@ -55,9 +55,10 @@ B200ASR_API int b200asr_fbank_fwd(const float* wave, const int* wave_len, int B,
  * replaces src/audio.py:51-54,57-77 (Delta), :25-27 (CMVN, unbiased std, eps added to std), :85-89
  * (Postprocess).  feat [B, t_max, n_mel*(delta_order+1)], rows >= n_frames[b] are zero (pad_sequence,
  * src/data.py:39).                                                                                          */
+B200ASR_API size_t b200asr_delta_cmvn_workspace_bytes(int B, int t_max, int n_mel, int delta_order);
 B200ASR_API int b200asr_delta_cmvn_fwd(const float* fbank, const int* n_frames, int B, int t_max, int n_mel,
-                           int delta_order, int delta_window, int apply_cmvn, float cmvn_eps, float* feat,
-                           b200asr_stream stream);
+                                       int delta_order, int delta_window, int apply_cmvn, float cmvn_eps,
+                                       float* feat, void* workspace, size_t workspace_bytes, b200asr_stream stream);
 
 /* ---- K9: log-softmax over the vocabulary (src/asr.py:96) -------------------------------------------------
  * log_probs may alias logits.  lse [n_rows] and argmax [n_rows] (int64; util.py:117-118 / test_asr.py:116-118)

@@ -3,7 +3,7 @@ import importlib, sys, os, torch, numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 pkg = importlib.import_module("end-to-end-asr-pytorch_b200")
 L = pkg.lib; lib = L.load()
-B, T, I, H = 64, 200, 1024, 512
+B, T, I, H = int(os.environ.get("B", 64)), 200, 1024, 512
 torch.manual_seed(0)
 ref = torch.nn.LSTM(I, H, bidirectional=True, batch_first=True)
 params = [p.detach().cuda() for p in ref.parameters()]
