@@ -160,7 +160,7 @@ __device__ __forceinline__ float pick_row(const float (&acc)[R][4], int kq, int 
 template <int R>
 __device__ __forceinline__ void fwd_group(const LstmParams& p, int g, int gt, int dir, int bg, int ub, const float4* Ws,
                                           const float* hsg, uint64_t* full, uint64_t* done, float* xbg,
-                                          uint64_t* stagger) {
+                                          uint64_t* turn) {
     constexpr int RL = R / 4;                 // rows each lane finishes
     const int H = p.H, UB = p.UB, T = p.T;
     const int Bh = p.Bc / p.NH;
@@ -201,10 +201,13 @@ __device__ __forceinline__ void fwd_group(const LstmParams& p, int g, int gt, in
             for (int q = 0; q < 4; ++q) acc[i][q] = 0.f;
 
         if (step > 0) {
-            // one-time stagger: group 1 enters its first K loop only after group 0 has left its own, so that the two
-            // groups run in anti-phase (one loops on the FMA pipes while the other exchanges state) instead of both
-            // waiting and both looping at the same time
-            if (step == 1 && g == 1 && p.NH == 2) mbar_wait(stagger, 0u);
+            // Turn taking: the two groups of a CTA alternate on the FMA pipes (A, B, A, B, ...).  A group's loop runs
+            // ~1.6x faster alone than next to the other group's loop, and in strict alternation each group's state
+            // exchange (~5.6k cycles) is hidden behind the other group's loop instead of both groups waiting at once.
+            if (p.NH == 2) {
+                if (g == 1) mbar_wait(&turn[1], (uint32_t)((step - 1) & 1));
+                else if (step >= 2) mbar_wait(&turn[0], (uint32_t)(step & 1));
+            }
             // warp-uniform wait: the 4 K-chunk lanes of a warp need all 4 chunks (a per-lane wait would diverge the
             // warp and serialise the four K-chunk loops)
 #pragma unroll
@@ -260,9 +263,9 @@ __device__ __forceinline__ void fwd_group(const LstmParams& p, int g, int gt, in
                     for (int q = 0; q < 4; ++q) unpack2(accp[rp][q], acc[2 * rp][q], acc[2 * rp + 1][q]);
             }
             if (trc) LSTM_TRACE(3);
-            if (step == 1 && g == 0) {
+            if (p.NH == 2) {             // hand the FMA pipes to the other group
                 __syncwarp();
-                if (lane == 0) mbar_arrive(stagger);
+                if (lane == 0) mbar_arrive(&turn[1 - g]);
             }
             // reduce the 4 K-chunks held by lanes l, l^8, l^16, l^24
 #pragma unroll
@@ -276,7 +279,8 @@ __device__ __forceinline__ void fwd_group(const LstmParams& p, int g, int gt, in
                 }
             if (trc) LSTM_TRACE(4);
         }
-        float hq[RL];
+        float hq[RL], cq[RL];
+        float4 gq[RL];
 #pragma unroll
         for (int i = 0; i < RL; ++i) {
             hq[i] = 0.f;
@@ -288,14 +292,12 @@ __device__ __forceinline__ void fwd_group(const LstmParams& p, int g, int gt, in
                 const float og = sigmoidf_(gx[i].w + pick_row<R>(acc, kq, i, 3));
                 const float c = fmaf(fg, c_reg[i], ig * gg);
                 c_reg[i] = c;
-                const float h = og * tanhf(c);
-                hq[i] = h;
-                const size_t row = ((size_t)dir * p.B + b) * T + tt;
-                *reinterpret_cast<float4*>(p.gates + (row * H + ug) * 4) = make_float4(ig, fg, gg, og);
-                p.cst[row * H + ug] = c;
-                p.out[((size_t)b * T + tt) * (p.ndir * H) + (size_t)dir * H + ug] = h;
+                hq[i] = og * tanhf(c);
+                cq[i] = c;
+                gq[i] = make_float4(ig, fg, gg, og);
             }
         }
+        // publish the new state FIRST (it is on the critical path of every peer CTA), then write the stash
         if (step + 1 < T) {
             if (has_tile) {
                 float* dstp = xbg + (size_t)(step & 1) * half_elems + (size_t)ug * Bh + bl0;
@@ -305,6 +307,16 @@ __device__ __forceinline__ void fwd_group(const LstmParams& p, int g, int gt, in
             __syncwarp();
             if (lane == 0) mbar_arrive(done);
             if (trc) LSTM_TRACE(5);
+        }
+#pragma unroll
+        for (int i = 0; i < RL; ++i) {
+            const int b = bglob0 + i;
+            if (has_tile && b < p.B) {
+                const size_t row = ((size_t)dir * p.B + b) * T + tt;
+                *reinterpret_cast<float4*>(p.gates + (row * H + ug) * 4) = gq[i];
+                p.cst[row * H + ug] = cq[i];
+                p.out[((size_t)b * T + tt) * (p.ndir * H) + (size_t)dir * H + ug] = hq[i];
+            }
         }
     }
 }
@@ -320,7 +332,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) bilstm_fwd_kernel(LstmParams 
     float* hs = reinterpret_cast<float*>(Ws + (size_t)H * UB);                   // [NH][4 chunks, padded]
     uint64_t* full = reinterpret_cast<uint64_t*>(hs + 2 * ((size_t)LSTM_NCHUNK * (KC * (Bc / NH) + LSTM_CHUNK_PAD)));
     uint64_t* done = full + 2 * LSTM_NCHUNK;                                     // [2]
-    uint64_t* stagger = done + 2;                                                // [1]
+    uint64_t* turn = done + 2;                                                   // [2] FMA-loop turn taking
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -336,7 +348,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) bilstm_fwd_kernel(LstmParams 
     if (tid == 0) {
         for (int i = 0; i < 2 * LSTM_NCHUNK; ++i) mbar_init(&full[i], 1);
         for (int i = 0; i < 2; ++i) mbar_init(&done[i], LSTM_GTHREADS / 32);
-        mbar_init(stagger, LSTM_GTHREADS / 32);
+        for (int i = 0; i < 2; ++i) mbar_init(&turn[i], LSTM_GTHREADS / 32);
         mbar_fence_init();
     }
     __syncthreads();
@@ -366,17 +378,18 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) bilstm_fwd_kernel(LstmParams 
     const int gt = tid - g * LSTM_GTHREADS;
     if (p.R == 8)
         fwd_group<8>(p, g, gt, dir, bg, ub, Ws, hs + (size_t)g * hs_half, &full[g * LSTM_NCHUNK], &done[g],
-                     xb + (size_t)g * 2 * half_elems, stagger);
+                     xb + (size_t)g * 2 * half_elems, turn);
     else
         fwd_group<4>(p, g, gt, dir, bg, ub, Ws, hs + (size_t)g * hs_half, &full[g * LSTM_NCHUNK], &done[g],
-                     xb + (size_t)g * 2 * half_elems, stagger);
+                     xb + (size_t)g * 2 * half_elems, turn);
 }
 
 // ------------------------------------------------------------------------------------------
 // Backward compute group.
 template <int R>
 __device__ __forceinline__ void bwd_group(const LstmParams& p, int g, int gt, int dir, int bg, int ub, const float* Wr,
-                                          const float* inb, float* dgs, uint64_t* full, uint64_t* done, float* xbg) {
+                                          const float* inb, float* dgs, uint64_t* full, uint64_t* done, float* xbg,
+                                          uint64_t* turn) {
     constexpr int RL = R / 4;
     const int H = p.H, UB = p.UB, T = p.T, nub = p.nub;
     const int Bh = p.Bc / p.NH;
@@ -473,6 +486,11 @@ __device__ __forceinline__ void bwd_group(const LstmParams& p, int g, int gt, in
         }
         named_bar_sync(1 + g, LSTM_GTHREADS);              // the dG tile of this step is complete
         if (step + 1 < T) {
+            // turn taking on the FMA pipes (see the forward kernel): the groups alternate on this GEMM
+            if (p.NH == 2) {
+                if (g == 1) mbar_wait(&turn[1], (uint32_t)(step & 1));
+                else if (step >= 1) mbar_wait(&turn[0], (uint32_t)((step - 1) & 1));
+            }
             // partial[b][k] = sum_c dGs[c][b] * Wr[c][k]; thread tiles of R rows x (2 strided float4 of k)
             const int NKQ = H / 8;
             const int ntiles = NKQ * NBO;
@@ -553,7 +571,10 @@ __device__ __forceinline__ void bwd_group(const LstmParams& p, int g, int gt, in
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(done);
+            if (lane == 0) {
+                if (p.NH == 2) mbar_arrive(&turn[1 - g]);
+                mbar_arrive(done);
+            }
         }
     }
 }
@@ -568,6 +589,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) bilstm_bwd_kernel(LstmParams 
     float* dGs = inbox + (size_t)Bc * H;                         // [NH][4UB*Bh]
     uint64_t* full = reinterpret_cast<uint64_t*>(dGs + (size_t)4 * UB * Bc);
     uint64_t* done = full + 2 * LSTM_NCHUNK;
+    uint64_t* turn = done + 2;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -584,6 +606,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) bilstm_bwd_kernel(LstmParams 
     if (tid == 0) {
         for (int i = 0; i < 2 * LSTM_NCHUNK; ++i) mbar_init(&full[i], 1);
         for (int i = 0; i < 2; ++i) mbar_init(&done[i], LSTM_GTHREADS / 32);
+        for (int i = 0; i < 2; ++i) mbar_init(&turn[i], LSTM_GTHREADS / 32);
         mbar_fence_init();
     }
     __syncthreads();
@@ -615,10 +638,10 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) bilstm_bwd_kernel(LstmParams 
     const int gt = tid - g * LSTM_GTHREADS;
     if (p.R == 8)
         bwd_group<8>(p, g, gt, dir, bg, ub, Wr, inbox + (size_t)g * inbox_elems, dGs + (size_t)g * 4 * UB * Bh,
-                     &full[g * LSTM_NCHUNK], &done[g], xb + (size_t)g * 2 * nub * inbox_elems);
+                     &full[g * LSTM_NCHUNK], &done[g], xb + (size_t)g * 2 * nub * inbox_elems, turn);
     else
         bwd_group<4>(p, g, gt, dir, bg, ub, Wr, inbox + (size_t)g * inbox_elems, dGs + (size_t)g * 4 * UB * Bh,
-                     &full[g * LSTM_NCHUNK], &done[g], xb + (size_t)g * 2 * nub * inbox_elems);
+                     &full[g * LSTM_NCHUNK], &done[g], xb + (size_t)g * 2 * nub * inbox_elems, turn);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -668,10 +691,10 @@ static int halves_for(int Bc) { return (Bc % 8 == 0) ? 2 : 1; }
 static int rows_for(int Bc) { return ((Bc / halves_for(Bc)) % 8 == 0) ? 8 : 4; }
 static size_t smem_fwd_bytes(int H, int UB, int Bc) {
     const int Bh = Bc / halves_for(Bc);
-    return (size_t)H * UB * 16 + 2 * ((size_t)H * Bh + LSTM_NCHUNK * LSTM_CHUNK_PAD) * 4 + (2 * LSTM_NCHUNK + 3) * 8 + 128;
+    return (size_t)H * UB * 16 + 2 * ((size_t)H * Bh + LSTM_NCHUNK * LSTM_CHUNK_PAD) * 4 + (2 * LSTM_NCHUNK + 4) * 8 + 128;
 }
 static size_t smem_bwd_bytes(int H, int UB, int Bc) {
-    return (size_t)4 * UB * H * 4 + (size_t)Bc * H * 4 + (size_t)4 * UB * Bc * 4 + (2 * LSTM_NCHUNK + 2) * 8 + 128;
+    return (size_t)4 * UB * H * 4 + (size_t)Bc * H * 4 + (size_t)4 * UB * Bc * 4 + (2 * LSTM_NCHUNK + 4) * 8 + 128;
 }
 
 static int make_plan(int B, int H, int ndir, Plan* out) {
