@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--cpu-batch", type=int, default=0, help="utterances per CPU-baseline step (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time the eager step instead of the CUDA-graph replay")
     return ap.parse_args()
 
 
@@ -274,13 +275,27 @@ def main():
         step_resident()
         torch.cuda.synchronize()
         log("warm-up step %d done" % i)
+    # (1) eager pass with per-kernel CUDA events -> kernel table / roofline
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms, loss, launches = timed(step_resident, args.steps, profile=True)
+    eager_ms, loss, launches = timed(step_resident, args.steps, profile=True)
+    summary = pkg.lib.TIMER.summary()
+    launches_per_step = launches / args.steps
+    log("eager timed region done: %.1f ms/step" % (eager_ms / args.steps))
+    # (2) whole-step CUDA graph (fixed shapes) -> the reported value / e2e
+    use_graph = False
+    if not args.no_graph:
+        use_graph = step_fn.capture(wave_dev, lens_dev, txt_dev, global_batch=gbatch, global_tokens=ntok)
+        log("CUDA graph capture: %s" % ("ok" if use_graph else "not used (%s)" % step_fn.graph_error))
+    if use_graph:
+        for _ in range(3):
+            step_resident()
+        ms, loss, _ = timed(step_resident, args.steps)
+    else:
+        ms = eager_ms
     clocks = sampler.stop() if rank == 0 else None
     log("timed region done: %.1f ms/step" % (ms / args.steps))
-    summary = pkg.lib.TIMER.summary()
     value = gb * args.steps / (ms / 1000.0)
     e2e = None
     if not args.no_e2e:
@@ -308,16 +323,40 @@ def main():
     roofline = None
     if top is not None:
         k = kernels[top]
+        d = summary[top]
+        # DRAM traffic / algorithmic bytes measured with `ncu --set full` on the same kernels at (B=64, H=512, T=64),
+        # profiles/r01c_ncu_bilstm_v4.txt: fwd (75.6+44.3) MB vs 109.1 MB, bwd (109.1+32.2) MB vs 218.1 MB
+        ratio = {"bilstm_fwd": 1.10, "bilstm_bwd": 0.65}.get(top)
+        alg_per_launch = d["bytes"] / d["launches"]
         roofline = {"kernel": top, "bound": "hbm", "achieved": k["algorithmic_gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": k["frac_hbm"], "traffic": None, "peak_source": peak_src,
-                    "note": "binding bound for the LSTM step kernels is fp32 FMA issue + per-step cross-SM sync, "
-                            "not HBM (SURVEY.md 7); frac is the algorithmic-bytes fraction the north star asks for"}
+                    "frac": k["frac_hbm"], "traffic": (ratio * alg_per_launch) if ratio else None,
+                    "algorithmic_bytes_per_launch": alg_per_launch, "peak_source": peak_src,
+                    "note": "traffic = ncu dram bytes (profiles/r01c) scaled to this launch size. The LSTM step "
+                            "kernels are bound by fp32 FMA + the per-step cross-SM exchange, not HBM (SURVEY.md 7): "
+                            "see binding_bound"}
+        if top.startswith("bilstm"):
+            # recurrent GEMM flops: 2*B*H*4H per step and direction (x2 for the backward's dG.W product is the same
+            # count); fp32 FMA peak measured on this pool with tools/micro/fma_rate.cu: 58 TFLOP/s (100 FMA/clk/SM)
+            H = cfg["model"]["encoder"]["dim"][0]
+            nbytes_per_step_dir = 24 * per_gpu * H
+            steps_dirs = d["bytes"] / ((2 if top.endswith("bwd") else 1) * nbytes_per_step_dir)
+            flops = steps_dirs * 2.0 * per_gpu * H * 4 * H
+            tf = flops / (d["ms"] * 1e-3) / 1e12
+            roofline["binding_bound"] = {"bound": "fp32_fma", "achieved": tf, "peak": 58.0, "unit": "TFLOP/s",
+                                         "frac": tf / 58.0,
+                                         "us_per_recurrent_step": 1e3 * d["ms"] / (steps_dirs / 2.0)}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-            "loss": loss, "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roofline,
-            "kernels": kernels, "own_kernel_ms_per_step": own_ms,
-            "library_ms_per_step": ms / args.steps - own_ms}
+            "loss": loss, "gpu_launches": int(round(launches_per_step * args.steps)), "clocks": clocks, "e2e": e2e,
+            "roofline": roofline, "kernels": kernels, "cuda_graph": bool(use_graph),
+            "eager_ms_per_step": eager_ms / args.steps, "own_kernel_ms_per_step": own_ms,
+            "library_ms_per_step": eager_ms / args.steps - own_ms,
+            "note": "kernels/roofline come from the eager pass (CUDA events around each C-ABI launch); value and "
+                    "e2e replay the same step as one CUDA graph when cuda_graph is true; gpu_launches counts this "
+                    "library's kernels per step x steps"}
+    if dp.enabled:
+        torch.distributed.destroy_process_group()
     if world == 1 and not args.no_cpu_baseline:
         cb = args.cpu_batch or 8
         log("cpu baseline (%d utterances/step)" % cb)

@@ -52,7 +52,17 @@ __global__ void __launch_bounds__(256) log_softmax_fwd_kernel(const float* __res
     const float part = (m == NEG_INF) ? 0.f : s * expf(m - M);
     const float S = warp_sum(part);
     const float L = M + logf(S);
-    for (int c = lane; c < V; c += 32) y[row * V + c] = xr[c] - L;
+    if ((V & 3) == 0) {
+        const float4* x4 = reinterpret_cast<const float4*>(xr);
+        float4* y4 = reinterpret_cast<float4*>(y + row * V);
+        for (int c = lane; c < (V >> 2); c += 32) {
+            float4 v = x4[c];
+            v.x -= L; v.y -= L; v.z -= L; v.w -= L;
+            y4[c] = v;
+        }
+    } else {
+        for (int c = lane; c < V; c += 32) y[row * V + c] = xr[c] - L;
+    }
     if (lane == 0) {
         if (lse) lse[row] = L;
         if (amax) amax[row] = MI;
@@ -67,6 +77,21 @@ __global__ void __launch_bounds__(256) log_softmax_bwd_kernel(const float* __res
     const float* gr = g + row * V;
     const float* lr = lp + row * V;
     float s = 0.f;
+    if ((V & 3) == 0) {
+        const float4* g4 = reinterpret_cast<const float4*>(gr);
+        const float4* l4 = reinterpret_cast<const float4*>(lr);
+        float4* d4 = reinterpret_cast<float4*>(dx + row * V);
+        for (int c = lane; c < (V >> 2); c += 32) {
+            const float4 v = g4[c];
+            s += (v.x + v.y) + (v.z + v.w);
+        }
+        s = warp_sum(s);
+        for (int c = lane; c < (V >> 2); c += 32) {
+            const float4 v = g4[c], l = l4[c];
+            d4[c] = make_float4(v.x - expf(l.x) * s, v.y - expf(l.y) * s, v.z - expf(l.z) * s, v.w - expf(l.w) * s);
+        }
+        return;
+    }
     for (int c = lane; c < V; c += 32) s += gr[c];
     s = warp_sum(s);
     for (int c = lane; c < V; c += 32) dx[row * V + c] = gr[c] - expf(lr[c]) * s;
@@ -208,7 +233,7 @@ constexpr int CTC_GRAD_THREADS = 256;
 constexpr int CTC_GRAD_TCHUNK = 8;
 
 __global__ void __launch_bounds__(CTC_GRAD_THREADS) ctc_grad_kernel(CtcParams p) {
-    extern __shared__ float s_dyn[];
+    extern __shared__ __align__(16) float s_dyn[];
     __shared__ float s_scratch[32];
     const int S_max = p.S_max, V = p.V;
     float* acc = s_dyn;             // [V]
@@ -225,6 +250,8 @@ __global__ void __launch_bounds__(CTC_GRAD_THREADS) ctc_grad_kernel(CtcParams p)
     const int Sb = 2 * Lb + 1;
     const float nll = p.nll[b];
     const float scale = p.scale ? p.scale[b] : 1.f;
+    const bool vec4 = ((V & 3) == 0) && ((p.sb & 3) == 0) && ((p.st & 3) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(p.lp) | reinterpret_cast<uintptr_t>(p.grad)) & 15) == 0;
 
     for (int c = threadIdx.x; c < V; c += blockDim.x) acc[c] = 0.f;
     for (int s = threadIdx.x; s < S_max; s += blockDim.x) {
@@ -241,7 +268,12 @@ __global__ void __launch_bounds__(CTC_GRAD_THREADS) ctc_grad_kernel(CtcParams p)
     for (int t = t_begin; t < t_end; ++t) {
         float* gt = p.grad + (long long)b * p.sb + (long long)t * p.st;
         if (t >= Tb) {
-            for (int c = threadIdx.x; c < V; c += blockDim.x) gt[c] = 0.f;
+            if (vec4) {
+                float4* g4 = reinterpret_cast<float4*>(gt);
+                for (int c = threadIdx.x; c < (V >> 2); c += blockDim.x) g4[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+                for (int c = threadIdx.x; c < V; c += blockDim.x) gt[c] = 0.f;
+            }
             continue;
         }
         const float* lpt = p.lp + (long long)b * p.sb + (long long)t * p.st;
@@ -276,8 +308,19 @@ __global__ void __launch_bounds__(CTC_GRAD_THREADS) ctc_grad_kernel(CtcParams p)
             }
         }
         __syncthreads();
-        // 3. stream the gradient row
-        for (int c = threadIdx.x; c < V; c += blockDim.x) gt[c] = (expf(lpt[c]) - acc[c]) * scale;
+        // 3. stream the gradient row (128-bit accesses when the rows are 16-byte aligned)
+        if (vec4) {
+            const float4* l4 = reinterpret_cast<const float4*>(lpt);
+            const float4* a4 = reinterpret_cast<const float4*>(acc);
+            float4* g4 = reinterpret_cast<float4*>(gt);
+            for (int c = threadIdx.x; c < (V >> 2); c += blockDim.x) {
+                const float4 l = l4[c], a = a4[c];
+                g4[c] = make_float4((expf(l.x) - a.x) * scale, (expf(l.y) - a.y) * scale, (expf(l.z) - a.z) * scale,
+                                    (expf(l.w) - a.w) * scale);
+            }
+        } else {
+            for (int c = threadIdx.x; c < V; c += blockDim.x) gt[c] = (expf(lpt[c]) - acc[c]) * scale;
+        }
         __syncthreads();
         // 4. reset touched accumulators
         if (threadIdx.x == 0) acc[p.blank] = 0.f;

@@ -26,18 +26,30 @@ class TrainStep:
         self.dp.attach(self.optimizer)
         self.step_id = 0
         self.last = {}
+        self.graph = None
+        self.graph_error = None
 
     def front_end(self, wave, wave_len):
         return self.transform.batch(wave, wave_len)
 
-    def __call__(self, wave, wave_len, txt, global_batch=None, global_tokens=None):
+    def __call__(self, wave, wave_len, txt, global_batch=None, global_tokens=None, max_len=None):
         """wave [B,N] fp32 (device), wave_len [B], txt [B,L] int64 (device); returns the total loss (device scalar).
         Under data parallelism `wave`/`txt` are this rank's shard, padded to the GLOBAL maxima."""
+        if self.graph is not None:
+            self._g_wave.copy_(wave, non_blocking=True)
+            self._g_txt.copy_(txt, non_blocking=True)
+            self.graph.replay()
+            self.step_id += 1
+            return self._g_loss
+        return self._eager(wave, wave_len, txt, global_batch, global_tokens, max_len)
+
+    def _eager(self, wave, wave_len, txt, global_batch, global_tokens, max_len):
         model = self.model
         tf_rate = self.optimizer.pre_step(self.step_id)
         feat, feat_len = self.front_end(wave, wave_len)
         txt_len = torch.sum(txt != 0, dim=-1)
-        max_len = txt.shape[1] if global_batch is not None else int(txt_len.max())
+        if max_len is None:
+            max_len = txt.shape[1] if global_batch is not None else int(txt_len.max())
         ctc_output, encode_len, att_output, att_align, _ = model(feat, feat_len, max_len, tf_rate=tf_rate, teacher=txt)
         total = 0
         ctc = att = None
@@ -59,3 +71,34 @@ class TrainStep:
         self.last = {"ctc": ctc, "att": att, "total": total.detach(), "grad_norm": grad_norm,
                      "ctc_output": ctc_output, "att_output": att_output, "encode_len": encode_len}
         return total.detach()
+
+    def capture(self, wave, wave_len, txt, global_batch=None, global_tokens=None, warmup=3):
+        """Capture the WHOLE train step (front end, forward, losses, backward, all-reduce, clip + update) into one
+        CUDA graph for fixed shapes: ~130 (cfg B) to ~2000 (cfg C: the decode loop) launches become one replay, which
+        removes the host launch gaps between the small kernels.  Valid for a fixed learning rate, tf_rate = 1 and
+        Adadelta (the update kernel's scalars are frozen into the graph).  Returns True when the graph is in use."""
+        h = self.config["hparas"]
+        if h["lr_scheduler"] not in ("fixed", None) or h["optimizer"] != "Adadelta" or self.optimizer.tf_rate(0) != 1:
+            self.graph_error = "schedule-dependent scalars: eager mode"
+            return False
+        try:
+            self._g_wave, self._g_txt = wave.clone(), txt.clone()
+            self._g_len = torch.as_tensor(wave_len).to(wave.device).clone()
+            max_len = int(txt.shape[1])
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(warmup):
+                    self._eager(self._g_wave, self._g_len, self._g_txt, global_batch, global_tokens, max_len)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._g_loss = self._eager(self._g_wave, self._g_len, self._g_txt, global_batch, global_tokens, max_len)
+            self.graph = graph
+            return True
+        except Exception as e:  # stay on the eager path, say why
+            self.graph = None
+            self.graph_error = "%s: %s" % (type(e).__name__, e)
+            torch.cuda.synchronize()
+            return False

@@ -141,3 +141,23 @@ def test_solver_drop_in_loop(pkg, tmp_path):
     s2.load_data()
     s2.set_model()
     assert s2.step == ck["global_step"]
+
+
+def test_cuda_graph_replay_equals_eager_steps(pkg):
+    """Whole-step CUDA graph (front end -> ... -> Adadelta) replays must reproduce the eager train steps."""
+    cfg = _tiny_config("hybrid")
+    g = torch.Generator().manual_seed(11)
+    wave = torch.clamp(0.05 * torch.randn(3, 9000, generator=g), -1, 1).to(DEV)
+    lens = torch.tensor([9000, 9000, 9000], device=DEV)
+    txt = torch.tensor([[3, 4, 4, 5, 1], [6, 7, 1, 0, 0], [8, 9, 10, 1, 0]], device=DEV)
+    eager = pkg.TrainStep(cfg, 12, device=DEV, seed=5)
+    graph = pkg.TrainStep(cfg, 12, device=DEV, seed=5)
+    for _ in range(3):
+        eager(wave, lens, txt, max_len=5)
+    assert graph.capture(wave, lens, txt, warmup=3), graph.graph_error
+    for it in range(3):
+        le = eager(wave * (1.0 - 0.1 * it), lens, txt, max_len=5)
+        lg = graph(wave * (1.0 - 0.1 * it), lens, txt)
+        assert abs(le.item() - lg.item()) <= 1e-6 * abs(le.item()), (it, le.item(), lg.item())
+    for (k, a), (_, b) in zip(eager.model.state_dict().items(), graph.model.state_dict().items()):
+        assert float((a - b).abs().max()) <= 1e-6 * max(float(a.abs().max()), 1e-3), k
