@@ -68,8 +68,9 @@ class TrainStep:
         total.backward()
         grad_norm = self.optimizer.step()
         self.step_id += 1
-        self.last = {"ctc": ctc, "att": att, "total": total.detach(), "grad_norm": grad_norm,
-                     "ctc_output": ctc_output, "att_output": att_output, "encode_len": encode_len}
+        det = lambda t: t.detach() if t is not None else None     # keep no reference to the autograd graph
+        self.last = {"ctc": det(ctc), "att": det(att), "total": total.detach(), "grad_norm": grad_norm,
+                     "ctc_output": det(ctc_output), "att_output": det(att_output), "encode_len": encode_len}
         return total.detach()
 
     def capture(self, wave, wave_len, txt, global_batch=None, global_tokens=None, warmup=3):
@@ -82,6 +83,9 @@ class TrainStep:
             self.graph_error = "schedule-dependent scalars: eager mode"
             return False
         try:
+            import gc
+            self.last = {}
+            gc.collect()                 # drop autograd nodes created on another stream by earlier eager steps
             self._g_wave, self._g_txt = wave.clone(), txt.clone()
             self._g_len = torch.as_tensor(wave_len).to(wave.device).clone()
             max_len = int(txt.shape[1])
