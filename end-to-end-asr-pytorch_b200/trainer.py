@@ -66,6 +66,9 @@ class TrainStep:
                 att = ops.cross_entropy(att_output.reshape(b * t, -1), tgt, ignore_index=0, reduction="sum") / global_tokens
             total = total + att * (1 - model.ctc_weight)
         total.backward()
+        if model.enable_att:     # drop the step's cached keys / alignments / decoder state (they pin the autograd graph)
+            model.attention.reset_mem()
+            model.decoder.hidden_state = None
         grad_norm = self.optimizer.step()
         self.step_id += 1
         det = lambda t: t.detach() if t is not None else None     # keep no reference to the autograd graph
