@@ -68,7 +68,7 @@ class ASR(nn.Module):
         encode_feature, encode_len = self.encoder(audio_feature, feature_len)
 
         if self.enable_ctc:
-            ctc_output, self.last_ctc_argmax = ops.log_softmax(self.ctc_layer(encode_feature))
+            ctc_output, self.last_ctc_argmax = ops.log_softmax(ops.linear3x(encode_feature, self.ctc_layer))
 
         if self.enable_att:
             decode_step = int(decode_step)
@@ -156,7 +156,7 @@ class Decoder(nn.Module):
         return self.hidden_state[0].transpose(0, 1).reshape(-1, self.dim * self.layer)
 
     def project(self, x):
-        return self.char_trans(self.final_dropout(x))
+        return ops.linear3x(self.final_dropout(x), self.char_trans)
 
     def forward(self, x, project=True):
         h_all, c_all = self.hidden_state
@@ -220,7 +220,7 @@ class Attention(nn.Module):
         query = torch.tanh(self.proj_q(dec_state)).view(bs * self.num_head, self.dim)
         if self.key is None:
             self.att_layer.compute_mask(enc_feat, enc_len.to(enc_feat.device))
-            self.key = torch.tanh(self.proj_k(enc_feat))
+            self.key = torch.tanh(ops.linear3x(enc_feat, self.proj_k))
             self.value = torch.tanh(self.proj_v(enc_feat)) if self.v_proj else enc_feat
             if self.num_head > 1:
                 self.key = self.key.view(bs, ts, self.num_head, self.dim).permute(0, 2, 1, 3)

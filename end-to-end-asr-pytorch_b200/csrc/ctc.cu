@@ -2,9 +2,11 @@
 //
 //   log_softmax_fwd_kernel : one warp per row, online max/sum, writes log-probs (+ lse, argmax)
 //   log_softmax_bwd_kernel : dlogits = g - exp(lp) * sum_c g
-//   ctc_alpha_beta_kernel  : grid (B,2): CTA y=0 runs the alpha recursion, CTA y=1 the beta
-//                            recursion of the same utterance concurrently (they are independent);
-//                            one thread per extended-label position, lattice rows stream to HBM
+//   ctc_alpha_beta_warp_kernel : WARP-SYNCHRONOUS alpha/beta: one warp per (utterance, direction) - alpha and
+//                            beta of an utterance run concurrently (they are independent) - each lane keeps R
+//                            consecutive extended-label positions in registers, neighbours via warp shuffles,
+//                            no barrier in the T-long chain; lattice rows stream to HBM for the gradient pass
+//   ctc_alpha_beta_kernel  : block-per-(utterance, direction) fallback for targets longer than 191 labels
 //   ctc_grad_kernel        : grid (T-chunks, B): per (b,t) row combines alpha+beta per class with a
 //                            deterministic occurrence-chain sum and streams the V-wide gradient row
 //
@@ -229,6 +231,165 @@ __global__ void __launch_bounds__(1024) ctc_alpha_beta_kernel(CtcParams p) {
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Warp-synchronous alpha/beta: one WARP per (utterance, direction); lane l keeps the R consecutive extended-label
+// positions s = l*R .. l*R+R-1 of the current lattice row in registers, the two neighbours that live in the adjacent
+// lane come through one pair of warp shuffles per frame, and there is no block barrier and no shared-memory lattice
+// in the T-long dependency chain.  The emission gathers of frame t+1 are issued before the update of frame t.
+constexpr int CTC_WARPS = 4;
+
+template <int R>
+__global__ void __launch_bounds__(CTC_WARPS * 32) ctc_alpha_beta_warp_kernel(CtcParams p) {
+    extern __shared__ float s_dyn[];                     // per warp: labels[S_max] (int) + last row [S_max]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int item = blockIdx.x * CTC_WARPS + warp;      // (b, direction)
+    if (item >= 2 * p.B) return;
+    const int b = item >> 1;
+    const bool is_beta = item & 1;
+    const int S_max = p.S_max;
+    int* lab_s = reinterpret_cast<int*>(s_dyn) + (size_t)warp * 2 * S_max;
+    float* row_s = reinterpret_cast<float*>(lab_s + S_max);
+
+    long long Tb64 = p.in_len[b];
+    long long Lb64 = p.tgt_len[b];
+    const int Tb = (int)(Tb64 < 0 ? 0 : (Tb64 > p.T ? p.T : Tb64));
+    const int Lb = (int)(Lb64 < 0 ? 0 : (Lb64 > p.L_max ? p.L_max : Lb64));
+    const int Sb = 2 * Lb + 1;
+    const float* lpb = p.lp + (long long)b * p.sb;
+    float* lat = (is_beta ? p.beta : p.alpha) + (long long)b * p.T * S_max;
+
+    int lab[R];
+    bool in_range[R], skip[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int s = lane * R + r;
+        in_range[r] = s < Sb;
+        lab[r] = (in_range[r] && (s & 1)) ? (int)p.targets[(long long)b * p.L_max + (s >> 1)] : p.blank;
+        if (s < S_max) lab_s[s] = in_range[r] ? lab[r] : -1;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int s = lane * R + r;
+        skip[r] = false;
+        if (!is_beta) {
+            if (s >= 2 && s < Sb && lab[r] != p.blank && lab[r] != lab_s[s - 2]) skip[r] = true;
+        } else {
+            if (s + 2 < Sb && lab_s[s + 2] != p.blank && lab_s[s + 2] != lab[r]) skip[r] = true;
+        }
+        if (!is_beta && s < S_max) {
+            // occurrence chains of equal labels (consumed by ctc_grad_kernel)
+            int prev = -1, last = 0;
+            if ((s & 1) && s < Sb) {
+                for (int q = s - 2; q >= 1; q -= 2)
+                    if (lab_s[q] == lab[r]) { prev = q; break; }
+                last = 1;
+                for (int q = s + 2; q < Sb; q += 2)
+                    if (lab_s[q] == lab[r]) { last = 0; break; }
+            }
+            p.prev_same[(long long)b * S_max + s] = prev;
+            p.is_last[(long long)b * S_max + s] = last;
+        }
+    }
+    if (Tb == 0) {
+        if (!is_beta && lane == 0) p.nll[b] = (Lb == 0) ? 0.f : INFINITY;
+        return;
+    }
+    const int t0 = is_beta ? Tb - 1 : 0;
+    const int dt = is_beta ? -1 : 1;
+    float a[R], e[R];
+    {   // boundary row
+        const float* lpt = lpb + (long long)t0 * p.st;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int s = lane * R + r;
+            float v = NEG_INF;
+            if (!is_beta) {
+                if (s == 0) v = lpt[p.blank];
+                else if (s == 1 && Sb > 1) v = lpt[lab[r]];
+            } else {
+                if (s == Sb - 1) v = lpt[p.blank];
+                else if (s == Sb - 2 && Sb > 1) v = lpt[lab[r]];
+            }
+            a[r] = v;
+            if (s < S_max) lat[(long long)t0 * S_max + s] = v;
+        }
+        if (Tb > 1) {
+            const float* lpn = lpb + (long long)(t0 + dt) * p.st;
+#pragma unroll
+            for (int r = 0; r < R; ++r) e[r] = lpn[lab[r]];
+        }
+    }
+    for (int step = 1; step < Tb; ++step) {
+        const int t = t0 + dt * step;
+        float en[R];
+        if (step + 1 < Tb) {
+            const float* lpn = lpb + (long long)(t + dt) * p.st;
+#pragma unroll
+            for (int r = 0; r < R; ++r) en[r] = lpn[lab[r]];
+        }
+        // neighbours across the lane boundary
+        float n1, n2;
+        if (!is_beta) {
+            n1 = __shfl_up_sync(0xffffffffu, a[R - 1], 1);
+            n2 = __shfl_up_sync(0xffffffffu, a[R >= 2 ? R - 2 : 0], 1);
+            if (R == 1) n2 = __shfl_up_sync(0xffffffffu, a[0], 2);
+            if (lane == 0) { n1 = NEG_INF; n2 = NEG_INF; }
+            if (R == 1 && lane == 1) n2 = NEG_INF;
+        } else {
+            n1 = __shfl_down_sync(0xffffffffu, a[0], 1);
+            n2 = __shfl_down_sync(0xffffffffu, a[R >= 2 ? 1 : 0], 1);
+            if (R == 1) n2 = __shfl_down_sync(0xffffffffu, a[0], 2);
+            if (lane == 31) { n1 = NEG_INF; n2 = NEG_INF; }
+            if (R == 1 && lane == 30) n2 = NEG_INF;
+        }
+        float nw[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float a1, a2;
+            if (!is_beta) {
+                a1 = (r >= 1) ? a[r >= 1 ? r - 1 : 0] : n1;
+                a2 = (r >= 2) ? a[r >= 2 ? r - 2 : 0] : (r == 1 ? n1 : n2);
+            } else {
+                a1 = (r + 1 < R) ? a[r + 1 < R ? r + 1 : 0] : n1;
+                a2 = (r + 2 < R) ? a[r + 2 < R ? r + 2 : 0] : (r + 1 < R ? n1 : n2);
+            }
+            if (!skip[r]) a2 = NEG_INF;
+            nw[r] = in_range[r] ? lse3(a[r], a1, a2) + e[r] : NEG_INF;
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            a[r] = nw[r];
+            e[r] = en[r];
+            const int s = lane * R + r;
+            if (s < S_max) lat[(long long)t * S_max + s] = nw[r];
+        }
+    }
+    if (!is_beta) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int s = lane * R + r;
+            if (s < S_max) row_s[s] = a[r];
+        }
+        __syncwarp();
+        if (lane == 0) {
+            const float l1 = row_s[Sb - 1];
+            const float l2 = (Sb > 1) ? row_s[Sb - 2] : NEG_INF;
+            const float m = fmaxf(l1, l2);
+            const float ll = (m == NEG_INF) ? NEG_INF : logf(expf(l1 - m) + expf(l2 - m)) + m;
+            p.nll[b] = -ll;
+        }
+    }
+}
+
+template <int R>
+static int launch_ctc_warp(const CtcParams& p, cudaStream_t stream) {
+    const int items = 2 * p.B;
+    const size_t smem = (size_t)CTC_WARPS * 2 * p.S_max * sizeof(float);
+    ctc_alpha_beta_warp_kernel<R><<<(items + CTC_WARPS - 1) / CTC_WARPS, CTC_WARPS * 32, smem, stream>>>(p);
+    return 0;
+}
+
 constexpr int CTC_GRAD_THREADS = 256;
 constexpr int CTC_GRAD_TCHUNK = 8;
 
@@ -385,15 +546,28 @@ extern "C" int b200asr_ctc_fwd_bwd(const float* log_probs, long long stride_b, l
     p.prev_same = reinterpret_cast<int*>(ws + 2 * (size_t)B * T * S);
     p.is_last = p.prev_same + (size_t)B * S;
 
-    int threads = (p.S_max + 31) / 32 * 32;
-    if (threads > 1024) threads = 1024;
-    const size_t smem_ab = S * (2 * sizeof(float) + 2 * sizeof(int));
-    B200_REQUIRE(smem_ab <= (size_t)max_optin_smem(), "ctc_fwd_bwd: target too long for shared memory (L=%d)", L_max);
-    if (smem_ab > 48 * 1024)
-        B200_CUDA(cudaFuncSetAttribute(ctc_alpha_beta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem_ab));
-    ctc_alpha_beta_kernel<<<dim3(B, 2), threads, smem_ab, (cudaStream_t)stream>>>(p);
-    B200_LAUNCH_CHECK("ctc_alpha_beta_kernel");
+    const int need = (p.S_max + 31) / 32;      // extended-label positions per lane
+    if (need <= 12 && (size_t)CTC_WARPS * 2 * p.S_max * sizeof(float) <= 48 * 1024) {
+        if (need <= 1) launch_ctc_warp<1>(p, (cudaStream_t)stream);
+        else if (need <= 2) launch_ctc_warp<2>(p, (cudaStream_t)stream);
+        else if (need <= 3) launch_ctc_warp<3>(p, (cudaStream_t)stream);
+        else if (need <= 4) launch_ctc_warp<4>(p, (cudaStream_t)stream);
+        else if (need <= 6) launch_ctc_warp<6>(p, (cudaStream_t)stream);
+        else if (need <= 8) launch_ctc_warp<8>(p, (cudaStream_t)stream);
+        else launch_ctc_warp<12>(p, (cudaStream_t)stream);
+        B200_LAUNCH_CHECK("ctc_alpha_beta_warp_kernel");
+    } else {
+        // very long targets: block-per-(utterance, direction) fallback with the lattice row in shared memory
+        int threads = (p.S_max + 31) / 32 * 32;
+        if (threads > 1024) threads = 1024;
+        const size_t smem_ab = S * (2 * sizeof(float) + 2 * sizeof(int));
+        B200_REQUIRE(smem_ab <= (size_t)max_optin_smem(), "ctc_fwd_bwd: target too long for shared memory (L=%d)", L_max);
+        if (smem_ab > 48 * 1024)
+            B200_CUDA(cudaFuncSetAttribute(ctc_alpha_beta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem_ab));
+        ctc_alpha_beta_kernel<<<dim3(B, 2), threads, smem_ab, (cudaStream_t)stream>>>(p);
+        B200_LAUNCH_CHECK("ctc_alpha_beta_kernel");
+    }
     if (grad) {
         const size_t smem_g = (size_t)V * sizeof(float) + S * (sizeof(float) + 3 * sizeof(int));
         B200_REQUIRE(smem_g <= (size_t)max_optin_smem(), "ctc_fwd_bwd: vocabulary %d too large for shared memory", V);

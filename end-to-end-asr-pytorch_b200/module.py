@@ -122,7 +122,7 @@ class RNNLayer(nn.Module):
                     output = output[:, :-rem, :]
                 output = output.contiguous().view(bs, ts // self.sample_rate, fd * self.sample_rate)
         if self.proj:
-            output = torch.tanh(self.pj(output))
+            output = torch.tanh(ops.linear3x(output, self.pj))
         return output, x_len
 
 

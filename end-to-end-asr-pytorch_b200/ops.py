@@ -457,3 +457,39 @@ class LocAttnStepFn(Function):
 def loc_attention_step(q, key, value, prev_att, enc_len, conv_w, proj_w, e_w, e_b, temperature):
     """-> (context [B,E], attn [B,T])"""
     return LocAttnStepFn.apply(q, key, value, prev_att, enc_len, conv_w, proj_w, e_w, e_b, temperature)
+
+
+# ----------------------------------------------------------------------------------------------------------
+class Linear3xFn(Function):
+    """y = x W^T + b for the large dense layers of the step (CTC head, key projection, vocabulary projection) on
+    the tensor cores with the same error-compensated 3xTF32 scheme as the LSTM input projection (fp32-class)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        Op, mm = _gemm_ops()
+        shp = x.shape
+        x2 = _f32c(x).reshape(-1, shp[-1])
+        y = mm(Op(x2), Op(weight.detach()).t(), bias=bias.detach() if bias is not None else None,
+               out=torch.empty((x2.shape[0], weight.shape[0]), device=x.device, dtype=torch.float32))
+        ctx.save_for_backward(x2, weight)
+        ctx.shp = shp
+        ctx.has_bias = bias is not None
+        return y.view(*shp[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, gy):
+        Op, mm = _gemm_ops()
+        x2, weight = ctx.saved_tensors
+        g2 = Op(_f32c(gy).reshape(-1, weight.shape[0]))
+        dx = mm(g2, Op(weight.detach())).view(ctx.shp) if ctx.needs_input_grad[0] else None
+        dw = mm(g2.t(), Op(x2)) if ctx.needs_input_grad[1] else None
+        db = gy.reshape(-1, weight.shape[0]).sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        return dx, dw, db
+
+
+def linear3x(x, layer):
+    """Apply an nn.Linear through the 3xTF32 tensor-core path when the problem is large enough to matter."""
+    rows = x.numel() // x.shape[-1]
+    if x.is_cuda and rows * layer.in_features * layer.out_features >= (1 << 24):
+        return Linear3xFn.apply(x, layer.weight, layer.bias)
+    return torch.nn.functional.linear(x, layer.weight, layer.bias)
