@@ -302,6 +302,32 @@ def test_gemm_tf32x3_is_fp32_class(pkg):
     assert torch.equal(s.hi + s.lo, a) and int((s.hi.view(torch.int32) & 0x1fff).abs().max()) == 0
 
 
+def test_linear3x_matches_fp64_linear(pkg):
+    """CTC head / vocabulary projection through the 3xTF32 path: forward and all three gradients."""
+    torch.manual_seed(3)
+    lin = torch.nn.Linear(256, 1000)
+    x = torch.randn(4, 70, 256)
+    xr = x.double().requires_grad_(True)
+    ref = torch.nn.functional.linear(xr, lin.weight.double(), lin.bias.double())
+    g = torch.randn(4, 70, 1000)
+    ref.backward(g.double())
+    lin_d = torch.nn.Linear(256, 1000).to(DEV)
+    lin_d.load_state_dict(lin.state_dict())
+    xd = x.to(DEV).requires_grad_(True)
+    y = pkg.ops.linear3x(xd, lin_d)
+    assert y.shape == (4, 70, 1000) and scaled_err(y.detach().cpu().numpy(), ref.detach().numpy()) < 1e-5
+    y.backward(g.to(DEV))
+    w64 = lin.weight.double().requires_grad_(True)
+    b64 = lin.bias.double().requires_grad_(True)
+    torch.nn.functional.linear(x.double(), w64, b64).backward(g.double())
+    assert scaled_err(xd.grad.cpu().numpy(), xr.grad.numpy()) < 1e-5
+    assert scaled_err(lin_d.weight.grad.cpu().numpy(), w64.grad.numpy()) < 1e-5
+    assert scaled_err(lin_d.bias.grad.cpu().numpy(), b64.grad.numpy()) < 1e-5
+    # tiny problems stay on the plain library path
+    small = torch.nn.Linear(8, 4).to(DEV)
+    assert pkg.ops.linear3x(torch.randn(3, 8, device=DEV), small).shape == (3, 4)
+
+
 # ------------------------------------------------------------------------------------------- optimizer
 def test_grad_norm_and_adadelta_vs_torch(pkg):
     from ctypes import c_void_p

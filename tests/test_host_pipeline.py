@@ -124,3 +124,19 @@ def test_data_parallel_rules_match_single_process_gloo():
         assert p.exitcode == 0
     assert world == 2 and tmax == 20.0
     assert err < 1e-4, err
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (CPU arm) prints one JSON line with the contract's keys; tiny sample here."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--cpu-batch", "1", "--n-samples", "16000"], capture_output=True, text=True,
+                         timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "utt/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["e2e"]["value"] == line["value"]
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["config"]["workload"].startswith("cfgB")
