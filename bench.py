@@ -285,7 +285,9 @@ def main():
     log("eager timed region done: %.1f ms/step" % (eager_ms / args.steps))
     # (2) whole-step CUDA graph (fixed shapes) -> the reported value / e2e
     use_graph = False
-    if not args.no_graph:
+    # multi-GPU runs stay eager: the captured graph would contain the NCCL all-reduce, whose teardown at process exit
+    # was seen to hang (the eager data-parallel path is the validated one; the graph is worth ~1 % on cfg B)
+    if not args.no_graph and world == 1:
         use_graph = step_fn.capture(wave_dev, lens_dev, txt_dev, global_batch=gbatch, global_tokens=ntok)
         log("CUDA graph capture: %s" % ("ok" if use_graph else "not used (%s)" % step_fn.graph_error))
     if use_graph:
@@ -355,8 +357,6 @@ def main():
             "note": "kernels/roofline come from the eager pass (CUDA events around each C-ABI launch); value and "
                     "e2e replay the same step as one CUDA graph when cuda_graph is true; gpu_launches counts this "
                     "library's kernels per step x steps"}
-    if dp.enabled:
-        torch.distributed.destroy_process_group()
     if world == 1 and not args.no_cpu_baseline:
         cb = args.cpu_batch or 8
         log("cpu baseline (%d utterances/step)" % cb)
@@ -369,6 +369,7 @@ def main():
                                           "64/all cores)" % cb,
                                 "ms_per_step": r["ms_per_step"]}
     print(json.dumps(line))
+    sys.stdout.flush()
     return 0
 
 
