@@ -551,21 +551,23 @@ __device__ __forceinline__ void bwd_group(const LstmParams& p, int g, int gt, in
 #pragma unroll
                 for (int r = 0; r < 2; ++r) {
                     const int k0 = r * (H >> 1) + kq2 * 4;
+                    if (vec_ok) {
+                        const int dst = k0 / UB, uu = k0 - dst * UB;
+                        float* o = outbase + (((size_t)dst * nub + ub) * Bh + bo2 * R) * UB + uu;
 #pragma unroll
-                    for (int i = 0; i < R; ++i) {
-                        const int rowl = bo2 * R + i;
-                        if (vec_ok) {
-                            const int dst = k0 / UB, uu = k0 - dst * UB;
-                            float* o = outbase + (((size_t)dst * nub + ub) * Bh + rowl) * UB + uu;
-                            *reinterpret_cast<float4*>(o) =
+                        for (int i = 0; i < R; ++i)
+                            *reinterpret_cast<float4*>(o + (size_t)i * UB) =
                                 make_float4(a[i][r * 4], a[i][r * 4 + 1], a[i][r * 4 + 2], a[i][r * 4 + 3]);
-                        } else {
+                    } else {
+                        // unit blocks that are not a multiple of 4 (e.g. UB = 10 at H = 640): resolve the destination
+                        // of each of the 4 k columns once (the runtime division is expensive), then store row by row
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const int k = k0 + j;
-                                const int dst = k / UB, uu = k - dst * UB;
-                                outbase[(((size_t)dst * nub + ub) * Bh + rowl) * UB + uu] = a[i][r * 4 + j];
-                            }
+                        for (int j = 0; j < 4; ++j) {
+                            const int k = k0 + j;
+                            const int dst = k / UB, uu = k - dst * UB;
+                            float* o = outbase + (((size_t)dst * nub + ub) * Bh + bo2 * R) * UB + uu;
+#pragma unroll
+                            for (int i = 0; i < R; ++i) o[(size_t)i * UB] = a[i][r * 4 + j];
                         }
                     }
                 }

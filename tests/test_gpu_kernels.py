@@ -308,7 +308,7 @@ def test_linear3x_matches_fp64_linear(pkg):
     lin = torch.nn.Linear(256, 1000)
     x = torch.randn(4, 70, 256)
     xr = x.double().requires_grad_(True)
-    ref = torch.nn.functional.linear(xr, lin.weight.double(), lin.bias.double())
+    ref = torch.nn.functional.linear(xr, lin.weight.detach().double(), lin.bias.detach().double())
     g = torch.randn(4, 70, 1000)
     ref.backward(g.double())
     lin_d = torch.nn.Linear(256, 1000).to(DEV)
@@ -317,8 +317,8 @@ def test_linear3x_matches_fp64_linear(pkg):
     y = pkg.ops.linear3x(xd, lin_d)
     assert y.shape == (4, 70, 1000) and scaled_err(y.detach().cpu().numpy(), ref.detach().numpy()) < 1e-5
     y.backward(g.to(DEV))
-    w64 = lin.weight.double().requires_grad_(True)
-    b64 = lin.bias.double().requires_grad_(True)
+    w64 = lin.weight.detach().double().requires_grad_(True)
+    b64 = lin.bias.detach().double().requires_grad_(True)
     torch.nn.functional.linear(x.double(), w64, b64).backward(g.double())
     assert scaled_err(xd.grad.cpu().numpy(), xr.grad.numpy()) < 1e-5
     assert scaled_err(lin_d.weight.grad.cpu().numpy(), w64.grad.numpy()) < 1e-5
