@@ -193,7 +193,7 @@ def main():
               "frames": 1 + (args.n_samples - 400) // 160, "vocab": vocab,
               "parallelism": "dp%d (utterance shards + 1 NCCL grad all-reduce)" % world,
               "l2": "inputs+activations per step (>1 GB) exceed the 126 MB L2; no explicit flush",
-              "gemm": "cuBLAS fp32 (TF32 off) for the plain input-projection / weight-grad GEMMs"}
+              "gemm": "3xTF32 error-compensated cuBLAS (tcgen05) for the input-projection / weight-grad GEMMs; fp32-accurate"}
 
     # ------------------------------------------------------------------------------- reference (CPU) arm
     if args.impl == "reference":
