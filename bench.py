@@ -327,25 +327,28 @@ def main():
         k = kernels[top]
         d = summary[top]
         # DRAM traffic / algorithmic bytes measured with `ncu --set full` on the same kernels at (B=64, H=512, T=64),
-        # profiles/r01c_ncu_bilstm_v4.txt: fwd (75.6+44.3) MB vs 109.1 MB, bwd (109.1+32.2) MB vs 218.1 MB
+        # profiles/r01d_ncu_bilstm_*.txt: fwd (75.5+44.1) MB vs 109.1 MB, bwd (109.1+32.2) MB vs 218.1 MB
         ratio = {"bilstm_fwd": 1.10, "bilstm_bwd": 0.65}.get(top)
         alg_per_launch = d["bytes"] / d["launches"]
         roofline = {"kernel": top, "bound": "hbm", "achieved": k["algorithmic_gbs"], "peak": peak, "unit": "GB/s",
                     "frac": k["frac_hbm"], "traffic": (ratio * alg_per_launch) if ratio else None,
                     "algorithmic_bytes_per_launch": alg_per_launch, "peak_source": peak_src,
                     "note": "traffic = ncu dram bytes (profiles/r01c) scaled to this launch size. The LSTM step "
-                            "kernels are bound by fp32 FMA + the per-step cross-SM exchange, not HBM (SURVEY.md 7): "
+                            "kernels are bound by the step GEMM issue rate + the per-step cross-SM exchange, not HBM (SURVEY.md 7): "
                             "see binding_bound"}
         if top.startswith("bilstm"):
-            # recurrent GEMM flops: 2*B*H*4H per step and direction (x2 for the backward's dG.W product is the same
-            # count); fp32 FMA peak measured on this pool with tools/micro/fma_rate.cu: 58 TFLOP/s (100 FMA/clk/SM)
+            # recurrent GEMM flops: 2*B*H*4H per step and direction (the backward's dG.W product is the same count).
+            # Peaks measured on this pool (profiles/r01d_micro_*): packed fp32 FMA 58 TFLOP/s (100 FMA/clk/SM);
+            # warp-level mma.sync tf32 246 TFLOP/s raw (424 MAC/clk/SM) = 82 TFLOP/s fp32-equivalent at 3 MMAs/MAC
             H = cfg["model"]["encoder"]["dim"][0]
             nbytes_per_step_dir = 24 * per_gpu * H
             steps_dirs = d["bytes"] / ((2 if top.endswith("bwd") else 1) * nbytes_per_step_dir)
             flops = steps_dirs * 2.0 * per_gpu * H * 4 * H
             tf = flops / (d["ms"] * 1e-3) / 1e12
-            roofline["binding_bound"] = {"bound": "fp32_fma", "achieved": tf, "peak": 58.0, "unit": "TFLOP/s",
-                                         "frac": tf / 58.0,
+            on_tc = lib.b200asr_bilstm_uses_tensor_cores(per_gpu, H, 2) == 1
+            pk = 82.0 if on_tc else 58.0
+            roofline["binding_bound"] = {"bound": "mma_sync_3xtf32" if on_tc else "fp32_fma", "achieved": tf,
+                                         "peak": pk, "unit": "TFLOP/s (fp32-equivalent)", "frac": tf / pk,
                                          "us_per_recurrent_step": 1e3 * d["ms"] / (steps_dirs / 2.0)}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,

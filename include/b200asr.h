@@ -94,6 +94,9 @@ B200ASR_API int b200asr_ctc_fwd_bwd(const float* log_probs, long long stride_b, 
  * (b200asr_bilstm_plan reports it).  Launched cooperatively: all CTAs are co-resident.                       */
 B200ASR_API size_t b200asr_bilstm_workspace_bytes(int B, int T, int H, int ndir);
 B200ASR_API int b200asr_bilstm_plan(int B, int H, int ndir, int* unit_block, int* batch_block, int* n_ctas);
+/* 1 when the step GEMMs of this shape run on the tensor cores (3xTF32 mma), 0 for the packed-fp32-FMA kernels,
+ * -1 when the shape has no decomposition */
+B200ASR_API int b200asr_bilstm_uses_tensor_cores(int B, int H, int ndir);
 B200ASR_API int b200asr_bilstm_fwd(float* gates, const float* w_hh, float* cstate, float* out, int B, int T, int H, int ndir,
                        void* workspace, size_t workspace_bytes, b200asr_stream stream);
 B200ASR_API int b200asr_bilstm_bwd(float* gates, const float* w_hh, const float* cstate, const float* dout, int B, int T,
@@ -101,6 +104,10 @@ B200ASR_API int b200asr_bilstm_bwd(float* gates, const float* w_hh, const float*
 
 /* debug: when non-NULL, CTA 0 of the next b200asr_bilstm_fwd calls records clock64 stamps into [T][16] int64 */
 B200ASR_API void b200asr_debug_set_lstm_trace(long long* device_buffer);
+/* debug/test: 0 (default) = tensor-core (3xTF32 mma) step GEMMs wherever the planner finds a 16-row-tile
+ * decomposition, 1 = always the packed-fp32-FMA step kernels.  Both are fp32-class and parity-tested.
+ * Upper bits (mode >> 4) are measurement switches used by tools/time_lstm.py and tools/trace_lstm.py. */
+B200ASR_API void b200asr_debug_set_lstm_mode(int mode);
 
 /* ---- K13: one LSTM cell step (decoder, src/asr.py:214-221) -------------------------------------------------
  * preact [B, 4H] gate-major (i,f,g,o) = x.W_ih^T + h.W_hh^T + biases; gates [B,4H] activated (stash).        */

@@ -163,16 +163,7 @@ def _torch_lstm(I, H, bidir, seed):
     return torch.nn.LSTM(I, H, bidirectional=bidir, num_layers=1, batch_first=True)
 
 
-@pytest.mark.parametrize("B,T,I,H,bidir", [
-    (3, 7, 8, 16, True),        # UB=1 scalar scatter path, partial batch block
-    (5, 9, 12, 32, False),      # unidirectional
-    (4, 1, 8, 32, True),        # single step
-    (9, 6, 10, 48, True),       # two batch groups, tail rows
-    (8, 13, 40, 320, True),     # UB % 4 == 0 path with several unit blocks
-    (32, 11, 24, 640, True),    # cfg-D shape: UB = 10
-    (64, 10, 120, 512, True),   # cfg-B/C shape: UB = 16, Bc = 32, 128 CTAs
-])
-def test_bilstm_fwd_bwd_vs_aten_cpu(pkg, B, T, I, H, bidir):
+def _check_bilstm(pkg, B, T, I, H, bidir):
     ref = _torch_lstm(I, H, bidir, 3)
     torch.manual_seed(4)
     x = torch.randn(B, T, I)
@@ -191,6 +182,34 @@ def test_bilstm_fwd_bwd_vs_aten_cpu(pkg, B, T, I, H, bidir):
     for p, q, (name, _) in zip(params, ref.parameters(), ref.named_parameters()):
         scale = float(q.grad.abs().max())
         assert float((p.grad.cpu() - q.grad).abs().max()) < 1e-4 * max(scale, 1e-3), name
+
+
+@pytest.mark.parametrize("B,T,I,H,bidir", [
+    (3, 7, 8, 16, True),        # UB=1 scalar scatter path, partial batch block
+    (5, 9, 12, 32, False),      # unidirectional
+    (4, 1, 8, 32, True),        # single step
+    (9, 6, 10, 48, True),       # two batch groups, tail rows
+    (8, 13, 40, 320, True),     # UB % 4 == 0 path with several unit blocks
+    (32, 11, 24, 640, True),    # cfg-D shape: UB = 10 (tensor-core step kernels, 3 unit pairs, one padded)
+    (64, 10, 120, 512, True),   # cfg-B/C shape: UB = 16, Bc = 32, 128 CTAs (tensor-core step kernels)
+    (40, 9, 16, 512, False),    # unidirectional tensor-core plan (UB = 8), second batch group mostly padding rows
+    (130, 5, 16, 512, True),    # more CTAs than SMs: three consecutive launches over 44-row blocks
+    (64, 4, 24, 640, True),     # cfg D at batch 64: two launches of 32 rows
+])
+def test_bilstm_fwd_bwd_vs_aten_cpu(pkg, B, T, I, H, bidir):
+    _check_bilstm(pkg, B, T, I, H, bidir)
+
+
+@pytest.mark.parametrize("B,T,I,H,bidir", [(32, 11, 24, 640, True), (64, 10, 120, 512, True), (130, 5, 16, 512, True)])
+def test_bilstm_fp32_fma_kernels_on_the_large_shapes(pkg, B, T, I, H, bidir):
+    """The packed-FMA step kernels stay the fallback for shapes without a 16-row-tile plan; keep them covered at
+    the BASELINE shapes too by forcing them."""
+    lib = pkg.load_library()
+    lib.b200asr_debug_set_lstm_mode(1)
+    try:
+        _check_bilstm(pkg, B, T, I, H, bidir)
+    finally:
+        lib.b200asr_debug_set_lstm_mode(0)
 
 
 def test_bilstm_pad_through_semantics(pkg):

@@ -35,16 +35,26 @@ def test_error_convention_without_gpu(pkg):
         pkg.lib.ptr(torch.zeros(3))            # host tensors are refused: no CPU fallback
 
 
-@pytest.mark.parametrize("B,H,ndir,exp", [(64, 512, 2, (16, 32, 128)), (32, 640, 2, (10, 32, 128)),
-                                           (32, 512, 2, (16, 16, 128))])
-def test_lstm_plan_fills_the_sms(pkg, B, H, ndir, exp):
+@pytest.mark.parametrize("B,H,ndir,mode,exp", [
+    (64, 512, 2, 0, (16, 32, 128)), (32, 640, 2, 0, (10, 32, 128)),
+    (32, 512, 2, 0, (8, 32, 128)),          # tensor-core plan: 16-row halves, 8 units per CTA
+    (32, 512, 2, 1, (16, 16, 128)),         # forced fp32-FMA kernels keep the old decomposition
+    (8, 320, 2, 0, (10, 4, 128)),           # tiny batch: the FMA kernels stay cheaper than a padded MMA tile
+    (130, 512, 2, 0, (16, 32, 128)),        # too many CTAs for one launch: three launches of 44 rows
+    (64, 640, 2, 0, (10, 32, 128)),         # cfg D at batch 64: two launches of 32 rows
+])
+def test_lstm_plan_fills_the_sms(pkg, B, H, ndir, mode, exp):
     from ctypes import c_int, byref
     lib = pkg.load_library()
     ub, bc, n = c_int(), c_int(), c_int()
-    assert lib.b200asr_bilstm_plan(B, H, ndir, byref(ub), byref(bc), byref(n)) == 0
-    assert (ub.value, bc.value, n.value) == exp
-    assert n.value <= 148 and H % ub.value == 0
-    assert lib.b200asr_bilstm_workspace_bytes(B, 100, H, ndir) > 0
+    lib.b200asr_debug_set_lstm_mode(mode)
+    try:
+        assert lib.b200asr_bilstm_plan(B, H, ndir, byref(ub), byref(bc), byref(n)) == 0
+        assert (ub.value, bc.value, n.value) == exp
+        assert n.value <= 148 and H % ub.value == 0
+        assert lib.b200asr_bilstm_workspace_bytes(B, 100, H, ndir) > 0
+    finally:
+        lib.b200asr_debug_set_lstm_mode(0)
 
 
 def test_host_tables_bit_identical_to_torchaudio(pkg):

@@ -75,12 +75,45 @@ __global__ void k(float* out, int iters, float s0) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// dependent-issue latency: CH independent accumulator chains per warp, operands fixed
+template <int CH>
+__global__ void kc(float* out, int iters, float s0) {
+    float c[CH][4];
+    for (int m = 0; m < CH; ++m) for (int i = 0; i < 4; ++i) c[m][i] = 0.f;
+    uint32_t a[4], b[2];
+    for (int i = 0; i < 4; ++i) a[i] = __float_as_uint(s0 + threadIdx.x * 1e-3f + i);
+    for (int i = 0; i < 2; ++i) b[i] = __float_as_uint(s0 * 0.5f + i);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int m = 0; m < CH; ++m) mma_tf32(c[m], a, b);
+    }
+    float s = 0;
+    for (int m = 0; m < CH; ++m) for (int i = 0; i < 4; ++i) s += c[m][i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+template <int CH>
+void sweep(float* out, int clk) {
+    for (int warps : {4, 8}) {
+        const int iters = 20000;
+        cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+        for (int rep = 0; rep < 2; ++rep) {
+            cudaEventRecord(a);
+            kc<CH><<<148, warps * 32>>>(out, iters, 1.f);
+            cudaEventRecord(b); cudaEventSynchronize(b);
+        }
+        float ms; cudaEventElapsedTime(&ms, a, b);
+        const double cyc = ms * 1e-3 * clk * 1e3 / iters;     // cycles per loop iteration (= CH MMAs per warp)
+        printf("chains/warp %2d warps/SM %d : %.1f cycles per round  -> %.1f cycles per MMA per SMSP-warp, %.0f MAC/clk/SM\n", CH, warps, cyc,
+               cyc / CH, (double)warps * CH * 1024 / cyc);
+    }
+}
+
 int main() {
     float* out; cudaMalloc(&out, 148 * 1024 * 4);
     int clk; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
     const char* names[3] = {"tf32 m16n8k8     ", "3xTF32 (split in loop)", "bf16 m16n8k16    "};
     for (int mode = 0; mode < 3; ++mode)
-        for (int warps : {4, 8, 10, 16, 32}) {
+        for (int warps : {4, 8, 16}) {
             const int iters = 20000;
             cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
             for (int rep = 0; rep < 2; ++rep) {
@@ -98,5 +131,7 @@ int main() {
             printf("%s warps/SM %2d : %.3f ms  %.1f TFLOP/s-equiv  %.0f MAC/clk/SM (at %.2f GHz nominal)%s\n", names[mode], warps, ms,
                    2 * mac / ms / 1e9, mac / 148 / (ms * 1e-3) / (clk * 1e3), clk / 1e6, e ? cudaGetErrorString(e) : "");
         }
+    sweep<1>(out, clk); sweep<2>(out, clk); sweep<3>(out, clk); sweep<4>(out, clk); sweep<6>(out, clk);
+    sweep<8>(out, clk); sweep<12>(out, clk); sweep<16>(out, clk);
     return 0;
 }
