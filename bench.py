@@ -339,14 +339,14 @@ def main():
         if top.startswith("bilstm"):
             # recurrent GEMM flops: 2*B*H*4H per step and direction (the backward's dG.W product is the same count).
             # Peaks measured on this pool (profiles/r01d_micro_*): packed fp32 FMA 58 TFLOP/s (100 FMA/clk/SM);
-            # warp-level mma.sync tf32 246 TFLOP/s raw (424 MAC/clk/SM) = 82 TFLOP/s fp32-equivalent at 3 MMAs/MAC
+            # warp-level mma.sync tf32 278 TFLOP/s raw (478 MAC/clk/SM) = 92.7 TFLOP/s fp32-equivalent at 3 MMAs/MAC
             H = cfg["model"]["encoder"]["dim"][0]
             nbytes_per_step_dir = 24 * per_gpu * H
             steps_dirs = d["bytes"] / ((2 if top.endswith("bwd") else 1) * nbytes_per_step_dir)
             flops = steps_dirs * 2.0 * per_gpu * H * 4 * H
             tf = flops / (d["ms"] * 1e-3) / 1e12
             on_tc = lib.b200asr_bilstm_uses_tensor_cores(per_gpu, H, 2) == 1
-            pk = 82.0 if on_tc else 58.0
+            pk = 92.7 if on_tc else 58.0
             roofline["binding_bound"] = {"bound": "mma_sync_3xtf32" if on_tc else "fp32_fma", "achieved": tf,
                                          "peak": pk, "unit": "TFLOP/s (fp32-equivalent)", "frac": tf / pk,
                                          "us_per_recurrent_step": 1e3 * d["ms"] / (steps_dirs / 2.0)}
