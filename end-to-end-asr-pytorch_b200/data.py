@@ -68,8 +68,13 @@ def create_dataset(tokenizer, ascending, name, path, bucketing, batch_size, trai
     if name.lower() == "synthetic":
         n = extra.get("n_samples", 192000)
         v = extra.get("vocab_size", tokenizer.vocab_size if tokenizer is not None else 31)
-        tr = SyntheticDataset(v, batch_size, n, extra.get("n_batches", 64), seed=0)
         dv = SyntheticDataset(v, batch_size, n, 2, seed=10 ** 6)
+        if train_split is None:            # decoding: (dev, test) like the LibriSpeech branch below
+            tt = SyntheticDataset(v, batch_size, n, 2, seed=2 * 10 ** 6)
+            msg = _data_msg(name, path, str(dev_split), len(dv), str(test_split), len(tt), batch_size, False)
+            msg = [m.replace("Dev", "Test").replace("Train", "Dev") for m in msg]
+            return dv, tt, 1, 1, "test", msg
+        tr = SyntheticDataset(v, batch_size, n, extra.get("n_batches", 64), seed=0)
         msg = _data_msg(name, path, str(train_split), len(tr), str(dev_split), len(dv), batch_size, False)
         return tr, dv, 1, 1, "train", msg
     if name.lower() != "librispeech":

@@ -6,6 +6,7 @@ import os
 import sys
 
 import torch
+import yaml
 
 from .dist import DataParallel
 from .option import default_hparas
@@ -59,8 +60,18 @@ class BaseSolver:
             self.max_step = config["hparas"]["max_step"]
             self.verbose("Exp. name : {}".format(self.exp_name))
             self.verbose("Loading data... large corpus may took a while.")
+        elif mode == "test":
+            # greedy decoding; same bookkeeping as src/solver.py:63-73
+            os.makedirs(paras.outdir, exist_ok=True)
+            self.ckpdir = os.path.join(paras.outdir, self.exp_name)
+            with open(config["src"]["config"], "r") as f:
+                self.src_config = yaml.load(f, Loader=yaml.FullLoader)
+            self.paras.load = config["src"]["ckpt"]
+            self.log = _NullWriter()
+            self.step = 0
+            self.verbose("Evaluating result of tr. config @ {}".format(config["src"]["config"]))
         else:
-            raise NotImplementedError("mode '%s': decoding (bin/test_asr.py) is outside this hot path" % mode)
+            raise NotImplementedError("mode '%s' is outside this hot path" % mode)
 
     def backward(self, loss):
         """loss.backward(); all-reduce (DP); global norm + clip(GRAD_CLIP) + NaN-skip + optimizer update in fused
@@ -80,10 +91,14 @@ class BaseSolver:
             for k, v in ckpt.items():
                 if type(v) is float:
                     metric, score = k, v
-            self.step = ckpt["global_step"]
-            self.optimizer.load_opt_state_dict(ckpt["optimizer"])
-            self.verbose("Load ckpt from {}, restarting at step {} (recorded {} = {:.2f} %)".format(
-                self.paras.load, self.step, metric, score))
+            if self.mode == "train":
+                self.step = ckpt["global_step"]
+                self.optimizer.load_opt_state_dict(ckpt["optimizer"])
+                self.verbose("Load ckpt from {}, restarting at step {} (recorded {} = {:.2f} %)".format(
+                    self.paras.load, self.step, metric, score))
+            else:
+                self.model.eval()
+                self.verbose("Evaluation target = {} (recorded {} = {:.2f} %)".format(self.paras.load, metric, score))
 
     def verbose(self, msg):
         if self.paras.verbose and self.dp.rank == 0:

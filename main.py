@@ -3,7 +3,7 @@
 """Same command line as the reference's main.py (/root/reference/main.py:13-47), driving the B200-native Solver.
     python main.py --config config/b200/cfgB_ctc_char.yaml [--njobs 0] [--seed 0] [--load ckpt]
     torchrun --nproc-per-node 8 --master-addr 127.0.0.1 main.py --config ...      (data parallel, one process per GPU)
---cpu / --test / --lm select reference workloads that are outside this hot path and are refused."""
+--test runs greedy decoding (decode.beam_size 1); --cpu / --lm select reference workloads outside this hot path."""
 import argparse
 import importlib
 
@@ -23,7 +23,7 @@ parser.add_argument("--cudnn-ctc", action="store_true", help="(reference flag) u
 parser.add_argument("--njobs", default=6, type=int, help="Number of DataLoader worker processes.")
 parser.add_argument("--cpu", action="store_true", help="(reference flag) use the reference itself for CPU runs")
 parser.add_argument("--no-pin", action="store_true", help="Disable pin-memory for dataloader")
-parser.add_argument("--test", action="store_true", help="(reference flag) decoding is outside this hot path")
+parser.add_argument("--test", action="store_true", help="Test the model (greedy decoding, decode.beam_size: 1).")
 parser.add_argument("--no-msg", action="store_true", help="Hide all messages.")
 parser.add_argument("--lm", action="store_true", help="(reference flag) RNNLM training is outside this hot path")
 parser.add_argument("--amp", action="store_true", help="(reference flag) unsupported")
@@ -36,14 +36,18 @@ def main():
     setattr(paras, "gpu", not paras.cpu)
     setattr(paras, "pin_memory", not paras.no_pin)
     setattr(paras, "verbose", not paras.no_msg)
-    if paras.cpu or paras.test or paras.lm or paras.cudnn_ctc:
-        raise SystemExit("--cpu / --test / --lm / --cudnn-ctc select reference paths outside the B200 hot path")
+    if paras.cpu or paras.lm or paras.cudnn_ctc:
+        raise SystemExit("--cpu / --lm / --cudnn-ctc select reference paths outside the B200 hot path")
     config = yaml.load(open(paras.config, "r"), Loader=yaml.FullLoader)
     np.random.seed(paras.seed)
     torch.manual_seed(paras.seed)
     torch.cuda.manual_seed_all(paras.seed)
     pkg = importlib.import_module("end-to-end-asr-pytorch_b200")
-    solver = pkg.train_asr.Solver(config, paras, "train")
+    if paras.test:          # greedy decoding (decode.beam_size: 1); beam search stays the reference's CPU path
+        assert paras.load is None, "Load option is mutually exclusive to --test"
+        solver = pkg.test_asr.Solver(config, paras, "test")
+    else:
+        solver = pkg.train_asr.Solver(config, paras, "train")
     solver.load_data()
     solver.set_model()
     solver.exec()

@@ -140,3 +140,63 @@ def test_bench_reference_arm_contract():
     assert line["value"] > 0 and line["e2e"]["value"] == line["value"]
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["kind"] == "port"
     assert line["config"]["workload"].startswith("cfgB")
+
+
+def test_greedy_decode_rows_and_synthetic_decode_split(pkg):
+    """Host side of the `--test` greedy path (bin/test_asr.py:199-217): csv rows, empty hypothesis -> one blank,
+    the reference's un-collapsed CTC hypotheses by default, and the (dev, test) split of the synthetic corpus."""
+    tok = pkg.data._VocabOnly(12)
+    res = [("0", [[3, 3, 0, 4, 1, 7]], [3, 4, 1, 0]), ("1", [[1, 5]], [6, 1])]
+    rows = pkg.test_asr.format_hyp_rows(tok, res)
+    assert rows == ["0\t3 3 4\t3 4", "1\t \t6"]
+    assert pkg.test_asr.format_hyp_rows(tok, res, collapse_repeats=True)[0] == "0\t3 4\t3 4"
+    dv, tt, bs_a, bs_b, mode, msg = pkg.data.create_dataset(tok, False, name="Synthetic", path="", bucketing=False,
+                                                            batch_size=3, dev_split=["a"], test_split=["b"],
+                                                            n_samples=8000, vocab_size=12)
+    assert mode == "test" and (bs_a, bs_b) == (1, 1) and len(dv) == 2 and len(tt) == 2
+    assert any("Test sets" in m for m in msg)
+    names, wave, wave_len, txt = pkg.data.collect_wave_batch([dv[0]], lambda n: 1 + (n - 400) // 160, "test")
+    assert wave.shape[0] == 3 and txt.shape[0] == 3 and list(wave_len) == sorted(wave_len, reverse=True)
+
+
+def test_greedy_decode_exec_with_stub_model(pkg, tmp_path):
+    """exec()/greedy_decode() of the `--test` Solver on stand-ins for the front end and the model: utterance
+    numbering across batches, arg-max feedback ids -> csv, CTC-only models read the kernel's arg-max ids."""
+    import argparse
+    S = pkg.test_asr.Solver
+    tok = pkg.data._VocabOnly(8)
+
+    class FrontEnd:
+        def batch(self, wave, wave_len, t_max=None):
+            return wave.unsqueeze(-1), torch.tensor([10, 8])
+
+    class Model:
+        def __init__(self, att):
+            self.enable_att, self.last_ctc_argmax, self.steps = att, None, []
+
+        def __call__(self, feat, feat_len, steps, emb_decoder=None):
+            self.steps.append(steps)
+            ids = torch.tensor([[3, 4, 1, 0, 0], [5, 5, 6, 1, 0]])
+            if self.enable_att:
+                return None, None, torch.nn.functional.one_hot(ids, 8).float(), None, None
+            self.last_ctc_argmax = ids
+            return torch.zeros(2, 5, 8), None, None, None, None
+
+    def batch(seed):
+        return (["a", "b"], torch.zeros(2, 16), torch.tensor([16, 12]), torch.tensor([[3, 4, 1], [5, 6, 1]]) + 0 * seed)
+
+    for att, collapse, want in ((True, False, "5 5 6"), (False, False, "5 5 6"), (False, True, "5 6")):
+        s = object.__new__(S)
+        s.config = {"decode": {"beam_size": 1, "max_len_ratio": 0.5, "ctc_collapse": collapse},
+                    "data": {"corpus": {"batch_size": 2}}}
+        s.paras = argparse.Namespace(verbose=False)
+        s.dp = argparse.Namespace(rank=0)
+        s.device, s.step, s.emb_decoder, s.tokenizer = "cpu", 0, None, tok
+        s.audio_transform, s.decoder = FrontEnd(), Model(att)
+        s.dv_set, s.tt_set = [batch(0), batch(1)], [batch(2)]
+        s.output_file = str(tmp_path / ("o%d%d" % (att, collapse))) + "_{}_{}.csv"
+        s.exec()
+        dev = open(s.output_file.format("dev", "output")).read().splitlines()
+        assert dev == ["idx\thyp\ttruth", "0\t3 4\t3 4", "1\t%s\t5 6" % want, "2\t3 4\t3 4", "3\t%s\t5 6" % want]
+        assert len(open(s.output_file.format("test", "output")).read().splitlines()) == 3
+        assert s.decoder.steps == [5, 5, 5]            # int(max feature length 10 * max_len_ratio 0.5)
