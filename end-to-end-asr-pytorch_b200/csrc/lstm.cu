@@ -6,17 +6,22 @@
 // step loops and drift out of phase: while one group waits for its state exchange, the FMA pipes work for the other,
 // so the cross-SM latency is hidden behind compute.
 //
-//   group g (4 warps): 32 register tiles of 4 gates x 8 rows (one W float4 feeds 32 FMAs - the loop is bound by
-//              shared-memory wavefronts otherwise); the K dimension of a tile is split over 4 lanes, one per
-//              bulk-copy chunk (a lane waits only for its own chunk; chunks are padded apart in shared memory so the 4
-//              lanes hit different banks), software-pipelined LDS->FMA loop, two warp shuffles reduce the K-chunks,
-//              then each of the 4 lanes finishes the pointwise cell update of two rows.
+//   group g (4 warps), step GEMM in one of two forms (the planner decides per shape, make_plan):
+//     tensor cores (default whenever a half is exactly 16 rows, H % 32 == 0, UB even <= 16: every BASELINE shape):
+//              error-compensated 3xTF32 mma.sync.m16n8k8 with fragment-major operands, see "Tensor-core variant" below;
+//     fp32 FMA (every other shape): 32 register tiles of 4 gates x 8 rows (one W float4 feeds 32 FMAs), K split over
+//              4 lanes (one per bulk-copy chunk, chunks padded apart in shared memory), packed FFMA2 inner loops with
+//              explicit A/B register double buffering, two warp shuffles reduce the K-chunks, then each of the 4 lanes
+//              finishes the pointwise cell update of two rows.
+//     In both forms the two groups take turns on the math pipes (mbarrier hand-off), so that one group's exchange is
+//     hidden behind the other group's loop.
 //   control warp g (1 lane): waits on the group's "done" mbarrier, issues ONE fence + release for the whole group
 //              (off the compute warps' critical path), spins on the peers' counter, then pulls the next [H,Bh] state
 //              block (fwd) / [nub,Bh,UB] inbox of partial products (bwd) from L2 with 1-D bulk async copies (TMA)
 //              that complete on per-chunk "full" mbarriers.
 // There is no CTA-wide or grid-wide barrier in the step loops; the backward has one 128-thread named barrier per step
-// (the dG tile of a group feeds all of its GEMM tiles).
+// (the dG tile of a group feeds all of its GEMM tiles).  Batches whose CTAs cannot all be co-resident are processed as
+// consecutive launches over row blocks (Plan::nsplit).
 //
 //   fwd step : gates[b, 4UB] = Gx[b,t] + h_{t-1}[b,:] . Wslice^T ; pointwise ; publish h_t slice
 //   bwd step : dh = dOut[b,t] + sum_src partial_src[b, my units] ; pointwise -> dG[b,4UB] ;
