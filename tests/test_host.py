@@ -106,3 +106,36 @@ def test_init_adadelta_matches_reference_quirks(pkg):
     b = model.decoder.layers.bias_ih_l0
     assert float(b[32:64].min()) == 1.0 and float(b[:32].abs().max()) == 0 and float(b[64:].abs().max()) == 0
     assert float(model.decoder.layers.bias_hh_l0.abs().max()) == 0
+
+
+def test_lstm_planner_sweep_is_consistent(pkg):
+    """Every (B, H, ndir) either has a plan that fits the machine (<= 148 co-resident CTAs, unit block divides H,
+    a workspace size, tensor-core flag in {0,1}) or is refused with rc < 0 and a message - never a crash or a zero."""
+    from ctypes import c_int, byref
+    lib = pkg.load_library()
+    ub, bc, n = c_int(), c_int(), c_int()
+    seen_tc, seen_fma, refused = 0, 0, 0
+    for H in (16, 32, 48, 64, 96, 128, 160, 256, 320, 512, 640, 768, 1024):
+        for B in (1, 2, 3, 8, 16, 17, 32, 40, 64, 100, 130, 256):
+            for ndir in (1, 2):
+                rc = lib.b200asr_bilstm_plan(B, H, ndir, byref(ub), byref(bc), byref(n))
+                tc = lib.b200asr_bilstm_uses_tensor_cores(B, H, ndir)
+                ws = lib.b200asr_bilstm_workspace_bytes(B, 50, H, ndir)
+                if rc != 0:
+                    refused += 1
+                    assert rc < 0 and tc == -1 and ws == 0 and "no feasible decomposition" in pkg.lib.last_error()
+                    continue
+                assert 1 <= n.value <= 148 and H % ub.value == 0 and 4 <= bc.value <= 64 and ws > 0
+                assert tc in (0, 1)
+                if tc:
+                    assert bc.value == 32 and ub.value % 2 == 0 and ub.value <= 16 and H % 32 == 0
+                    seen_tc += 1
+                else:
+                    seen_fma += 1
+    assert seen_tc > 20 and seen_fma > 20
+    assert lib.b200asr_bilstm_uses_tensor_cores(64, 512, 2) == 1 and lib.b200asr_bilstm_uses_tensor_cores(3, 16, 2) == 0
+    lib.b200asr_debug_set_lstm_mode(1)
+    try:
+        assert lib.b200asr_bilstm_uses_tensor_cores(64, 512, 2) == 0
+    finally:
+        lib.b200asr_debug_set_lstm_mode(0)
