@@ -1137,6 +1137,9 @@ __device__ __forceinline__ void fwd_stream_mma(const LstmParams& p, int tid, int
 }
 
 // Shared memory: Wm[H/8][npairs][32] float4 | hs[NH][4 chunks, padded] | barriers
+// GEN3 = the experimental single-stream variant; it is a separate instantiation so that the measured and validated
+// generation-2 kernel is not perturbed by it.
+template <bool GEN3>
 __global__ void __launch_bounds__(LSTM_THREADS, 1) bilstm_fwd_mma_kernel(LstmParams p) {
     extern __shared__ __align__(128) unsigned char s_raw[];
     const int H = p.H, UB = p.UB, T = p.T, NH = p.NH;
@@ -1163,8 +1166,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) bilstm_fwd_mma_kernel(LstmPar
     }
     if (tid == 0) {
         for (int i = 0; i < 2 * LSTM_NCHUNK; ++i) mbar_init(&full[i], 1);
-        const bool stream = (p.flags & 16) && H % 128 == 0;    // generation 3: 8 warps arrive per half
-        for (int i = 0; i < 2; ++i) mbar_init(&done[i], stream ? 2 * LSTM_GTHREADS / 32 : LSTM_GTHREADS / 32);
+        for (int i = 0; i < 2; ++i) mbar_init(&done[i], GEN3 ? 2 * LSTM_GTHREADS / 32 : LSTM_GTHREADS / 32);
         for (int i = 0; i < 2; ++i) mbar_init(&turn[i], LSTM_GTHREADS / 32);
         mbar_fence_init();
     }
@@ -1187,7 +1189,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) bilstm_fwd_mma_kernel(LstmPar
         }
         return;
     }
-    if ((p.flags & 16) && H % 128 == 0) {
+    if constexpr (GEN3) {
         fwd_stream_mma(p, tid, dir, bg, ub, Wm, hs, full, done, xb, reinterpret_cast<float4*>(turn + 2));
         return;
     }
@@ -1500,6 +1502,7 @@ __device__ __forceinline__ void bwd_stream_mma(const LstmParams& p, int tid, int
 }
 
 // Shared memory: Wm[H/32][4UB/8][32][8] | inbox[NH][16*H] | dGs[NH][4UB*16] | barriers
+template <bool GEN3>
 __global__ void __launch_bounds__(LSTM_THREADS, 1) bilstm_bwd_mma_kernel(LstmParams p) {
     extern __shared__ __align__(128) unsigned char s_raw[];
     const int H = p.H, UB = p.UB, Bc = p.Bc, T = p.T, nub = p.nub, NH = p.NH;
@@ -1523,8 +1526,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) bilstm_bwd_mma_kernel(LstmPar
     }
     if (tid == 0) {
         for (int i = 0; i < 2 * LSTM_NCHUNK; ++i) mbar_init(&full[i], 1);
-        // generation 3 (flag bit 4): all 8 compute warps arrive on each half's `done`
-        for (int i = 0; i < 2; ++i) mbar_init(&done[i], (p.flags & 16) ? 2 * LSTM_GTHREADS / 32 : LSTM_GTHREADS / 32);
+        for (int i = 0; i < 2; ++i) mbar_init(&done[i], GEN3 ? 2 * LSTM_GTHREADS / 32 : LSTM_GTHREADS / 32);
         for (int i = 0; i < 2; ++i) mbar_init(&turn[i], LSTM_GTHREADS / 32);
         mbar_fence_init();
     }
@@ -1549,7 +1551,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) bilstm_bwd_mma_kernel(LstmPar
         }
         return;
     }
-    if (p.flags & 16) {
+    if constexpr (GEN3) {
         bwd_stream_mma(p, tid, dir, bg, ub, reinterpret_cast<const float4*>(Wr), inbox, dGs, full, done, xb);
         return;
     }
@@ -1619,8 +1621,7 @@ static size_t smem_bwd_bytes(int H, int UB, int Bc) {
 }
 static size_t smem_fwd_mma_bytes(int H, int UB) {
     const int npairs = (UB + 3) / 4;
-    return (size_t)H * npairs * 64 + 2 * ((size_t)H * 16 + LSTM_NCHUNK * LSTM_CHUNK_PAD) * 4 + (2 * LSTM_NCHUNK + 4) * 8 + 128 +
-           8192 /* partial-sum scratch of the experimental generation-3 kernel */;
+    return (size_t)H * npairs * 64 + 2 * ((size_t)H * 16 + LSTM_NCHUNK * LSTM_CHUNK_PAD) * 4 + (2 * LSTM_NCHUNK + 4) * 8 + 128;
 }
 
 // One launch over B rows: every (direction, batch-group, unit-block) CTA must be co-resident.
@@ -1778,9 +1779,13 @@ static int bilstm_run(bool bwd, float* gates, const float* w_hh, float* cstate, 
     p.err_flag = err_flag; p.B = B; p.T = T; p.H = H; p.ndir = ndir; p.UB = pl.UB; p.Bc = pl.Bc; p.nub = pl.nub;
     p.nbg = pl.nbg; p.NH = pl.NH; p.R = pl.R; p.mma = pl.mma; p.flags = g_lstm_flags;
     p.trace = (bwd == ((g_lstm_flags & 8) != 0)) ? g_trace : nullptr;   // flag bit 3: trace the backward kernel
-    const void* fn = pl.mma ? (bwd ? (const void*)bilstm_bwd_mma_kernel : (const void*)bilstm_fwd_mma_kernel)
-                            : (bwd ? (const void*)bilstm_bwd_kernel : (const void*)bilstm_fwd_kernel);
-    const size_t smem = bwd ? pl.smem_bwd : pl.smem_fwd;
+    const bool gen3 = pl.mma && (g_lstm_flags & 16) && (bwd || H % 128 == 0);   // experimental, never the default
+    const void* fn = !pl.mma ? (bwd ? (const void*)bilstm_bwd_kernel : (const void*)bilstm_fwd_kernel)
+                     : gen3  ? (bwd ? (const void*)bilstm_bwd_mma_kernel<true> : (const void*)bilstm_fwd_mma_kernel<true>)
+                             : (bwd ? (const void*)bilstm_bwd_mma_kernel<false> : (const void*)bilstm_fwd_mma_kernel<false>);
+    // + the 8 KB partial-sum scratch of the experimental generation-3 forward kernel
+    const size_t smem = (bwd ? pl.smem_bwd : pl.smem_fwd) + ((gen3 && !bwd) ? 8192 : 0);
+    B200_REQUIRE(smem <= (size_t)max_optin_smem(), "bilstm: %zu B of shared memory exceed the device limit", smem);
     B200_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, LSTM_THREADS, smem));
