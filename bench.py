@@ -49,6 +49,10 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time the eager step instead of the CUDA-graph replay")
+    ap.add_argument("--no-parity", action="store_true", help="skip the same-run parity check against the CPU path")
+    ap.add_argument("--parity-workloads", default="auto",
+                    help="comma list of workloads parity-checked at full size after the timed regions "
+                         "(auto = the benchmarked one, plus cfgB,cfgC,cfgD on a default 1-GPU run)")
     return ap.parse_args()
 
 
@@ -178,6 +182,123 @@ def cpu_arm(cfg, vocab, n_samples, batch, steps, warmup):
     total = sum(times)
     return {"value": batch * len(times) / total, "ms_per_step": 1000.0 * total / len(times), "batch": batch,
             "cores": torch.get_num_threads(), "loss": loss}
+
+
+def parity_check(pkg, step_fn, cfg, waves, lens, txt, dev, n_ref=8):
+    """Same-run, full-size parity (BASELINE metric, second half): the product path on the FULL per-GPU batch - front
+    end, encoder, CTC head / decoder, both losses, backward, all through the CUDA kernels at the benchmark's shapes -
+    against the reference's CPU path (oracle/ref_port.py: kaldi.fbank per utterance, ATen LSTM / CTC / CE) on the
+    first `n_ref` utterances, from the SAME state_dict and the SAME waveforms.  The GPU loss is restricted to those
+    utterances (CTC weights 0 and CE targets ignored for the others), so losses and every parameter gradient are
+    directly comparable while all B rows run through the kernels.  Utterances are independent given the global T_max
+    (SURVEY.md F5), which both sides share.  Mirrors /root/reference/bin/train_asr.py:104-137."""
+    from oracle import ref_port
+    import numpy as np
+    model, opt = step_fn.model, step_fn.optimizer
+    lam = model.ctc_weight
+    B = waves.shape[0]
+    n = min(n_ref, B)
+    P = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    # ---- product path
+    model.train()
+    opt.pre_step(step_fn.step_id)                      # zero the flat gradient buffer
+    wave_dev, txt_dev = waves.to(dev), txt.to(dev)
+    feat, feat_len = step_fn.front_end(wave_dev, lens.to(dev))
+    txt_len = (txt_dev != 0).sum(-1)
+    ctc_out, enc_len, att_out, _, _ = model(feat, feat_len, int(txt.shape[1]), tf_rate=1.0, teacher=txt_dev)
+    total = 0
+    g = {}
+    if ctc_out is not None:
+        w = torch.zeros(B, device=dev)
+        w[:n] = 1.0 / (txt_len[:n].clamp_min(1).float() * n)
+        ctc, nll = pkg.ops.CTCLossFn.apply(ctc_out.transpose(0, 1), txt_dev, enc_len, txt_len, 0, w)
+        total = total + ctc * lam
+        g.update(ctc_loss=float(ctc), nll=nll[:n].detach().cpu().double().numpy(),
+                 ctc_output=ctc_out[:n].detach().cpu(), ctc_argmax=model.last_ctc_argmax[:n].cpu())
+    if att_out is not None:
+        b, t, v = att_out.shape
+        tgt = txt_dev[:, :t].clone()
+        tgt[n:] = 0
+        ce = pkg.ops.cross_entropy(att_out.reshape(b * t, v), tgt.reshape(-1), ignore_index=0)
+        total = total + ce * (1 - lam)
+        g.update(att_loss=float(ce), att_output=att_out[:n].detach().cpu())
+    total.backward()
+    if model.enable_att:
+        model.attention.reset_mem()
+        model.decoder.hidden_state = None
+    opt.buf.rebind_grads()
+    torch.cuda.synchronize()
+    g_grads = {k: p.grad.detach().cpu().clone() for k, p in model.named_parameters() if p.grad is not None}
+    g_feat = feat[:n].detach().cpu()
+    # ---- reference CPU path
+    torch.set_num_threads(min(16, os.cpu_count() or 1))
+    Pr = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    wl = [waves[b:b + 1, :int(lens[b])] for b in range(n)]
+    tl = [[int(x) for x in txt[b] if int(x) != 0] for b in range(n)]
+    f_ref, l_ref, t_ref, order = ref_port.collate(wl, cfg["data"]["audio"], tl)
+    assert order == list(range(n)), "synthetic batch must already be sorted by length"
+    if f_ref.shape[1] < feat.shape[1]:                 # the encoder computes through padding: share the global T_max
+        f_ref = torch.nn.functional.pad(f_ref, (0, 0, 0, feat.shape[1] - f_ref.shape[1]))
+    res = ref_port.forward_losses(Pr, cfg["model"], f_ref, l_ref, t_ref)
+    res["total_loss"].backward()
+
+    def rel(a, b, floor):
+        a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+        return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor)))
+
+    out = {"utterances_compared": n, "batch_through_kernels": B, "frames": int(feat.shape[1]),
+           "feat_max_abs_err": float((g_feat - f_ref).abs().max()),
+           "total_loss_rel_err": abs(float(total) - float(res["total_loss"])) / abs(float(res["total_loss"]))}
+    if ctc_out is not None:
+        lp_ref = res["ctc_output"].detach()
+        lp = g["ctc_output"][:, :lp_ref.shape[1]]
+        nll_ref = torch.nn.functional.ctc_loss(lp_ref.transpose(0, 1), t_ref, res["encode_len"], (t_ref != 0).sum(-1),
+                                               blank=0, reduction="none").double().numpy()
+        am_ref = lp_ref.argmax(-1)
+        mism = (g["ctc_argmax"][:, :am_ref.shape[1]] != am_ref)
+        top2 = lp_ref.topk(2, dim=-1).values
+        margin = (top2[..., 0] - top2[..., 1])
+        out.update(ctc_loss_rel_err=abs(g["ctc_loss"] - float(res["ctc_loss"])) / abs(float(res["ctc_loss"])),
+                   ctc_nll_rel_err=rel(g["nll"], nll_ref, 1e-3),
+                   logits_rel_err=rel(lp.numpy(), lp_ref.numpy(), 1.0),
+                   logits_max_abs_err=float((lp - lp_ref).abs().max()),
+                   ctc_argmax_equal=bool(not mism.any()), ctc_argmax_mismatches=int(mism.sum()),
+                   ctc_argmax_frames=int(mism.numel()),
+                   ctc_argmax_mismatch_max_ref_margin=float(margin[mism].max()) if mism.any() else 0.0)
+    if att_out is not None:
+        a_ref = res["att_output"].detach()
+        a = g["att_output"][:, :a_ref.shape[1]]
+        mism = a.argmax(-1) != a_ref.argmax(-1)
+        top2 = a_ref.topk(2, dim=-1).values
+        margin = (top2[..., 0] - top2[..., 1])
+        out.update(att_loss_rel_err=abs(g["att_loss"] - float(res["att_loss"])) / abs(float(res["att_loss"])),
+                   att_logits_rel_err=rel(a.numpy(), a_ref.numpy(), 1.0),
+                   att_logits_max_abs_err=float((a - a_ref).abs().max()),
+                   att_argmax_equal=bool(not mism.any()), att_argmax_mismatches=int(mism.sum()),
+                   att_argmax_tokens=int(mism.numel()),
+                   att_argmax_mismatch_max_ref_margin=float(margin[mism].max()) if mism.any() else 0.0)
+    sq_g = sq_r = 0.0
+    worst, worst_key = 0.0, None
+    errs = []
+    for k, ref in Pr.items():
+        if ref.grad is None or k not in g_grads:
+            continue
+        r = ref.grad.double()
+        d = g_grads[k].double()
+        sq_g += float((d ** 2).sum())
+        sq_r += float((r ** 2).sum())
+        errs.append((k, float((d - r).abs().max()), float(r.abs().max())))
+    gmax = max(m for _, _, m in errs)
+    for k, e, m in errs:
+        # error relative to the tensor's own scale; tensors whose true gradient is zero up to rounding (e.g. the
+        # softmax-invariant energy bias) are measured against 1e-6 of the largest gradient instead
+        e = e / max(m, 1e-6 * gmax)
+        if e > worst:
+            worst, worst_key = e, k
+    out.update(grad_norm_rel_err=abs(sq_g ** 0.5 - sq_r ** 0.5) / sq_r ** 0.5, grad_norm_ref=sq_r ** 0.5,
+               grad_max_scaled_err=worst, grad_worst_tensor=worst_key)
+    opt.buf.grad.zero_()
+    return out
 
 
 def main():
@@ -311,6 +432,30 @@ def main():
 
     if rank != 0:
         return 0
+    # ---- same-run parity at the benchmark's full size (CTC-loss rel-err is half of BASELINE.json's metric) ----
+    parity = None
+    if not args.no_parity:
+        names = [args.workload]
+        if args.parity_workloads == "auto":
+            if world == 1 and not args.batch and args.n_samples == 192000:
+                names += [w for w in ("cfgB", "cfgC", "cfgD") if w != args.workload]
+        else:
+            names = [w for w in args.parity_workloads.split(",") if w]
+        parity = {}
+        for w in names:
+            log("parity check %s (full batch through the kernels vs the CPU path on 8 utterances)" % w)
+            if w == args.workload:
+                parity[w] = parity_check(pkg, step_fn, cfg, waves, lens, txt, dev)
+            else:
+                cfg_w = pkg.synthetic.load_config(w)
+                vocab_w = cfg_w["data"]["corpus"]["vocab_size"]
+                st = pkg.trainer.TrainStep(cfg_w, vocab_w, device=dev, dp=dp, seed=0)
+                wv, ln, tx = pkg.synthetic.make_batch(vocab_w, cfg_w["data"]["corpus"]["batch_size"], args.n_samples,
+                                                      seed=1000)
+                parity[w] = parity_check(pkg, st, cfg_w, wv, ln, tx, dev)
+                del st
+                torch.cuda.empty_cache()
+            log("parity %s: %s" % (w, json.dumps(parity[w])))
     peak, peak_src = peaks()
     kernels = {}
     top, top_ms = None, -1.0
@@ -356,7 +501,7 @@ def main():
             "loss": loss, "gpu_launches": int(round(launches_per_step * args.steps)), "clocks": clocks, "e2e": e2e,
             "roofline": roofline, "kernels": kernels, "cuda_graph": bool(use_graph),
             "eager_ms_per_step": eager_ms / args.steps, "own_kernel_ms_per_step": own_ms,
-            "library_ms_per_step": eager_ms / args.steps - own_ms,
+            "library_ms_per_step": eager_ms / args.steps - own_ms, "parity": parity,
             "note": "kernels/roofline come from the eager pass (CUDA events around each C-ABI launch); value and "
                     "e2e replay the same step as one CUDA graph when cuda_graph is true; gpu_launches counts this "
                     "library's kernels per step x steps"}

@@ -33,6 +33,7 @@
 // Reference behaviour restated: torch.nn.LSTM as called from /root/reference/src/module.py:112-113,129-132 (single
 // layer, batch_first, zero initial state, run over the zero-padded frames - no packing), gates i,f,g,o.
 #include "common.cuh"
+#include "lstm_umma.h"
 #include "../../include/b200asr.h"
 
 namespace b200asr {
@@ -56,8 +57,7 @@ struct LstmParams {
     int B, T, H, ndir, UB, Bc, nub, nbg, NH, R;
     int b0, Bend;        // this launch covers batch rows [b0, Bend) of the B rows the tensors hold
     int flags;           // debug switches: bit 2 = first-generation MMA loops (every warp polls, compiler-pipelined),
-                         // bit 3 = clock64 trace of the backward instead of the forward kernel,
-                         // bit 4 = EXPERIMENTAL generation-3 single-stream kernels (never the default)
+                         // bit 3 = clock64 trace of the backward instead of the forward kernel
     int mma;             // 1: tensor-core (3xTF32 mma.sync) step GEMMs, see the *_mma kernels
 };
 
@@ -1001,145 +1001,6 @@ __device__ __forceinline__ void fwd_group_mma_v2(const LstmParams& p, int g, int
     }
 }
 
-// ---- forward, tensor cores, generation 3 (EXPERIMENTAL, off unless debug flag bit 4 is set; not yet run on a GPU):
-// one stream of 8 warps alternates between the two 16-row halves in program order (see bwd_stream_mma).  Warps q and
-// q+4 share unit quad q and split its K range in halves (chunks 0-1 / 2-3), so each scheduler always has two MMA warps;
-// the two partial sums are swapped through a double-buffered 8 KB scratch so that warp kh finishes row gid + 8*kh.
-// Needs H % 128 == 0 (k-halves of whole 8-k-step blocks, no block straddling a bulk-copy chunk).
-__device__ __forceinline__ void fwd_stream_mma(const LstmParams& p, int tid, int dir, int bg, int ub, const float4* Wm,
-                                               const float* hs, uint64_t* full, uint64_t* done, float* xb,
-                                               float4* scratch) {
-    const int H = p.H, UB = p.UB, T = p.T;
-    const int KS = H / 8, KSH = KS / 2, KSC = KS / LSTM_NCHUNK;
-    const int KC = H / LSTM_NCHUNK;
-    const int npairs = (UB + 3) / 4;
-    const int warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
-    const int q = warp & 3, kh = warp >> 2;
-    const bool has_pair = q < npairs;
-    const int u = q * 4 + tig;
-    const bool has_unit = has_pair && u < UB;
-    const int ug = ub * UB + (has_unit ? u : 0);
-    const size_t half_elems = (size_t)H * 16;
-    const size_t hs_half = (size_t)LSTM_NCHUNK * (KC * 16 + LSTM_CHUNK_PAD);
-    const size_t pub_off = ((size_t)(ug >> 3) * 32 + gid * 4 + (ug & 3)) * 4 + 2 * ((ug >> 2) & 1) + kh;
-    const size_t wstride = (size_t)npairs * 32;
-    float c_reg[2] = {0.f, 0.f};
-    int par = 0;
-
-    for (int step = 0; step < T; ++step) {
-        const int tt = dir ? (T - 1 - step) : step;
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-            const int brow = p.b0 + bg * p.Bc + g * 16 + gid + 8 * kh;
-            const bool ok = has_unit && brow < p.Bend;
-            float4 gx = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ok) gx = *reinterpret_cast<const float4*>(p.gates + ((((size_t)dir * p.B + brow) * T + tt) * H + ug) * 4);
-            float mine[4] = {0.f, 0.f, 0.f, 0.f};              // i, f, g, o pre-activation sums of my row
-            if (step > 0) {
-                if (q == 0) {                                  // warps 0 and 4 poll for their K half
-                    mbar_wait(&full[g * LSTM_NCHUNK + 2 * kh], (uint32_t)((step - 1) & 1));
-                    mbar_wait(&full[g * LSTM_NCHUNK + 2 * kh + 1], (uint32_t)((step - 1) & 1));
-                }
-                named_bar_sync(3 + kh, LSTM_GTHREADS);
-                if (has_pair) {
-                    float d0[3][4], d1[3][4];
-#pragma unroll
-                    for (int z = 0; z < 3; ++z)
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) d0[z][i] = d1[z][i] = 0.f;
-                    const float4* ap = reinterpret_cast<const float4*>(hs + (size_t)g * hs_half) + lane;
-                    const float4* wp = Wm + (size_t)q * 32 + lane;
-                    int ldk = kh * KSH, ldrem = KSC, ldpad = 2 * kh;
-#define LSTM_MMA_LOAD(areg, wreg)                                                   \
-    {                                                                               \
-        _Pragma("unroll") for (int j = 0; j < 4; ++j) {                             \
-            areg[j] = ap[(size_t)(ldk + j) * 32 + ldpad];                           \
-            wreg[j] = wp[(size_t)(ldk + j) * wstride];                              \
-        }                                                                           \
-        ldk += 4; ldrem -= 4;                                                       \
-        if (ldrem == 0) { ldrem = KSC; ++ldpad; }                                   \
-    }
-#define LSTM_MMA_BLOCK(areg, wreg)                                                  \
-    _Pragma("unroll") for (int j = 0; j < 4; ++j) {                                 \
-        uint32_t ah[4], al[4], bh[4], bl[4];                                        \
-        split4(areg[j], ah, al);                                                    \
-        split4(wreg[j], bh, bl);                                                    \
-        mma_tf32(d0[0], ah, bh[0], bh[1]);                                          \
-        mma_tf32(d1[0], ah, bh[2], bh[3]);                                          \
-        mma_tf32(d0[1], al, bh[0], bh[1]);                                          \
-        mma_tf32(d1[1], al, bh[2], bh[3]);                                          \
-        mma_tf32(d0[2], ah, bl[0], bl[1]);                                          \
-        mma_tf32(d1[2], ah, bl[2], bl[3]);                                          \
-    }
-                    float4 aA[4], wA[4], aB[4], wB[4];
-                    LSTM_MMA_LOAD(aA, wA)
-                    int done_ks = 0;
-#pragma unroll 1
-                    for (; done_ks + 8 < KSH; done_ks += 8) {
-                        LSTM_MMA_LOAD(aB, wB)
-                        LSTM_MMA_BLOCK(aA, wA)
-                        LSTM_MMA_LOAD(aA, wA)
-                        LSTM_MMA_BLOCK(aB, wB)
-                    }
-                    LSTM_MMA_LOAD(aB, wB)
-                    LSTM_MMA_BLOCK(aA, wA)
-                    LSTM_MMA_BLOCK(aB, wB)
-#undef LSTM_MMA_LOAD
-#undef LSTM_MMA_BLOCK
-                    float t0[4], t1[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        t0[i] = d0[0][i] + (d0[1][i] + d0[2][i]);
-                        t1[i] = d1[0][i] + (d1[1][i] + d1[2][i]);
-                    }
-                    // fragment rows: [0],[1] = row gid, [2],[3] = row gid+8.  I keep row gid + 8*kh, my partner the other
-                    mine[0] = kh ? t0[2] : t0[0];
-                    mine[1] = kh ? t0[3] : t0[1];
-                    mine[2] = kh ? t1[2] : t1[0];
-                    mine[3] = kh ? t1[3] : t1[1];
-                    const float4 other = kh ? make_float4(t0[0], t0[1], t1[0], t1[1])
-                                            : make_float4(t0[2], t0[3], t1[2], t1[3]);
-                    scratch[(((size_t)par * 4 + q) * 2 + kh) * 32 + lane] = other;
-                }
-                named_bar_sync(5 + q, 64);                     // the two K halves of quad q
-                if (has_pair) {
-                    const float4 o = scratch[(((size_t)par * 4 + q) * 2 + (1 - kh)) * 32 + lane];
-                    mine[0] += o.x; mine[1] += o.y; mine[2] += o.z; mine[3] += o.w;
-                }
-                par ^= 1;
-            }
-            float hq = 0.f, cq = 0.f;
-            float4 gq = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ok) {
-                const float ig = sigmoidf_(gx.x + mine[0]);
-                const float fg = sigmoidf_(gx.y + mine[1]);
-                const float gg = tanhf(gx.z + mine[2]);
-                const float og = sigmoidf_(gx.w + mine[3]);
-                const float c = fmaf(fg, c_reg[g], ig * gg);
-                c_reg[g] = c;
-                hq = og * tanhf(c);
-                cq = c;
-                gq = make_float4(ig, fg, gg, og);
-            }
-            if (step + 1 < T) {
-                if (has_unit) xb[((size_t)g * 2 + (step & 1)) * half_elems + pub_off] = hq;
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&done[g]);
-            }
-            if (ok) {
-                const size_t row = ((size_t)dir * p.B + brow) * T + tt;
-                *reinterpret_cast<float4*>(p.gates + (row * H + ug) * 4) = gq;
-                p.cst[row * H + ug] = cq;
-                p.out[((size_t)brow * T + tt) * (p.ndir * H) + (size_t)dir * H + ug] = hq;
-            }
-        }
-    }
-}
-
-// Shared memory: Wm[H/8][npairs][32] float4 | hs[NH][4 chunks, padded] | barriers
-// GEN3 = the experimental single-stream variant; it is a separate instantiation so that the measured and validated
-// generation-2 kernel is not perturbed by it.
-template <bool GEN3>
 __global__ void __launch_bounds__(LSTM_THREADS, 1) bilstm_fwd_mma_kernel(LstmParams p) {
     extern __shared__ __align__(128) unsigned char s_raw[];
     const int H = p.H, UB = p.UB, T = p.T, NH = p.NH;
@@ -1166,7 +1027,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) bilstm_fwd_mma_kernel(LstmPar
     }
     if (tid == 0) {
         for (int i = 0; i < 2 * LSTM_NCHUNK; ++i) mbar_init(&full[i], 1);
-        for (int i = 0; i < 2; ++i) mbar_init(&done[i], GEN3 ? 2 * LSTM_GTHREADS / 32 : LSTM_GTHREADS / 32);
+        for (int i = 0; i < 2; ++i) mbar_init(&done[i], LSTM_GTHREADS / 32);
         for (int i = 0; i < 2; ++i) mbar_init(&turn[i], LSTM_GTHREADS / 32);
         mbar_fence_init();
     }
@@ -1187,10 +1048,6 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) bilstm_fwd_mma_kernel(LstmPar
                          xb + ((size_t)g * 2 + 0) * half_elems, xb + ((size_t)g * 2 + 1) * half_elems,
                          hs + (size_t)g * hs_half, soff, doff, bytes, g == 0);
         }
-        return;
-    }
-    if constexpr (GEN3) {
-        fwd_stream_mma(p, tid, dir, bg, ub, Wm, hs, full, done, xb, reinterpret_cast<float4*>(turn + 2));
         return;
     }
     const int g = tid / LSTM_GTHREADS;
@@ -1373,136 +1230,6 @@ __device__ __forceinline__ void bwd_group_mma(const LstmParams& p, int g, int gt
     }
 }
 
-// ---- backward, tensor cores, generation 3 (EXPERIMENTAL, off unless debug flag bit 4 is set; not yet run on a
-// GPU): ONE stream of 8 warps works on the two 16-row halves alternately in program order instead of two 4-warp
-// groups taking turns.  While the stream computes half B, half A's exchange is in flight, so the hiding is the same,
-// but during a GEMM every scheduler has TWO MMA warps (the ALU split work of one overlaps the MMAs of the other: a
-// lone warp serialises them, tools/micro/mma_rate.cu) and the pointwise pass has one (row, unit) item per thread.
-__device__ __forceinline__ void bwd_stream_mma(const LstmParams& p, int tid, int dir, int bg, int ub, const float4* Wm,
-                                               const float* inbox, float* dGs, uint64_t* full, uint64_t* done,
-                                               float* xb) {
-    const int H = p.H, UB = p.UB, T = p.T, nub = p.nub;
-    const int warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
-    constexpr int NW = 2 * LSTM_GTHREADS / 32;                 // 8 compute warps
-    const int KS2 = (4 * UB) / 8;
-    const int NB = H / 32;
-    const size_t inbox_elems = (size_t)16 * H;
-    const unsigned inv_ub = (65536u + UB - 1) / UB;
-    const bool it_in = tid < 16 * UB;                          // one (row, unit) item of the 16 x UB tile per thread
-    const int it_b = it_in ? tid / UB : 0;
-    const int it_u = it_in ? tid - it_b * UB : 0;
-    const int ug = ub * UB + it_u;
-    float dc_reg[2] = {0.f, 0.f};
-
-    for (int step = 0; step < T; ++step) {
-        const int fstep = T - 1 - step;
-        const int tt = dir ? (T - 1 - fstep) : fstep;
-        const int tt_prev = dir ? tt + 1 : tt - 1;
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-            const int row_b = p.b0 + bg * p.Bc + g * 16 + it_b;
-            const bool ok = it_in && row_b < p.Bend;
-            float4 gtv = make_float4(0.f, 0.f, 0.f, 0.f);
-            float ct = 0.f, cp = 0.f, dh = 0.f;
-            if (ok) {
-                const size_t row = ((size_t)dir * p.B + row_b) * T + tt;
-                gtv = *reinterpret_cast<const float4*>(p.gates + (row * H + ug) * 4);
-                ct = p.cst[row * H + ug];
-                if (fstep > 0) cp = p.cst[(((size_t)dir * p.B + row_b) * T + tt_prev) * H + ug];
-                dh = p.out[((size_t)row_b * T + tt) * (p.ndir * H) + (size_t)dir * H + ug];
-            }
-            const float* inb = inbox + (size_t)g * inbox_elems;
-            float* dgs = dGs + (size_t)g * 4 * UB * 16;
-            if (step > 0) {
-                if (warp == 0) {
-#pragma unroll
-                    for (int c = 0; c < LSTM_NCHUNK; ++c) mbar_wait(&full[g * LSTM_NCHUNK + c], (uint32_t)((step - 1) & 1));
-                }
-                named_bar_sync(3, 2 * LSTM_GTHREADS);
-                if (it_in) {
-                    const float* ib = inb + (size_t)it_b * UB + it_u;
-                    float s0 = 0.f, s1 = 0.f;
-                    int s = 0;
-                    for (; s + 1 < nub; s += 2) {
-                        s0 += ib[(size_t)s * 16 * UB];
-                        s1 += ib[(size_t)(s + 1) * 16 * UB];
-                    }
-                    if (s < nub) s0 += ib[(size_t)s * 16 * UB];
-                    dh += s0 + s1;
-                }
-            }
-            float4 dg = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ok) {
-                const float ig = gtv.x, fg = gtv.y, gg = gtv.z, og = gtv.w;
-                const float tc = tanhf(ct);
-                const float dc = dc_reg[g] + dh * og * (1.f - tc * tc);
-                dg.x = dc * gg * ig * (1.f - ig);
-                dg.y = dc * cp * fg * (1.f - fg);
-                dg.z = dc * ig * (1.f - gg * gg);
-                dg.w = dh * tc * og * (1.f - og);
-                dc_reg[g] = dc * fg;
-                const size_t row = ((size_t)dir * p.B + row_b) * T + tt;
-                *reinterpret_cast<float4*>(p.gates + (row * H + ug) * 4) = dg;
-            }
-            if (it_in) {
-                float* d = dgs + ((size_t)(it_u >> 1) * 32 + (it_b & 7) * 4) * 4 + (it_b >> 3) + 2 * (it_u & 1);
-                d[0] = dg.x; d[4] = dg.y; d[8] = dg.z; d[12] = dg.w;
-            }
-            named_bar_sync(1, 2 * LSTM_GTHREADS);              // dG tile of this half complete
-            if (step + 1 < T) {
-                float* outbase = xb + ((size_t)g * 2 + (step & 1)) * nub * inbox_elems;
-                const float4* ap = reinterpret_cast<const float4*>(dgs) + lane;
-                for (int nb = warp; nb < NB; nb += NW) {
-                    float d[4][3][4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-#pragma unroll
-                        for (int q = 0; q < 3; ++q)
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) d[j][q][i] = 0.f;
-                    const float4* wp = Wm + ((size_t)nb * KS2 * 32 + lane) * 2;
-#pragma unroll 2
-                    for (int ks = 0; ks < KS2; ++ks) {
-                        const float4 av = ap[(size_t)ks * 32];
-                        const float4 w01 = wp[(size_t)ks * 64], w23 = wp[(size_t)ks * 64 + 1];
-                        uint32_t ah[4], al[4], bh[4], bl[4];
-                        split4(av, ah, al);
-                        split4(w01, bh, bl);
-                        mma_tf32(d[0][0], ah, bh[0], bh[1]);
-                        mma_tf32(d[1][0], ah, bh[2], bh[3]);
-                        mma_tf32(d[0][1], al, bh[0], bh[1]);
-                        mma_tf32(d[1][1], al, bh[2], bh[3]);
-                        mma_tf32(d[0][2], ah, bl[0], bl[1]);
-                        mma_tf32(d[1][2], ah, bl[2], bl[3]);
-                        split4(w23, bh, bl);
-                        mma_tf32(d[2][0], ah, bh[0], bh[1]);
-                        mma_tf32(d[3][0], ah, bh[2], bh[3]);
-                        mma_tf32(d[2][1], al, bh[0], bh[1]);
-                        mma_tf32(d[3][1], al, bh[2], bh[3]);
-                        mma_tf32(d[2][2], ah, bl[0], bl[1]);
-                        mma_tf32(d[3][2], ah, bl[2], bl[3]);
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int k = (nb * 4 + j) * 8 + 2 * tig;
-                        const int dst = (int)(((unsigned)k * inv_ub) >> 16);
-                        const int uu = k - dst * UB;
-                        float* o = outbase + (((size_t)dst * nub + ub) * 16 + gid) * UB + uu;
-                        *reinterpret_cast<float2*>(o) = make_float2(d[j][0][0] + (d[j][1][0] + d[j][2][0]),
-                                                                   d[j][0][1] + (d[j][1][1] + d[j][2][1]));
-                        *reinterpret_cast<float2*>(o + (size_t)8 * UB) =
-                            make_float2(d[j][0][2] + (d[j][1][2] + d[j][2][2]), d[j][0][3] + (d[j][1][3] + d[j][2][3]));
-                    }
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&done[g]);
-            }
-        }
-    }
-}
-
-// Shared memory: Wm[H/32][4UB/8][32][8] | inbox[NH][16*H] | dGs[NH][4UB*16] | barriers
-template <bool GEN3>
 __global__ void __launch_bounds__(LSTM_THREADS, 1) bilstm_bwd_mma_kernel(LstmParams p) {
     extern __shared__ __align__(128) unsigned char s_raw[];
     const int H = p.H, UB = p.UB, Bc = p.Bc, T = p.T, nub = p.nub, NH = p.NH;
@@ -1526,7 +1253,7 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) bilstm_bwd_mma_kernel(LstmPar
     }
     if (tid == 0) {
         for (int i = 0; i < 2 * LSTM_NCHUNK; ++i) mbar_init(&full[i], 1);
-        for (int i = 0; i < 2; ++i) mbar_init(&done[i], GEN3 ? 2 * LSTM_GTHREADS / 32 : LSTM_GTHREADS / 32);
+        for (int i = 0; i < 2; ++i) mbar_init(&done[i], LSTM_GTHREADS / 32);
         for (int i = 0; i < 2; ++i) mbar_init(&turn[i], LSTM_GTHREADS / 32);
         mbar_fence_init();
     }
@@ -1549,10 +1276,6 @@ __global__ void __launch_bounds__(LSTM_THREADS, 1) bilstm_bwd_mma_kernel(LstmPar
                          xb + (((size_t)g * 2 + 1) * nub + ub) * inbox_elems, inbox + (size_t)g * inbox_elems, off, off,
                          bytes, g == 0);
         }
-        return;
-    }
-    if constexpr (GEN3) {
-        bwd_stream_mma(p, tid, dir, bg, ub, reinterpret_cast<const float4*>(Wr), inbox, dGs, full, done, xb);
         return;
     }
     const int g = tid / LSTM_GTHREADS;
@@ -1607,8 +1330,9 @@ struct Plan {
 };
 
 static int g_lstm_flags = 0;  // experiment switches, see LstmParams::flags (set through the upper bits of the mode)
-static int g_lstm_mode = 0;   // 0: tensor-core step GEMMs when the shape allows, 1: always the fp32-FMA kernels,
-                              // 2: tensor cores with 6 instead of 12 accumulator chains (measurement only)
+static int g_lstm_mode = 0;   // 0: tcgen05 (lstm_umma.cu) when the shape allows, else mma.sync, else fp32 FMA;
+                              // 1: always the fp32-FMA kernels, 2: mma.sync with 6 instead of 12 accumulator chains
+                              // (measurement only), 3: never tcgen05 (the mma.sync generation, for A/B comparisons)
 
 static int halves_for(int Bc) { return (Bc % 8 == 0) ? 2 : 1; }
 static int rows_for(int Bc) { return ((Bc / halves_for(Bc)) % 8 == 0) ? 8 : 4; }
@@ -1729,7 +1453,13 @@ extern "C" size_t b200asr_bilstm_workspace_bytes(int B, int T, int H, int ndir) 
     Plan pl;
     if (make_plan(B, H, ndir, &pl) != 0) return 0;
     const size_t x = pl.xbuf_fwd_bytes > pl.xbuf_bwd_bytes ? pl.xbuf_fwd_bytes : pl.xbuf_bwd_bytes;
-    return align_up(pl.pack_bytes, 256) + align_up(x, 256) + LSTM_COUNTER_BYTES /*counters + err flag*/;
+    const size_t legacy = align_up(pl.pack_bytes, 256) + align_up(x, 256) + LSTM_COUNTER_BYTES /*counters + err flag*/;
+    const size_t um = lstm_umma_workspace_bytes(B, H, ndir);
+    return legacy > um ? legacy : um;
+}
+
+extern "C" int b200asr_bilstm_uses_tcgen05(int B, int H, int ndir) {
+    return (g_lstm_mode == 0 && lstm_umma_fwd_supported(B, H, ndir)) ? 1 : 0;
 }
 
 extern "C" int b200asr_bilstm_plan(int B, int H, int ndir, int* unit_block, int* batch_block, int* n_ctas) {
@@ -1758,6 +1488,9 @@ static int bilstm_run(bool bwd, float* gates, const float* w_hh, float* cstate, 
     B200_REQUIRE(make_plan(B, H, ndir, &pl) == 0,
                  "bilstm: no feasible decomposition for B=%d H=%d ndir=%d (H must be a multiple of 16)", B, H, ndir);
     B200_REQUIRE(workspace_bytes >= b200asr_bilstm_workspace_bytes(B, T, H, ndir), "bilstm: workspace too small");
+    if (!bwd && g_lstm_mode == 0 && lstm_umma_fwd_supported(B, H, ndir))
+        return lstm_umma_fwd(gates, w_hh, cstate, out_or_dout, B, T, H, ndir, workspace, workspace_bytes,
+                             (g_lstm_flags & 8) ? nullptr : g_trace, g_lstm_flags >> 4, stream);
     unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
     float* packed = reinterpret_cast<float*>(ws);
     const size_t xoff = align_up(pl.pack_bytes, 256);
@@ -1779,12 +1512,9 @@ static int bilstm_run(bool bwd, float* gates, const float* w_hh, float* cstate, 
     p.err_flag = err_flag; p.B = B; p.T = T; p.H = H; p.ndir = ndir; p.UB = pl.UB; p.Bc = pl.Bc; p.nub = pl.nub;
     p.nbg = pl.nbg; p.NH = pl.NH; p.R = pl.R; p.mma = pl.mma; p.flags = g_lstm_flags;
     p.trace = (bwd == ((g_lstm_flags & 8) != 0)) ? g_trace : nullptr;   // flag bit 3: trace the backward kernel
-    const bool gen3 = pl.mma && (g_lstm_flags & 16) && (bwd || H % 128 == 0);   // experimental, never the default
     const void* fn = !pl.mma ? (bwd ? (const void*)bilstm_bwd_kernel : (const void*)bilstm_fwd_kernel)
-                     : gen3  ? (bwd ? (const void*)bilstm_bwd_mma_kernel<true> : (const void*)bilstm_fwd_mma_kernel<true>)
-                             : (bwd ? (const void*)bilstm_bwd_mma_kernel<false> : (const void*)bilstm_fwd_mma_kernel<false>);
-    // + the 8 KB partial-sum scratch of the experimental generation-3 forward kernel
-    const size_t smem = (bwd ? pl.smem_bwd : pl.smem_fwd) + ((gen3 && !bwd) ? 8192 : 0);
+                             : (bwd ? (const void*)bilstm_bwd_mma_kernel : (const void*)bilstm_fwd_mma_kernel);
+    const size_t smem = bwd ? pl.smem_bwd : pl.smem_fwd;
     B200_REQUIRE(smem <= (size_t)max_optin_smem(), "bilstm: %zu B of shared memory exceed the device limit", smem);
     B200_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;

@@ -1,0 +1,432 @@
+// K7 on the 5th-generation tensor cores: the persistent BiLSTM recurrence with the step GEMM issued as tcgen05.mma
+// (kind::f16, fp32 accumulators in TMEM) instead of warp-level mma.sync.  Same CTA decomposition and the same
+// cross-SM exchange protocol as csrc/lstm.cu (one CTA per (direction, batch group of 32 rows, unit block), W_hh slice
+// resident in shared memory for all T steps, per-step release/acquire counter + 1-D bulk copies of the next state).
+//
+// fp32 parity on a 16-bit tensor-core path - the "2 x 2 block" split product.  Every fp32 operand x is held as two
+// fp16 numbers  x = hi + lo / 2048,  hi = fp16(x),  lo = fp16((x - hi) * 2048)  (22+ significant bits; h in (-1,1) and
+// recurrent weights are far inside the fp16 range).  The step product h . W^T then needs hi.hi + (hi.lo + lo.hi)/2048.
+// Because a single CTA only has 32 batch rows and 4*UB <= 64 gate columns, one MMA has room to spare in M and N, so
+// the hi and lo parts are STACKED along M and N:
+//        A = [ h_hi ; h_lo ]  (M = 64 rows)        B = [ W_hi ; W_lo ]  (N = 8*UB rows),   both K-major over k = 0..H-1
+// and ONE tcgen05.mma per 16 values of k produces all four blocks hi.hi | hi.lo / lo.hi | lo.lo of D at the cost of a
+// single instruction (H/16 = 32 MMAs per step at H = 512 instead of 3 x 64 warp-level MMAs per warp).  The epilogue
+// adds  D[hi,hi] + (D[hi,lo] + D[lo,hi]) / 2048  (lo.lo is below fp32 resolution and dropped).
+// Row / column orders are chosen so that no shuffle or shared-memory round trip is needed after the TMEM load:
+//   A rows  : TMEM quadrant q (rows 16q..16q+15) = [hi of batch rows 8q..8q+7 ; lo of the same 8 rows]
+//   B rows  : n = 8g + 2*tq + e  <->  unit = 4*(g/2) + tq, gate = 2*(g%2) + e   (n < 4*UBp: hi, then the lo copy)
+//   tcgen05.ld.16x256b gives thread (r = lane/4, tq = lane%4) of a warp on quadrant q the hi row AND the lo row of
+//   batch row 8q+r at columns 8g + 2tq + {0,1}; the warp with unit quad j reads groups 2j and 2j+1 = all four gates
+//   of unit 4j + tq, for P1 = hi.hi, P2 = lo.hi and (second pair of loads) P3 = hi.lo: one LSTM cell per thread.
+// The state exchange moves the next A operand between CTAs already in its shared-memory image (fp16 hi/lo, K-major,
+// 128-byte swizzle) and is pipelined per K ATOM (64 values of k = the hidden units of 64/UB producer CTAs): every
+// epilogue warp releases its stores with one red.release on the counter of the atom(s) its units belong to; lane a of
+// the consumer's control warp polls counter a and pulls atom a with one 8 KB bulk copy as soon as ITS producers are
+// done, and the MMA lane issues the four MMAs of an atom when it lands - the slowest producer, the copies and the MMAs
+// of one step overlap instead of running back to back.  No CTA-wide barrier, fence or grid-wide counter in the loop.
+//
+// Reference behaviour restated: torch.nn.LSTM as called from /root/reference/src/module.py:112-113,129-132 (single
+// layer, batch_first, zero initial state, run over the zero-padded frames, gates i,f,g,o).
+#include <cuda_fp16.h>
+#include "common.cuh"
+#include "umma.cuh"
+#include "lstm_umma.h"
+
+namespace b200asr {
+namespace {
+
+constexpr int UL_BC = 32;                 // batch rows per CTA (A operand: 32 hi rows + 32 lo rows = M 64)
+constexpr int UL_MAX_CTRL = 8;            // control warps (each owns every UL_MAX_CTRL-th K atom)
+constexpr int UL_ATOM_A = 64 * 128;       // bytes of one K atom (64 values of k) of the A operand
+constexpr int UL_MAX_ATOMS = 16;
+constexpr int UL_COUNTER_BYTES = 4096;
+
+struct UlParams {
+    float* gates;          // [ndir][B][T][H][4]  in: x.W_ih^T + b (gate-interleaved), out: activated gates (stash)
+    const uint8_t* wpack;  // [ndir][nub] shared-memory images of the B operand
+    float* cst;            // [ndir][B][T][H]
+    float* out;            // [B][T][ndir*H]
+    uint8_t* xbuf;         // [ndir][nbg][2] images of the A operand
+    unsigned* counters;    // [ndir][nbg]
+    int* err_flag;
+    long long* trace;
+    int B, T, H, ndir, UB, nub, nbg, NA, NC, flags;
+    int b0, Bend;
+};
+
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void red_relaxed_add_u32(unsigned* p, unsigned v) {
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Poll with RELAXED loads (an acquire load per iteration costs a gpu-scope fence each time) and acquire once at the end.
+__device__ __forceinline__ void ul_spin_until(const unsigned* ctr, unsigned target, int* err_flag) {
+    const long long t0 = clock64();
+    while (ld_relaxed_u32(ctr) < target) {
+        if (clock64() - t0 > (1LL << 33)) {  // ~4 s: a peer died; abort instead of hanging the GPU
+            *err_flag = 1;
+            __threadfence_system();
+            __trap();
+        }
+    }
+    (void)ld_acquire_u32(ctr);      // one acquire once the flag is up
+}
+__device__ __forceinline__ void ul_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
+    hi = __float2half_rn(x);
+    lo = __float2half_rn((x - __half2float(hi)) * 2048.f);
+}
+
+// W_hh [ndir][4H][H] (PyTorch gate-major rows) -> per-CTA shared-memory images of B = [W_hi ; W_lo]
+template <int UBP>
+__global__ void ul_pack_fwd_kernel(const float* __restrict__ w, uint8_t* __restrict__ dst, int H, int UB, int ndir) {
+    constexpr int N = 8 * UBP, NH = 4 * UBP;
+    const int nub = H / UB, NA = H / 64;
+    const long long per_cta = (long long)N * H;
+    const long long n_el = (long long)ndir * nub * per_cta;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_el; i += (long long)gridDim.x * blockDim.x) {
+        const int cta = (int)(i / per_cta);
+        const int r = (int)(i - (long long)cta * per_cta);
+        const int n = r / H, k = r - n * H;
+        const int dir = cta / nub, ub = cta - dir * nub;
+        const int nn = n % NH;
+        const int g = nn >> 3, tq = (nn >> 1) & 3, e = nn & 1;
+        const int unit = (g >> 1) * 4 + tq, gate = 2 * (g & 1) + e;
+        float v = 0.f;
+        if (unit < UB) v = w[((long long)dir * 4 * H + (long long)gate * H + (ub * UB + unit)) * H + k];
+        __half hi, lo;
+        split_f16(v, hi, lo);
+        uint8_t* img = dst + (size_t)cta * ((size_t)NA * N * 128);
+        const uint32_t off = (uint32_t)(k >> 6) * (N * 128) + umma::sw128_offset(n, (k & 63) * 2);
+        *reinterpret_cast<__half*>(img + off) = (n < NH) ? hi : lo;
+    }
+}
+
+#define UL_TRACE(slot) \
+    do { if (p.trace && blockIdx.x == 0) p.trace[(size_t)step * 16 + (slot)] = clock64(); } while (0)
+
+// Warp roles: warps [0, UBP) epilogue / pointwise - warp w owns TMEM quadrant q = w % 4 (the hardware rule) and the
+// unit quad j = w / 4, i.e. ONE cell (batch row 8q + lane/4, unit 4j + lane%4) per thread; warp UBP = MMA issue (one
+// lane) and TMEM allocation; warp UBP+1 = publisher (one lane: ONE gpu-scope fence + release per CTA and step, after
+// the epilogue warps arrived on `pub`); warps UBP+2 .. UBP+1+NC = control, one lane each, control warp c owns K atoms
+// c, c+NC, ...
+template <int UBP>
+__global__ void __launch_bounds__(32 * (UBP + 2 + UL_MAX_CTRL), 1) bilstm_fwd_umma_kernel(UlParams p) {
+    constexpr int N = 8 * UBP;            // B operand rows (gate columns, hi + lo copies)
+    constexpr int NH = 4 * UBP;
+    constexpr uint32_t TMEM_COLS = N <= 32 ? 32 : N <= 64 ? 64 : N <= 128 ? 128 : 256;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int H = p.H, T = p.T, NA = p.NA, UB = p.UB;
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + (size_t)NA * UL_ATOM_A;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sB + (size_t)NA * N * 128);    // [UL_MAX_ATOMS]
+    uint64_t* d_free = full + UL_MAX_ATOMS;      // the epilogue warps have read D out of TMEM
+    uint64_t* mma_done = d_free + 1;
+    uint64_t* wload = d_free + 2;
+    uint64_t* pub = d_free + 3;                  // the epilogue warps have stored h_step
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_free + 4);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int NC = p.NC;
+    int blk = blockIdx.x;
+    const int ub = blk % p.nub; blk /= p.nub;
+    const int bg = blk % p.nbg; blk /= p.nbg;
+    const int dir = blk;
+
+    if (tid == 0) {
+        for (int a = 0; a < UL_MAX_ATOMS; ++a) mbar_init(&full[a], 1);
+        mbar_init(d_free, UBP);
+        mbar_init(pub, UBP);
+        mbar_init(mma_done, 1);
+        mbar_init(wload, 1);
+        mbar_fence_init();
+    }
+    if (warp == UBP) umma::tmem_alloc(tmem_slot, TMEM_COLS);
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    uint8_t* xb = p.xbuf + ((size_t)dir * p.nbg + bg) * 2 * ((size_t)NA * UL_ATOM_A);
+    unsigned* ctr0 = p.counters + ((size_t)dir * p.nbg + bg) * UL_MAX_ATOMS;
+
+    if (warp == UBP + 1) {
+        // ------------------------------------------------------------------ publisher lane
+        if (lane == 0) {
+            const int a0 = (ub * UB) >> 6, a1 = (ub * UB + UB - 1) >> 6;
+            for (int step = 0; step + 1 < T; ++step) {
+                mbar_wait(pub, (uint32_t)(step & 1));       // every epilogue warp stored its part of h_step
+                UL_TRACE(8);
+                fence_acq_rel_gpu();                        // their stores (observed through the mbarrier) first ...
+                red_relaxed_add_u32(ctr0 + a0, 1u);         // ... then the flag(s) of the K atom(s) of my unit block
+                if (a1 != a0) red_relaxed_add_u32(ctr0 + a1, 1u);
+                UL_TRACE(9);
+            }
+        }
+    } else if (warp > UBP + 1) {
+        // ------------------------------------------------------------------ control warps (one lane each)
+        const int c = warp - UBP - 2;
+        if (lane == 0 && c < NC) {
+            if (c == 0) {
+                const uint8_t* wsrc = p.wpack + ((size_t)dir * p.nub + ub) * ((size_t)NA * N * 128);
+                mbar_expect_tx(wload, (uint32_t)(NA * N * 128));
+                for (int a = 0; a < NA; ++a)
+                    bulk_g2s(sB + (size_t)a * N * 128, wsrc + (size_t)a * N * 128, N * 128, wload);
+            }
+            unsigned per_step[(UL_MAX_ATOMS + 1) / 2];
+            for (int i = 0, a = c; a < NA; a += NC, ++i) {
+                unsigned nprod = 0;                       // producer CTAs whose units fall into atom a
+                for (int u = 0; u < p.nub; ++u)
+                    if ((u * UB) / 64 <= a && (u * UB + UB - 1) / 64 >= a) ++nprod;
+                per_step[i] = nprod;
+            }
+            for (int step = 0; step + 1 < T; ++step) {
+                // my own MMAs of `step` must have read the atoms before they are overwritten (they finished long
+                // ago: every producer ran the same MMAs before it could publish)
+                if (step > 0) mbar_wait(mma_done, (uint32_t)((step - 1) & 1));
+                for (int i = 0, a = c; a < NA; a += NC, ++i) {
+                    ul_spin_until(ctr0 + a, (unsigned)(step + 1) * per_step[i], p.err_flag);
+                    if (a == 0) UL_TRACE(10);
+                    if (a == NA - 1) UL_TRACE(15);
+                    if (!(p.flags & 1)) fence_proxy_async();
+                    const uint8_t* src = xb + (size_t)(step & 1) * ((size_t)NA * UL_ATOM_A) + (size_t)a * UL_ATOM_A;
+                    mbar_expect_tx(&full[a], UL_ATOM_A);
+                    bulk_g2s(sA + (size_t)a * UL_ATOM_A, src, UL_ATOM_A, &full[a]);
+                    if (a == 0) UL_TRACE(11);
+                }
+            }
+        }
+    } else if (warp == UBP) {
+        // ------------------------------------------------------------------ MMA lane
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma::instr_desc(umma::FMT_F16, 64, N);
+            const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+            mbar_wait(wload, 0);
+            for (int step = 1; step < T; ++step) {
+                if (step > 1) mbar_wait(d_free, (uint32_t)(step & 1));      // epilogue of step-1 has drained D
+                for (int a = 0; a < NA; ++a) {
+                    mbar_wait(&full[a], (uint32_t)((step - 1) & 1));
+                    umma::fence_after_sync();
+                    if (a == 0) UL_TRACE(1);
+                    if (a == NA - 1) UL_TRACE(6);
+                    if (a == 1) UL_TRACE(12);
+                    if (a == 3) UL_TRACE(13);
+                    if (a == 5) UL_TRACE(14);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint64_t da = umma::desc_k_sw128(a_base + a * UL_ATOM_A + j * 32);
+                        const uint64_t db = umma::desc_k_sw128(b_base + a * (N * 128) + j * 32);
+                        umma::mma_ss<umma::FMT_F16>(tmem, da, db, idesc, (a | j) != 0);
+                    }
+                }
+                umma::commit(mma_done);
+                UL_TRACE(2);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue / pointwise warps
+        const int q = warp & 3, jq = warp >> 2, r = lane >> 2, tq = lane & 3;
+        const int brow = p.b0 + bg * UL_BC + 8 * q + r;
+        const int unit = 4 * jq + tq;                     // my unit of the CTA's block
+        const bool ok = (brow < p.Bend) && (unit < UB);
+        const int ug = ub * UB + (unit < UB ? unit : 0);  // = my k in the next A operand
+        const uint32_t t_lane = tmem + ((uint32_t)(32 * q) << 16);
+        const int a_row_hi = 16 * q + r, a_row_lo = 16 * q + 8 + r;
+        const uint32_t pub_hi = (uint32_t)(ug >> 6) * UL_ATOM_A + umma::sw128_offset(a_row_hi, (ug & 63) * 2);
+        const uint32_t pub_lo = (uint32_t)(ug >> 6) * UL_ATOM_A + umma::sw128_offset(a_row_lo, (ug & 63) * 2);
+        float c_reg = 0.f;
+        const bool trc = (warp == 0 && lane == 0);
+        float4 st_g = make_float4(0.f, 0.f, 0.f, 0.f);
+        float st_c = 0.f, st_h = 0.f;
+        size_t st_row = 0, st_out = 0;
+        bool st_pending = false;
+
+        for (int step = 0; step < T; ++step) {
+            const int tt = dir ? (T - 1 - step) : step;
+            if (trc) UL_TRACE(0);
+            const size_t rowbase = ((size_t)dir * p.B + (ok ? brow : 0)) * T + tt;
+            float4 pre = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok) pre = *reinterpret_cast<const float4*>(p.gates + (rowbase * H + ug) * 4);
+            if (step > 0) {
+                mbar_wait(mma_done, (uint32_t)((step - 1) & 1));
+                umma::fence_after_sync();
+                if (trc) UL_TRACE(3);
+                // column group g = 2*jq + gh holds gates (2gh, 2gh+1) of my unit: v0,v1 = hi row, v2,v3 = lo row
+                uint32_t dif[4], dgo[4], eif[4], ego[4];
+                umma::ld_16x256b_x1(t_lane + 16 * jq, dif);
+                umma::ld_16x256b_x1(t_lane + 16 * jq + 8, dgo);
+                umma::ld_16x256b_x1(t_lane + NH + 16 * jq, eif);
+                umma::ld_16x256b_x1(t_lane + NH + 16 * jq + 8, ego);
+                umma::wait_ld();
+                umma::fence_before_sync();      // my TMEM reads are done: the next step's MMAs may overwrite D
+                __syncwarp();
+                if (lane == 0) ul_arrive(d_free);
+                if (trc) UL_TRACE(4);
+                if (st_pending) {
+                    *reinterpret_cast<float4*>(p.gates + (st_row * H + ug) * 4) = st_g;
+                    p.cst[st_row * H + ug] = st_c;
+                    p.out[st_out] = st_h;
+                    st_pending = false;
+                }
+                const float k = 1.f / 2048.f;
+                pre.x += __uint_as_float(dif[0]) + (__uint_as_float(dif[2]) + __uint_as_float(eif[0])) * k;
+                pre.y += __uint_as_float(dif[1]) + (__uint_as_float(dif[3]) + __uint_as_float(eif[1])) * k;
+                pre.z += __uint_as_float(dgo[0]) + (__uint_as_float(dgo[2]) + __uint_as_float(ego[0])) * k;
+                pre.w += __uint_as_float(dgo[1]) + (__uint_as_float(dgo[3]) + __uint_as_float(ego[1])) * k;
+            }
+            const float ig = sigmoidf_(pre.x);
+            const float fg = sigmoidf_(pre.y);
+            const float gg = tanhf(pre.z);
+            const float og = sigmoidf_(pre.w);
+            const float c = fmaf(fg, c_reg, ig * gg);
+            c_reg = ok ? c : 0.f;
+            const float hq = ok ? og * tanhf(c) : 0.f;
+            if (trc) UL_TRACE(7);
+            if (step + 1 < T) {
+                // publish h_step as element (A row, k = ug) of the next A operand, fp16 hi / lo
+                uint8_t* dstimg = xb + (size_t)(step & 1) * ((size_t)NA * UL_ATOM_A);
+                if (unit < UB) {
+                    __half hi, lo;
+                    split_f16(hq, hi, lo);
+                    *reinterpret_cast<__half*>(dstimg + pub_hi) = hi;
+                    *reinterpret_cast<__half*>(dstimg + pub_lo) = lo;
+                }
+                __syncwarp();
+                if (lane == 0) ul_arrive(pub);
+                if (trc) UL_TRACE(5);
+            }
+            // the stash / output stores of this step are issued during the NEXT step (after its TMEM loads): stores
+            // in flight while the publisher runs its gpu-scope fence lengthen that fence by their L2 round trip
+            st_g = make_float4(ig, fg, gg, og);
+            st_c = c;
+            st_h = hq;
+            st_row = rowbase;
+            st_out = ((size_t)brow * T + tt) * (p.ndir * H) + (size_t)dir * H + ug;
+            st_pending = ok;
+        }
+        if (st_pending) {
+            *reinterpret_cast<float4*>(p.gates + (st_row * H + ug) * 4) = st_g;
+            p.cst[st_row * H + ug] = st_c;
+            p.out[st_out] = st_h;
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == UBP) umma::tmem_dealloc(tmem, TMEM_COLS);
+}
+
+struct UlPlan {
+    int UB, UBp, nub, nbg, ctas, NA, Bsub, nsplit;
+    size_t smem, pack_bytes, xbuf_bytes;
+};
+
+int ul_plan(int B, int H, int ndir, UlPlan* out) {
+    if (H % 64 != 0 || H / 64 > UL_MAX_ATOMS) return -1;
+    const int sms = sm_count();
+    const size_t cap = (size_t)max_optin_smem();
+    const int NA = H / 64;
+    for (int n = 1; n <= B; ++n) {
+        const int Bs = (B + n - 1) / n;
+        const int nbg = (Bs + UL_BC - 1) / UL_BC;
+        for (int UB = 2; UB <= 16; ++UB) {           // smallest unit block whose CTAs are all co-resident
+            if (H % UB) continue;
+            const int UBp = (UB + 3) / 4 * 4;
+            if (UBp != 8 && UBp != 12 && UBp != 16) continue;
+            const int nub = H / UB;
+            const int ctas = ndir * nbg * nub;
+            if (ctas > sms) continue;
+            const size_t smem = (size_t)NA * UL_ATOM_A + (size_t)NA * 8 * UBp * 128 + 256;
+            if (smem > cap) continue;
+            if ((size_t)ndir * nbg * UL_MAX_ATOMS * 4 > UL_COUNTER_BYTES - 64) continue;
+            out->UB = UB; out->UBp = UBp; out->nub = nub; out->nbg = nbg; out->ctas = ctas; out->NA = NA;
+            out->Bsub = Bs; out->nsplit = (B + Bs - 1) / Bs; out->smem = smem;
+            out->pack_bytes = (size_t)ndir * nub * NA * 8 * UBp * 128;
+            out->xbuf_bytes = (size_t)ndir * nbg * 2 * NA * UL_ATOM_A;
+            return 0;
+        }
+        if (Bs <= UL_BC) break;
+    }
+    return -2;
+}
+
+size_t ul_align(size_t x) { return (x + 255) / 256 * 256; }
+
+template <int UBP>
+int ul_launch_fwd(const UlPlan& pl, UlParams p, const float* w_hh, cudaStream_t stream) {
+    {
+        const long long n = (long long)p.ndir * pl.nub * 8 * UBP * p.H;
+        int blocks = (int)((n + 255) / 256);
+        if (blocks > 8192) blocks = 8192;
+        ul_pack_fwd_kernel<UBP><<<blocks, 256, 0, stream>>>(w_hh, const_cast<uint8_t*>(p.wpack), p.H, pl.UB, p.ndir);
+        B200_LAUNCH_CHECK("ul_pack_fwd_kernel");
+    }
+    const void* fn = (const void*)bilstm_fwd_umma_kernel<UBP>;
+    B200_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    int per_sm = 0;
+    const int threads = 32 * (UBP + 2 + p.NC);
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, pl.smem));
+    B200_REQUIRE((long long)per_sm * sm_count() >= pl.ctas, "bilstm(umma): %d CTAs cannot be co-resident (%d/SM x %d SMs)",
+                 pl.ctas, per_sm, sm_count());
+    for (int sp = 0; sp < pl.nsplit; ++sp) {
+        p.b0 = sp * pl.Bsub;
+        p.Bend = p.b0 + pl.Bsub < p.B ? p.b0 + pl.Bsub : p.B;
+        B200_CUDA(cudaMemsetAsync(p.counters, 0, UL_COUNTER_BYTES, stream));
+        void* args[] = {&p};
+        B200_CUDA(cudaLaunchCooperativeKernel(fn, dim3(pl.ctas), dim3(threads), args, pl.smem, stream));
+        count_launch();
+    }
+    return B200_OK;
+}
+
+}  // namespace
+
+bool lstm_umma_fwd_supported(int B, int H, int ndir) {
+    UlPlan pl;
+    return ul_plan(B, H, ndir, &pl) == 0;
+}
+
+size_t lstm_umma_workspace_bytes(int B, int H, int ndir) {
+    UlPlan pl;
+    if (ul_plan(B, H, ndir, &pl) != 0) return 0;
+    return ul_align(pl.pack_bytes) + ul_align(pl.xbuf_bytes) + UL_COUNTER_BYTES;
+}
+
+int lstm_umma_plan(int B, int H, int ndir, int* unit_block, int* batch_block, int* n_ctas) {
+    UlPlan pl;
+    if (ul_plan(B, H, ndir, &pl) != 0) return -1;
+    if (unit_block) *unit_block = pl.UB;
+    if (batch_block) *batch_block = UL_BC;
+    if (n_ctas) *n_ctas = pl.ctas;
+    return 0;
+}
+
+int lstm_umma_fwd(float* gates, const float* w_hh, float* cstate, float* out, int B, int T, int H, int ndir,
+                  void* workspace, size_t workspace_bytes, long long* trace, int flags, cudaStream_t stream) {
+    UlPlan pl;
+    B200_REQUIRE(ul_plan(B, H, ndir, &pl) == 0, "bilstm(umma): unsupported shape B=%d H=%d ndir=%d", B, H, ndir);
+    B200_REQUIRE(workspace_bytes >= lstm_umma_workspace_bytes(B, H, ndir), "bilstm(umma): workspace too small");
+    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+    UlParams p;
+    p.gates = gates; p.cst = cstate; p.out = out;
+    p.wpack = ws;
+    p.xbuf = ws + ul_align(pl.pack_bytes);
+    p.counters = reinterpret_cast<unsigned*>(ws + ul_align(pl.pack_bytes) + ul_align(pl.xbuf_bytes));
+    p.err_flag = reinterpret_cast<int*>(p.counters + (UL_COUNTER_BYTES / 4 - 4));
+    p.trace = trace;
+    p.flags = flags;
+    p.B = B; p.T = T; p.H = H; p.ndir = ndir; p.UB = pl.UB; p.nub = pl.nub; p.nbg = pl.nbg; p.NA = pl.NA;
+    p.NC = pl.NA < UL_MAX_CTRL ? pl.NA : UL_MAX_CTRL;
+    p.b0 = 0; p.Bend = B;
+    switch (pl.UBp) {
+        case 8: return ul_launch_fwd<8>(pl, p, w_hh, stream);
+        case 12: return ul_launch_fwd<12>(pl, p, w_hh, stream);
+        default: return ul_launch_fwd<16>(pl, p, w_hh, stream);
+    }
+}
+
+}  // namespace b200asr

@@ -1,0 +1,114 @@
+// tcgen05 / TMEM helpers for the sm_100a kernels: shared-memory matrix descriptors, the instruction descriptor,
+// TMEM allocation, single-thread MMA issue, commit -> mbarrier, TMEM -> register loads.
+//
+// Layout conventions used by every kernel in this library (validated on hardware by tools/micro/umma_probe.cu):
+//  * operands are K-major with the 128-byte swizzle: a tile of R rows x 128 bytes of K (32 tf32 / 64 f16 elements) is
+//    stored as R consecutive 128-byte rows, and inside each 1024-byte group of 8 rows the 16-byte chunk c of row r
+//    sits at chunk position c ^ (r & 7).  Tiles that are longer in K are a sequence of such "K atoms", each a
+//    separate R x 128 B block.  This is also what a TMA load with CU_TENSOR_MAP_SWIZZLE_128B produces.
+//  * one tcgen05.mma consumes 32 bytes of K (8 tf32 / 16 f16): inside an atom the descriptor start address advances
+//    by 32 bytes per MMA.
+//  * accumulators are fp32 in TMEM: M = 128 -> row r in lane r; M = 64 -> row r in lane (r / 16) * 32 + r % 16.
+#pragma once
+#include "common.cuh"
+
+namespace b200asr {
+namespace umma {
+
+constexpr int FMT_F16 = 0;
+constexpr int FMT_BF16 = 1;
+constexpr int FMT_TF32 = 2;
+
+// ---- descriptors -------------------------------------------------------------------------------------------
+// K-major, SWIZZLE_128B matrix descriptor (sm_100 "version 1"): start address >> 4 in [0,14), leading byte offset
+// (unused: one swizzle atom along K) in [16,30), stride byte offset = 1024 (distance between 8-row groups) in
+// [32,46), version = 1 in [46,48), layout type SWIZZLE_128B = 2 in [61,64).
+__device__ __forceinline__ uint64_t desc_k_sw128(uint32_t smem_addr) {
+    uint64_t d = static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+
+// Instruction descriptor (upper 32 bits of the "idesc" operand): fp32 accumulate, both operands K-major.
+__host__ __device__ constexpr uint32_t instr_desc(int fmt, int M, int N) {
+    return (1u << 4) | (static_cast<uint32_t>(fmt) << 7) | (static_cast<uint32_t>(fmt) << 10) |
+           (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+// Byte offset of element (row, byte-in-row) inside one K atom (R rows x 128 B) with the 128-byte swizzle.
+__host__ __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t byte_in_row) {
+    return row * 128u + ((((byte_in_row >> 4) ^ (row & 7u)) << 4) | (byte_in_row & 15u));
+}
+
+// ---- TMEM allocation (one warp, .sync.aligned) ----------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)),
+                 "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// ---- MMA issue (ONE thread) ---------------------------------------------------------------------------------
+template <int FMT>
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                       uint32_t accumulate) {
+    if (FMT == FMT_TF32) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+            "}\n" ::"r"(d_tmem),
+            "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+            "}\n" ::"r"(d_tmem),
+            "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
+}
+// All MMAs issued so far by this thread arrive on `bar` when they have completed (implies fence::before_thread_sync).
+__device__ __forceinline__ void commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---- TMEM -> registers --------------------------------------------------------------------------------------
+// 32 lanes x 32 bit, x8: thread i of the warp reads 8 consecutive columns of lane (lane_base + i).
+__device__ __forceinline__ void ld_32x32b_x8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+// 16 lanes x 256 bit, x1: thread i holds (row i/4, cols 2(i%4), 2(i%4)+1) in v0,v1 and row i/4 + 8 in v2,v3.
+__device__ __forceinline__ void ld_16x256b_x1(uint32_t taddr, uint32_t (&v)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void ld_16x256b_x4(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+}  // namespace umma
+}  // namespace b200asr

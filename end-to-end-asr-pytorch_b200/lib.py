@@ -35,6 +35,7 @@ SIGNATURES = {
     "b200asr_bilstm_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "b200asr_bilstm_plan": (c_int, [c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "b200asr_bilstm_uses_tensor_cores": (c_int, [c_int, c_int, c_int]),
+    "b200asr_bilstm_uses_tcgen05": (c_int, [c_int, c_int, c_int]),
     "b200asr_bilstm_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
     "b200asr_bilstm_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
     "b200asr_debug_set_lstm_trace": (None, [_P]),

@@ -62,6 +62,14 @@ class Solver(BaseSolver):
         self.global_batch = self.global_tokens = None
         self.timer.set()
         while self.step < self.max_step:
+            # curriculum hand-off (bin/train_asr.py:86-92): after `curriculum` length-sorted epochs, renew the loader
+            # with ascending=False so that sampling becomes random
+            if self.curriculum > 0 and n_epochs == self.curriculum:
+                self.verbose("Curriculum learning ends after {} epochs, starting random sampling.".format(n_epochs))
+                self.tr_set, _, _, _, _, _ = load_dataset(
+                    self.paras.njobs, self.paras.gpu, self.paras.pin_memory, False, device=self.device,
+                    **self.config["data"])
+                self.audio_transform = self.tr_set.audio_transform
             for data in self.tr_set:
                 tf_rate = self.optimizer.pre_step(self.step)
                 total_loss = 0

@@ -36,11 +36,16 @@ class TrainStep:
         """wave [B,N] fp32 (device), wave_len [B], txt [B,L] int64 (device); returns the total loss (device scalar).
         Under data parallelism `wave`/`txt` are this rank's shard, padded to the GLOBAL maxima."""
         if self.graph is not None:
-            self._g_wave.copy_(wave, non_blocking=True)
-            self._g_txt.copy_(txt, non_blocking=True)
-            self.graph.replay()
-            self.step_id += 1
-            return self._g_loss
+            # the captured step is valid for the captured shapes and loss normalisers only; the utterance lengths
+            # are read on the device, so they are refreshed like the waveforms (anything else: eager step)
+            if (tuple(wave.shape) == tuple(self._g_wave.shape) and tuple(txt.shape) == tuple(self._g_txt.shape)
+                    and (global_batch, global_tokens) == self._g_norm and max_len in (None, int(txt.shape[1]))):
+                self._g_wave.copy_(wave, non_blocking=True)
+                self._g_txt.copy_(txt, non_blocking=True)
+                self._g_len.copy_(torch.as_tensor(wave_len), non_blocking=True)
+                self.graph.replay()
+                self.step_id += 1
+                return self._g_loss
         return self._eager(wave, wave_len, txt, global_batch, global_tokens, max_len)
 
     def _eager(self, wave, wave_len, txt, global_batch, global_tokens, max_len):
@@ -91,6 +96,7 @@ class TrainStep:
             gc.collect()                 # drop autograd nodes created on another stream by earlier eager steps
             self._g_wave, self._g_txt = wave.clone(), txt.clone()
             self._g_len = torch.as_tensor(wave_len).to(wave.device).clone()
+            self._g_norm = (global_batch, global_tokens)
             max_len = int(txt.shape[1])
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())

@@ -97,6 +97,9 @@ B200ASR_API int b200asr_bilstm_plan(int B, int H, int ndir, int* unit_block, int
 /* 1 when the step GEMMs of this shape run on the tensor cores (3xTF32 mma), 0 for the packed-fp32-FMA kernels,
  * -1 when the shape has no decomposition */
 B200ASR_API int b200asr_bilstm_uses_tensor_cores(int B, int H, int ndir);
+/* 1 when the forward recurrence of this shape runs on the 5th-generation tensor cores (tcgen05.mma kind::f16 with
+ * fp32 accumulators in TMEM and the fp16 hi/lo "2 x 2 block" split product, csrc/lstm_umma.cu), else 0 */
+B200ASR_API int b200asr_bilstm_uses_tcgen05(int B, int H, int ndir);
 B200ASR_API int b200asr_bilstm_fwd(float* gates, const float* w_hh, float* cstate, float* out, int B, int T, int H, int ndir,
                        void* workspace, size_t workspace_bytes, b200asr_stream stream);
 B200ASR_API int b200asr_bilstm_bwd(float* gates, const float* w_hh, const float* cstate, const float* dout, int B, int T,
@@ -104,8 +107,9 @@ B200ASR_API int b200asr_bilstm_bwd(float* gates, const float* w_hh, const float*
 
 /* debug: when non-NULL, CTA 0 of the next b200asr_bilstm_fwd calls records clock64 stamps into [T][16] int64 */
 B200ASR_API void b200asr_debug_set_lstm_trace(long long* device_buffer);
-/* debug/test: 0 (default) = tensor-core (3xTF32 mma) step GEMMs wherever the planner finds a 16-row-tile
- * decomposition, 1 = always the packed-fp32-FMA step kernels.  Both are fp32-class and parity-tested.
+/* debug/test: 0 (default) = tcgen05 step GEMMs where the shape allows, else 3xTF32 mma.sync wherever the planner finds
+ * a 16-row-tile decomposition, else fp32 FMA; 1 = always the packed-fp32-FMA step kernels; 3 = never tcgen05 (the
+ * mma.sync generation).  All are fp32-class and parity-tested.
  * Upper bits (mode >> 4) are measurement switches used by tools/time_lstm.py and tools/trace_lstm.py. */
 B200ASR_API void b200asr_debug_set_lstm_mode(int mode);
 

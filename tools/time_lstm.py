@@ -1,4 +1,4 @@
-"""Per-step time of the BiLSTM step-kernel families (tensor-core 3xTF32 MMA vs packed fp32 FMA) at one shape.
+"""Per-step time of the BiLSTM step-kernel families (tcgen05 / mma.sync 3xTF32 / packed fp32 FMA) at one shape.
    env: B (64), H (512), T (300), I (1024).  Prints us/step for forward and backward and the max |difference| of the
    outputs / input gradients between the two families."""
 import importlib, os, sys, torch
@@ -13,9 +13,9 @@ x = torch.randn(B, T, I, device="cuda", requires_grad=True)
 gy = torch.randn(B, T, 2 * H, device="cuda")
 lib = L.load()
 res = {}
-MODES = ((1, "fp32-FMA"), (64, "MMA-v1"), (0, "MMA"))
-if os.environ.get("GEN3"):            # experimental single-stream kernels (debug flag bit 4), never the default
-    MODES += ((256, "MMA-gen3"),)
+MODES = ((3, "mma.sync"), (0, "tcgen05"))
+if os.environ.get("EXTRA_MODE"):
+    MODES += ((int(os.environ["EXTRA_MODE"]), "tcgen05-mode%s" % os.environ["EXTRA_MODE"]),)
 REPS = int(os.environ.get("REPS", 3))
 stats = {name: [] for _, name in MODES}
 fwd_only = {name: [] for _, name in MODES}
@@ -49,6 +49,6 @@ for _, name in MODES:
     print("%-16s B=%d H=%d T=%d us/step: fwd %s | bwd %s | fwd alone %s" % (
         name, B, H, T, " ".join("%.2f" % f for f, _ in stats[name]), " ".join("%.2f" % b for _, b in stats[name]),
         " ".join("%.2f" % f for f in fwd_only[name])), flush=True)
-a, b = res["fp32-FMA"], res[MODES[-1][1]]
+a, b = res[MODES[0][1]], res[MODES[-1][1]]
 print("max |dy| %.3e (max |y| %.3e)   max |d dx| %.3e (max |dx| %.3e)" % (
     float((a[0] - b[0]).abs().max()), float(a[0].abs().max()), float((a[1] - b[1]).abs().max()), float(a[1].abs().max())))
