@@ -68,7 +68,7 @@ class ASR(nn.Module):
         encode_feature, encode_len = self.encoder(audio_feature, feature_len)
 
         if self.enable_ctc:
-            ctc_output, self.last_ctc_argmax = ops.log_softmax(ops.linear3x(encode_feature, self.ctc_layer))
+            ctc_output, self.last_ctc_argmax = ops.log_softmax(ops.linear3x(encode_feature, self.ctc_layer), ctc_head=True)
 
         if self.enable_att:
             decode_step = int(decode_step)

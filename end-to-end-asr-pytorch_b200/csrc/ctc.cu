@@ -110,6 +110,7 @@ struct CtcParams {
     int B, T, V, L_max, S_max, blank;
     float* nll;          // [B]
     const float* scale;  // [B] or null
+    const float* upstream;  // device scalar multiplied into every gradient element (d total / d loss), or null
     float* grad;         // same strides as lp, or null
     float* alpha;        // [B,T,S_max]
     float* beta;         // [B,T,S_max]
@@ -143,7 +144,10 @@ __global__ void __launch_bounds__(1024) ctc_alpha_beta_kernel(CtcParams p) {
 
     for (int s = threadIdx.x; s < S_max; s += blockDim.x) {
         int l = -1;
-        if (s < Sb) l = (s & 1) ? (int)p.targets[(long long)b * p.L_max + (s >> 1)] : p.blank;
+        if (s < Sb) {
+            l = (s & 1) ? (int)p.targets[(long long)b * p.L_max + (s >> 1)] : p.blank;
+            l = l < 0 ? 0 : (l >= p.V ? p.V - 1 : l);      // never index outside the row (torch raises on such input)
+        }
         lab[s] = l;
     }
     __syncthreads();
@@ -266,6 +270,7 @@ __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_alpha_beta_warp_kernel(Ctc
         const int s = lane * R + r;
         in_range[r] = s < Sb;
         lab[r] = (in_range[r] && (s & 1)) ? (int)p.targets[(long long)b * p.L_max + (s >> 1)] : p.blank;
+        lab[r] = lab[r] < 0 ? 0 : (lab[r] >= p.V ? p.V - 1 : lab[r]);   // never index outside the row
         if (s < S_max) lab_s[s] = in_range[r] ? lab[r] : -1;
     }
     __syncwarp();
@@ -395,11 +400,13 @@ constexpr int CTC_GRAD_THREADS = 256;
 constexpr int CTC_GRAD_TCHUNK = 8;
 
 __global__ void __launch_bounds__(CTC_GRAD_THREADS) ctc_grad_kernel(CtcParams p) {
+    // grid (T chunks, B).  Phase 1 streams the dense part  g = exp(lp) * scale  of every row of the chunk (pure
+    // 128-bit streaming, no barrier); phase 2 subtracts the label-occupancy term at the <= L+1 distinct classes of the
+    // utterance (deterministic occurrence-chain sums, one owner thread per class, no atomics).
     extern __shared__ __align__(16) float s_dyn[];
     __shared__ float s_scratch[32];
     const int S_max = p.S_max, V = p.V;
-    float* acc = s_dyn;             // [V]
-    float* e = s_dyn + V;           // [S_max]
+    float* e = s_dyn;               // [S_max]
     int* lab = reinterpret_cast<int*>(e + S_max);
     int* prev_same = lab + S_max;
     int* is_last = prev_same + S_max;
@@ -411,37 +418,50 @@ __global__ void __launch_bounds__(CTC_GRAD_THREADS) ctc_grad_kernel(CtcParams p)
     const int Lb = (int)(Lb64 < 0 ? 0 : (Lb64 > p.L_max ? p.L_max : Lb64));
     const int Sb = 2 * Lb + 1;
     const float nll = p.nll[b];
-    const float scale = p.scale ? p.scale[b] : 1.f;
+    const float scale = (p.scale ? p.scale[b] : 1.f) * (p.upstream ? *p.upstream : 1.f);
     const bool vec4 = ((V & 3) == 0) && ((p.sb & 3) == 0) && ((p.st & 3) == 0) &&
                       ((reinterpret_cast<uintptr_t>(p.lp) | reinterpret_cast<uintptr_t>(p.grad)) & 15) == 0;
 
-    for (int c = threadIdx.x; c < V; c += blockDim.x) acc[c] = 0.f;
     for (int s = threadIdx.x; s < S_max; s += blockDim.x) {
         int l = -1;
-        if (s < Sb) l = (s & 1) ? (int)p.targets[(long long)b * p.L_max + (s >> 1)] : p.blank;
+        if (s < Sb) {
+            l = (s & 1) ? (int)p.targets[(long long)b * p.L_max + (s >> 1)] : p.blank;
+            l = l < 0 ? 0 : (l >= V ? V - 1 : l);     // same clamp as the lattice kernels (torch raises on such input)
+        }
         lab[s] = l;
         prev_same[s] = p.prev_same[(long long)b * S_max + s];
         is_last[s] = p.is_last[(long long)b * S_max + s];
     }
-    __syncthreads();
 
     const int t_begin = blockIdx.x * CTC_GRAD_TCHUNK;
     const int t_end = min(p.T, t_begin + CTC_GRAD_TCHUNK);
+    // ---- phase 1: dense stream
     for (int t = t_begin; t < t_end; ++t) {
         float* gt = p.grad + (long long)b * p.sb + (long long)t * p.st;
-        if (t >= Tb) {
-            if (vec4) {
-                float4* g4 = reinterpret_cast<float4*>(gt);
-                for (int c = threadIdx.x; c < (V >> 2); c += blockDim.x) g4[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-            } else {
-                for (int c = threadIdx.x; c < V; c += blockDim.x) gt[c] = 0.f;
+        const float* lpt = p.lp + (long long)b * p.sb + (long long)t * p.st;
+        const bool live = t < Tb;
+        if (vec4) {
+            const float4* l4 = reinterpret_cast<const float4*>(lpt);
+            float4* g4 = reinterpret_cast<float4*>(gt);
+            for (int c = threadIdx.x; c < (V >> 2); c += blockDim.x) {
+                float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (live) {
+                    const float4 l = l4[c];
+                    o = make_float4(expf(l.x) * scale, expf(l.y) * scale, expf(l.z) * scale, expf(l.w) * scale);
+                }
+                g4[c] = o;
             }
-            continue;
+        } else {
+            for (int c = threadIdx.x; c < V; c += blockDim.x) gt[c] = live ? expf(lpt[c]) * scale : 0.f;
         }
+    }
+    __syncthreads();
+    // ---- phase 2: occupancy of the utterance's own classes
+    for (int t = t_begin; t < t_end && t < Tb; ++t) {
+        float* gt = p.grad + (long long)b * p.sb + (long long)t * p.st;
         const float* lpt = p.lp + (long long)b * p.sb + (long long)t * p.st;
         const float* al = p.alpha + ((long long)b * p.T + t) * S_max;
         const float* be = p.beta + ((long long)b * p.T + t) * S_max;
-        // 1. alpha+beta, row max
         float mx = NEG_INF;
         for (int s = threadIdx.x; s < Sb; s += blockDim.x) {
             const float v = al[s] + be[s];
@@ -454,39 +474,21 @@ __global__ void __launch_bounds__(CTC_GRAD_THREADS) ctc_grad_kernel(CtcParams p)
             e[s] = (v == NEG_INF) ? 0.f : expf(v - m);
         }
         __syncthreads();
-        // 2a. blank (even s): fixed-order per-thread partials + fixed tree
+        // blank (even s): fixed-order per-thread partials + fixed tree
         float part = 0.f;
         for (int s = 2 * threadIdx.x; s < Sb; s += 2 * blockDim.x) part += e[s];
         const float tot_blank = block_sum(part, s_scratch);
-        if (threadIdx.x == 0)
-            acc[p.blank] = (tot_blank > 0.f) ? expf(logf(tot_blank) + m + nll - lpt[p.blank]) : 0.f;
-        // 2b. labels (odd s): the thread owning the last occurrence walks the chain backwards
+        if (threadIdx.x == 0 && tot_blank > 0.f)
+            gt[p.blank] -= expf(logf(tot_blank) + m + nll - lpt[p.blank]) * scale;
+        // labels (odd s): the thread owning the last occurrence walks the chain backwards
         for (int s = 2 * threadIdx.x + 1; s < Sb; s += 2 * blockDim.x) {
             if (is_last[s]) {
                 float tot = 0.f;
                 for (int q = s; q >= 0; q = prev_same[q]) tot += e[q];
                 const int l = lab[s];
-                if (l != p.blank) acc[l] = (tot > 0.f) ? expf(logf(tot) + m + nll - lpt[l]) : 0.f;
+                if (l >= 0 && l != p.blank && tot > 0.f) gt[l] -= expf(logf(tot) + m + nll - lpt[l]) * scale;
             }
         }
-        __syncthreads();
-        // 3. stream the gradient row (128-bit accesses when the rows are 16-byte aligned)
-        if (vec4) {
-            const float4* l4 = reinterpret_cast<const float4*>(lpt);
-            const float4* a4 = reinterpret_cast<const float4*>(acc);
-            float4* g4 = reinterpret_cast<float4*>(gt);
-            for (int c = threadIdx.x; c < (V >> 2); c += blockDim.x) {
-                const float4 l = l4[c], a = a4[c];
-                g4[c] = make_float4((expf(l.x) - a.x) * scale, (expf(l.y) - a.y) * scale, (expf(l.z) - a.z) * scale,
-                                    (expf(l.w) - a.w) * scale);
-            }
-        } else {
-            for (int c = threadIdx.x; c < V; c += blockDim.x) gt[c] = (expf(lpt[c]) - acc[c]) * scale;
-        }
-        __syncthreads();
-        // 4. reset touched accumulators
-        if (threadIdx.x == 0) acc[p.blank] = 0.f;
-        for (int s = 2 * threadIdx.x + 1; s < Sb; s += 2 * blockDim.x) acc[lab[s]] = 0.f;
         __syncthreads();
     }
 }
@@ -526,27 +528,47 @@ extern "C" size_t b200asr_ctc_workspace_bytes(int B, int T, int L_max) {
     return 2 * (size_t)B * T * S * sizeof(float) + 2 * (size_t)B * S * sizeof(int);
 }
 
-extern "C" int b200asr_ctc_fwd_bwd(const float* log_probs, long long stride_b, long long stride_t,
-                                   const long long* targets, const long long* input_lengths,
-                                   const long long* target_lengths, int B, int T, int V, int L_max, int blank,
-                                   float* nll, const float* grad_scale, float* grad, void* workspace,
-                                   size_t workspace_bytes, b200asr_stream stream) {
-    B200_REQUIRE(log_probs && targets && input_lengths && target_lengths && nll && workspace,
-                 "ctc_fwd_bwd: null pointer");
-    B200_REQUIRE(B > 0 && T > 0 && V > 0 && L_max >= 0, "ctc_fwd_bwd: bad sizes B=%d T=%d V=%d L=%d", B, T, V, L_max);
-    B200_REQUIRE(blank >= 0 && blank < V, "ctc_fwd_bwd: blank %d outside [0,%d)", blank, V);
-    B200_REQUIRE(workspace_bytes >= b200asr_ctc_workspace_bytes(B, T, L_max), "ctc_fwd_bwd: workspace too small");
-    CtcParams p;
+static int ctc_setup(CtcParams& p, const float* log_probs, long long stride_b, long long stride_t,
+                     const long long* targets, const long long* input_lengths, const long long* target_lengths, int B,
+                     int T, int V, int L_max, int blank, float* nll, const float* grad_scale, const float* upstream,
+                     float* grad, void* workspace, size_t workspace_bytes, const char* who) {
+    B200_REQUIRE(log_probs && targets && input_lengths && target_lengths && nll && workspace, "%s: null pointer", who);
+    B200_REQUIRE(B > 0 && T > 0 && V > 0 && L_max >= 0, "%s: bad sizes B=%d T=%d V=%d L=%d", who, B, T, V, L_max);
+    B200_REQUIRE(blank >= 0 && blank < V, "%s: blank %d outside [0,%d)", who, blank, V);
+    B200_REQUIRE(workspace_bytes >= b200asr_ctc_workspace_bytes(B, T, L_max), "%s: workspace too small", who);
     p.lp = log_probs; p.sb = stride_b; p.st = stride_t; p.targets = targets; p.in_len = input_lengths;
     p.tgt_len = target_lengths; p.B = B; p.T = T; p.V = V; p.L_max = L_max; p.S_max = 2 * L_max + 1; p.blank = blank;
-    p.nll = nll; p.scale = grad_scale; p.grad = grad;
+    p.nll = nll; p.scale = grad_scale; p.upstream = upstream; p.grad = grad;
     const size_t S = (size_t)p.S_max;
     float* ws = reinterpret_cast<float*>(workspace);
     p.alpha = ws;
     p.beta = ws + (size_t)B * T * S;
     p.prev_same = reinterpret_cast<int*>(ws + 2 * (size_t)B * T * S);
     p.is_last = p.prev_same + (size_t)B * S;
+    return B200_OK;
+}
 
+static int ctc_launch_grad(const CtcParams& p, cudaStream_t stream) {
+    const size_t S = (size_t)p.S_max;
+    const size_t smem_g = S * (sizeof(float) + 3 * sizeof(int));
+    B200_REQUIRE(smem_g <= (size_t)max_optin_smem(), "ctc: target too long for shared memory (L=%d)", p.L_max);
+    if (smem_g > 48 * 1024)
+        B200_CUDA(cudaFuncSetAttribute(ctc_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+    dim3 grid((p.T + CTC_GRAD_TCHUNK - 1) / CTC_GRAD_TCHUNK, p.B);
+    ctc_grad_kernel<<<grid, CTC_GRAD_THREADS, smem_g, stream>>>(p);
+    B200_LAUNCH_CHECK("ctc_grad_kernel");
+    return B200_OK;
+}
+
+extern "C" int b200asr_ctc_fwd_bwd(const float* log_probs, long long stride_b, long long stride_t,
+                                   const long long* targets, const long long* input_lengths,
+                                   const long long* target_lengths, int B, int T, int V, int L_max, int blank,
+                                   float* nll, const float* grad_scale, float* grad, void* workspace,
+                                   size_t workspace_bytes, b200asr_stream stream) {
+    CtcParams p;
+    const int rc = ctc_setup(p, log_probs, stride_b, stride_t, targets, input_lengths, target_lengths, B, T, V, L_max,
+                             blank, nll, grad_scale, nullptr, grad, workspace, workspace_bytes, "ctc_fwd_bwd");
+    if (rc != B200_OK) return rc;
     const int need = (p.S_max + 31) / 32;      // extended-label positions per lane
     // The warp-synchronous kernel wins while a lane holds few positions (subword targets: S <= 128); for long
     // character targets one position per thread + a block barrier is faster (measured: V=31, L~130: 3.7 vs 9.1 ms
@@ -559,6 +581,7 @@ extern "C" int b200asr_ctc_fwd_bwd(const float* log_probs, long long stride_b, l
         B200_LAUNCH_CHECK("ctc_alpha_beta_warp_kernel");
     } else {
         // long targets: block-per-(utterance, direction) kernel with the lattice row in shared memory
+        const size_t S = (size_t)p.S_max;
         int threads = (p.S_max + 31) / 32 * 32;
         if (threads > 1024) threads = 1024;
         const size_t smem_ab = S * (2 * sizeof(float) + 2 * sizeof(int));
@@ -569,14 +592,20 @@ extern "C" int b200asr_ctc_fwd_bwd(const float* log_probs, long long stride_b, l
         ctc_alpha_beta_kernel<<<dim3(B, 2), threads, smem_ab, (cudaStream_t)stream>>>(p);
         B200_LAUNCH_CHECK("ctc_alpha_beta_kernel");
     }
-    if (grad) {
-        const size_t smem_g = (size_t)V * sizeof(float) + S * (sizeof(float) + 3 * sizeof(int));
-        B200_REQUIRE(smem_g <= (size_t)max_optin_smem(), "ctc_fwd_bwd: vocabulary %d too large for shared memory", V);
-        if (smem_g > 48 * 1024)
-            B200_CUDA(cudaFuncSetAttribute(ctc_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
-        dim3 grid((T + CTC_GRAD_TCHUNK - 1) / CTC_GRAD_TCHUNK, B);
-        ctc_grad_kernel<<<grid, CTC_GRAD_THREADS, smem_g, (cudaStream_t)stream>>>(p);
-        B200_LAUNCH_CHECK("ctc_grad_kernel");
-    }
+    if (grad) return ctc_launch_grad(p, (cudaStream_t)stream);
     return B200_OK;
+}
+
+extern "C" int b200asr_ctc_grad(const float* log_probs, long long stride_b, long long stride_t,
+                                const long long* targets, const long long* input_lengths,
+                                const long long* target_lengths, int B, int T, int V, int L_max, int blank,
+                                const float* nll, const float* grad_scale, const float* upstream, float* grad,
+                                void* workspace, size_t workspace_bytes, b200asr_stream stream) {
+    B200_REQUIRE(grad, "ctc_grad: null gradient pointer");
+    CtcParams p;
+    const int rc = ctc_setup(p, log_probs, stride_b, stride_t, targets, input_lengths, target_lengths, B, T, V, L_max,
+                             blank, const_cast<float*>(nll), grad_scale, upstream, grad, workspace, workspace_bytes,
+                             "ctc_grad");
+    if (rc != B200_OK) return rc;
+    return ctc_launch_grad(p, (cudaStream_t)stream);
 }

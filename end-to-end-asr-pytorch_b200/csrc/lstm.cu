@@ -1491,6 +1491,9 @@ static int bilstm_run(bool bwd, float* gates, const float* w_hh, float* cstate, 
     if (!bwd && g_lstm_mode == 0 && lstm_umma_fwd_supported(B, H, ndir))
         return lstm_umma_fwd(gates, w_hh, cstate, out_or_dout, B, T, H, ndir, workspace, workspace_bytes,
                              (g_lstm_flags & 8) ? nullptr : g_trace, g_lstm_flags >> 4, stream);
+    if (bwd && g_lstm_mode == 0 && !(g_lstm_flags & 32) && lstm_umma_bwd_supported(B, H, ndir))
+        return lstm_umma_bwd(gates, w_hh, cstate, out_or_dout, B, T, H, ndir, workspace, workspace_bytes,
+                             (g_lstm_flags & 8) ? g_trace : nullptr, g_lstm_flags >> 4, stream);
     unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
     float* packed = reinterpret_cast<float*>(ws);
     const size_t xoff = align_up(pl.pack_bytes, 256);

@@ -320,6 +320,286 @@ __global__ void __launch_bounds__(32 * (UBP + 2 + UL_MAX_CTRL), 1) bilstm_fwd_um
     if (warp == UBP) umma::tmem_dealloc(tmem, TMEM_COLS);
 }
 
+// =====================================================================================================================
+// Backward (BPTT) step on tcgen05.  Per CTA (direction, batch group of 32 rows, unit block of UB units) and step:
+//   dh = dOut[b,t] + sum_src partial_src[b, my units]          (inbox: one [32 x UB] fp32 block per source CTA)
+//   pointwise -> dG[b, 4*UB] (written to the gate stash in place), dc carried in a register
+//   partial_me[b, 0..H) = dG[32 x 4UB] . W_slice[4UB x H]      -> scattered to every destination CTA's inbox
+// The step GEMM has K = 4*UB <= 64 (ONE 128-byte K atom) and N = H, so the tensor core is fed with
+//   A1 = [ dG_hi ; dG_lo ]  and  A2 = [ 0 ; dG_hi ]   (M = 64: per TMEM quadrant 8 "hi" rows then 8 "lo" rows)
+//   D[:, n-block] = A1 . W_hi^T + A2 . W_lo^T
+// i.e. the hi rows of D hold dG_hi.W_hi and the lo rows hold dG_lo.W_hi + dG_hi.W_lo (both scaled by 2048): ONE
+// accumulator region of 512 columns, 2*(4UB/16) MMAs of N = 256 per n-block, and tcgen05.ld.16x256b hands every
+// drain thread the (hi, lo) pair of the same (row, column).  dG has no bounded range, so every batch row is scaled by
+// a power of two that brings its largest |dG| to [2^13, 2^14) before the fp16 hi/lo split; the drain undoes it.
+template <int UB>
+__global__ void ul_pack_bwd_kernel(const float* __restrict__ w, uint8_t* __restrict__ dst, int H, int ndir) {
+    const int nub = H / UB;
+    const long long per_cta = (long long)2 * H * 64;           // (part, n, k) elements; k < 4*UB used
+    const long long n_el = (long long)ndir * nub * per_cta;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_el; i += (long long)gridDim.x * blockDim.x) {
+        const int cta = (int)(i / per_cta);
+        int r = (int)(i - (long long)cta * per_cta);
+        const int part = r / (H * 64);
+        r -= part * H * 64;
+        const int n = r >> 6, k = r & 63;
+        const int dir = cta / nub, ub = cta - dir * nub;
+        const int u = k >> 2, g = k & 3;
+        float v = 0.f;
+        if (u < UB) v = w[((long long)dir * 4 * H + (long long)g * H + (ub * UB + u)) * H + n];
+        __half hi, lo;
+        split_f16(v, hi, lo);
+        uint8_t* img = dst + (size_t)cta * ((size_t)2 * H * 128) + (size_t)part * H * 128;
+        *reinterpret_cast<__half*>(img + umma::sw128_offset(n, k * 2)) = part ? lo : hi;
+    }
+}
+
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+constexpr int ULB_EPI_WARPS = 16;
+constexpr int ULB_CTRL = 4;
+
+template <int UB>
+__global__ void __launch_bounds__(32 * (ULB_EPI_WARPS + 2 + ULB_CTRL), 1) bilstm_bwd_umma_kernel(UlParams p) {
+    constexpr int KS = (4 * UB) / 16;               // MMAs (k-steps of 16) per product and n-block
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int H = p.H, T = p.T, nub = p.nub;
+    const int NB = H / 256;                         // n-blocks of 256 accumulator columns
+    uint8_t* sWhi = smem;
+    uint8_t* sWlo = smem + (size_t)H * 128;
+    uint8_t* sA1 = sWlo + (size_t)H * 128;
+    uint8_t* sA2 = sA1 + 8192;
+    float* inbox = reinterpret_cast<float*>(sA2 + 8192);                       // [nub][32][UB]
+    const size_t inbox_bytes = (size_t)nub * UL_BC * UB * sizeof(float);
+    float* rscale = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(inbox) + inbox_bytes);   // [32]
+    uint64_t* in_full = reinterpret_cast<uint64_t*>(rscale + 32);
+    uint64_t* a_ready = in_full + 1;
+    uint64_t* mma_done = in_full + 2;               // [2]
+    uint64_t* d_free = in_full + 4;                 // [2]
+    uint64_t* pub = in_full + 6;
+    uint64_t* wload = in_full + 7;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_full + 8);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int blk = blockIdx.x;
+    const int ub = blk % p.nub; blk /= p.nub;
+    const int bg = blk % p.nbg; blk /= p.nbg;
+    const int dir = blk;
+    const uint32_t tmem_cols = H <= 256 ? 256u : 512u;
+
+    for (int i = tid; i < 16384 / 16; i += blockDim.x) reinterpret_cast<uint4*>(sA1)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) {
+        mbar_init(in_full, ULB_CTRL);
+        mbar_init(a_ready, ULB_EPI_WARPS);
+        for (int j = 0; j < 2; ++j) {
+            mbar_init(&mma_done[j], 1);
+            mbar_init(&d_free[j], ULB_EPI_WARPS);
+        }
+        mbar_init(pub, ULB_EPI_WARPS);
+        mbar_init(wload, 1);
+        mbar_fence_init();
+    }
+    if (warp == ULB_EPI_WARPS) umma::tmem_alloc(tmem_slot, tmem_cols);
+    fence_proxy_async_smem();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const size_t xelems = (size_t)nub * nub * UL_BC * UB;                       // one parity buffer of one (dir, bg)
+    float* xb = reinterpret_cast<float*>(p.xbuf) + ((size_t)dir * p.nbg + bg) * 2 * xelems;
+    unsigned* ctr = p.counters + ((size_t)dir * p.nbg + bg);
+
+    if (warp == ULB_EPI_WARPS + 1) {
+        // ------------------------------------------------------------------ publisher lane
+        if (lane == 0) {
+            for (int step = 0; step + 1 < T; ++step) {
+                mbar_wait(pub, (uint32_t)(step & 1));
+                UL_TRACE(8);
+                fence_acq_rel_gpu();
+                red_relaxed_add_u32(ctr, 1u);
+                UL_TRACE(9);
+            }
+        }
+    } else if (warp > ULB_EPI_WARPS + 1) {
+        // ------------------------------------------------------------------ control lanes: W load, inbox pulls
+        const int c = warp - ULB_EPI_WARPS - 2;
+        if (lane == 0) {
+            if (c == 0) {
+                const uint8_t* wsrc = p.wpack + ((size_t)dir * p.nub + ub) * ((size_t)2 * H * 128);
+                mbar_expect_tx(wload, (uint32_t)(2 * H * 128));
+                for (int off = 0; off < 2 * H * 128; off += 32768)
+                    bulk_g2s(sWhi + off, wsrc + off, 32768, wload);
+            }
+            const uint32_t chunk = (uint32_t)(inbox_bytes / ULB_CTRL);
+            for (int step = 0; step + 1 < T; ++step) {
+                // my epilogue warps summed the inbox of `step` before they released the A tile of `step`
+                mbar_wait(&mma_done[NB - 1], (uint32_t)(step & 1));
+                ul_spin_until(ctr, (unsigned)(step + 1) * (unsigned)nub, p.err_flag);
+                if (c == 0) UL_TRACE(10);
+                if (!(p.flags & 1)) fence_proxy_async();
+                const uint8_t* src = reinterpret_cast<const uint8_t*>(xb + (size_t)(step & 1) * xelems +
+                                                                      (size_t)ub * nub * UL_BC * UB) + (size_t)c * chunk;
+                mbar_expect_tx(in_full, chunk);
+                bulk_g2s(reinterpret_cast<uint8_t*>(inbox) + (size_t)c * chunk, src, chunk, in_full);
+                if (c == 0) UL_TRACE(11);
+            }
+        }
+    } else if (warp == ULB_EPI_WARPS) {
+        // ------------------------------------------------------------------ MMA lane
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma::instr_desc(umma::FMT_F16, 64, 256);
+            const uint32_t a1 = smem_u32(sA1), a2 = smem_u32(sA2), whi = smem_u32(sWhi), wlo = smem_u32(sWlo);
+            mbar_wait(wload, 0);
+            for (int step = 0; step + 1 < T; ++step) {
+                mbar_wait(a_ready, (uint32_t)(step & 1));
+                umma::fence_after_sync();
+                UL_TRACE(1);
+                for (int j = 0; j < NB; ++j) {
+                    if (step > 0) mbar_wait(&d_free[j], (uint32_t)((step - 1) & 1));
+                    umma::fence_after_sync();
+#pragma unroll
+                    for (int kk = 0; kk < KS; ++kk) {
+                        umma::mma_ss<umma::FMT_F16>(tmem + 256 * j, umma::desc_k_sw128(a1 + kk * 32),
+                                                    umma::desc_k_sw128(whi + j * 32768 + kk * 32), idesc, kk > 0);
+                        umma::mma_ss<umma::FMT_F16>(tmem + 256 * j, umma::desc_k_sw128(a2 + kk * 32),
+                                                    umma::desc_k_sw128(wlo + j * 32768 + kk * 32), idesc, 1);
+                    }
+                    umma::commit(&mma_done[j]);
+                }
+                UL_TRACE(2);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ pointwise + drain warps
+        // pointwise mapping: cell i = warp*32 + lane -> (batch row b = i / UB, unit u = i % UB)
+        const int ci = warp * 32 + lane;
+        const bool cell = ci < UL_BC * UB;
+        const int b = cell ? ci / UB : 0, u = cell ? ci % UB : 0;
+        const int brow = p.b0 + bg * UL_BC + b;
+        const bool ok = cell && brow < p.Bend;
+        const int ug = ub * UB + u;
+        const int row_hi = 16 * (b >> 3) + (b & 7), row_lo = row_hi + 8;
+        const uint32_t off_hi = umma::sw128_offset(row_hi, 8 * u), off_lo = umma::sw128_offset(row_lo, 8 * u);
+        // drain mapping: TMEM quadrant q, column quarter jq of every n-block
+        const int q = warp & 3, jq = warp >> 2, r = lane >> 2, tq = lane & 3;
+        const int drow = 8 * q + r;
+        const uint32_t t_lane = tmem + ((uint32_t)(32 * q) << 16);
+        float dc_reg = 0.f;
+        const bool trc = (warp == 0 && lane == 0);
+
+        for (int step = 0; step < T; ++step) {
+            const int fstep = T - 1 - step;
+            const int tt = dir ? (T - 1 - fstep) : fstep;
+            const int tt_prev = dir ? tt + 1 : tt - 1;
+            if (trc) UL_TRACE(0);
+            float4 gtv = make_float4(0.f, 0.f, 0.f, 0.f);
+            float ct = 0.f, cp = 0.f, dh = 0.f;
+            const size_t row = ((size_t)dir * p.B + (ok ? brow : 0)) * T + tt;
+            if (ok) {
+                gtv = *reinterpret_cast<const float4*>(p.gates + (row * H + ug) * 4);
+                ct = p.cst[row * H + ug];
+                if (fstep > 0) cp = p.cst[(((size_t)dir * p.B + brow) * T + tt_prev) * H + ug];
+                dh = p.out[((size_t)brow * T + tt) * (p.ndir * H) + (size_t)dir * H + ug];
+            }
+            if (step > 0) {
+                mbar_wait(in_full, (uint32_t)((step - 1) & 1));
+                if (trc) UL_TRACE(3);
+                if (cell) {
+                    const float* ib = inbox + (size_t)b * UB + u;
+                    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                    int s = 0;
+                    for (; s + 3 < nub; s += 4) {
+                        s0 += ib[(size_t)s * UL_BC * UB];
+                        s1 += ib[(size_t)(s + 1) * UL_BC * UB];
+                        s2 += ib[(size_t)(s + 2) * UL_BC * UB];
+                        s3 += ib[(size_t)(s + 3) * UL_BC * UB];
+                    }
+                    for (; s < nub; ++s) s0 += ib[(size_t)s * UL_BC * UB];
+                    dh += (s0 + s1) + (s2 + s3);
+                }
+            }
+            float4 dg = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok) {
+                const float ig = gtv.x, fg = gtv.y, gg = gtv.z, og = gtv.w;
+                const float tc = tanhf(ct);
+                const float dc = dc_reg + dh * og * (1.f - tc * tc);
+                dg.x = dc * gg * ig * (1.f - ig);
+                dg.y = dc * cp * fg * (1.f - fg);
+                dg.z = dc * ig * (1.f - gg * gg);
+                dg.w = dh * tc * og * (1.f - og);
+                dc_reg = dc * fg;
+                *reinterpret_cast<float4*>(p.gates + (row * H + ug) * 4) = dg;
+            }
+            if (trc) UL_TRACE(4);
+            if (step + 1 < T) {
+                // per-row power-of-two scale: the row's largest |dG| goes to [2^13, 2^14)
+                float m = fmaxf(fmaxf(fabsf(dg.x), fabsf(dg.y)), fmaxf(fabsf(dg.z), fabsf(dg.w)));
+#pragma unroll
+                for (int o = 1; o < UB; o <<= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                int e = (int)((__float_as_uint(m) >> 23) & 0xffu) - 127;
+                e = e < -100 ? -100 : (e > 100 ? 100 : e);
+                const float sc = __uint_as_float((uint32_t)(127 + 13 - e) << 23);
+                if (cell) {
+                    if (u == 0) rscale[b] = __uint_as_float((uint32_t)(127 + e - 13) << 23);
+                    __half hi[4], lo[4];
+                    split_f16(dg.x * sc, hi[0], lo[0]);
+                    split_f16(dg.y * sc, hi[1], lo[1]);
+                    split_f16(dg.z * sc, hi[2], lo[2]);
+                    split_f16(dg.w * sc, hi[3], lo[3]);
+                    const uint2 vh = make_uint2((uint32_t)__half_as_ushort(hi[0]) | ((uint32_t)__half_as_ushort(hi[1]) << 16),
+                                                (uint32_t)__half_as_ushort(hi[2]) | ((uint32_t)__half_as_ushort(hi[3]) << 16));
+                    const uint2 vl = make_uint2((uint32_t)__half_as_ushort(lo[0]) | ((uint32_t)__half_as_ushort(lo[1]) << 16),
+                                                (uint32_t)__half_as_ushort(lo[2]) | ((uint32_t)__half_as_ushort(lo[3]) << 16));
+                    *reinterpret_cast<uint2*>(sA1 + off_hi) = vh;
+                    *reinterpret_cast<uint2*>(sA1 + off_lo) = vl;
+                    *reinterpret_cast<uint2*>(sA2 + off_lo) = vh;
+                }
+                fence_proxy_async_smem();       // my generic-proxy writes of the A tiles -> visible to the tensor core
+                __syncwarp();
+                if (lane == 0) ul_arrive(a_ready);
+                if (trc) UL_TRACE(5);
+                // ---- drain the accumulator into the destinations' inboxes, n-block by n-block
+                float* outbase = xb + (size_t)(step & 1) * xelems;
+                for (int j = 0; j < NB; ++j) {
+                    mbar_wait(&mma_done[j], (uint32_t)(step & 1));
+                    umma::fence_after_sync();
+                    if (trc && j == 0) UL_TRACE(6);
+                    uint32_t v0[16], v1[16];
+                    umma::ld_16x256b_x4(t_lane + 256 * j + 64 * jq, v0);
+                    umma::ld_16x256b_x4(t_lane + 256 * j + 64 * jq + 32, v1);
+                    umma::wait_ld();
+                    umma::fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) ul_arrive(&d_free[j]);
+                    const float rs = rscale[drow];
+                    const float k = 1.f / 2048.f;
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const uint32_t* v = hh ? &v1[4 * g] : &v0[4 * g];
+                            const int n = 256 * j + 64 * jq + 32 * hh + 8 * g + 2 * tq;
+                            const int dst = n / UB, uu = n - dst * UB;
+                            const float o0 = (__uint_as_float(v[0]) + __uint_as_float(v[2]) * k) * rs;
+                            const float o1 = (__uint_as_float(v[1]) + __uint_as_float(v[3]) * k) * rs;
+                            *reinterpret_cast<float2*>(outbase + (((size_t)dst * nub + ub) * UL_BC + drow) * UB + uu) =
+                                make_float2(o0, o1);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) ul_arrive(pub);
+                if (trc) UL_TRACE(7);
+            }
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == ULB_EPI_WARPS) umma::tmem_dealloc(tmem, tmem_cols);
+}
+
 struct UlPlan {
     int UB, UBp, nub, nbg, ctas, NA, Bsub, nsplit;
     size_t smem, pack_bytes, xbuf_bytes;
@@ -383,7 +663,90 @@ int ul_launch_fwd(const UlPlan& pl, UlParams p, const float* w_hh, cudaStream_t 
     return B200_OK;
 }
 
+struct UlbPlan {
+    int UB, nub, nbg, ctas, Bsub, nsplit;
+    size_t smem, pack_bytes, xbuf_bytes;
+};
+
+int ulb_plan(int B, int H, int ndir, UlbPlan* out) {
+    if (H != 256 && H != 512) return -1;          // accumulator = H TMEM columns in n-blocks of 256
+    const int sms = sm_count();
+    const size_t cap = (size_t)max_optin_smem();
+    for (int n = 1; n <= B; ++n) {
+        const int Bs = (B + n - 1) / n;
+        const int nbg = (Bs + UL_BC - 1) / UL_BC;
+        for (int UB = 8; UB <= 16; UB += 8) {
+            if (H % UB) continue;
+            const int nub = H / UB;
+            const int ctas = ndir * nbg * nub;
+            if (ctas > sms) continue;
+            const size_t inbox = (size_t)nub * UL_BC * UB * 4;
+            const size_t smem = (size_t)2 * H * 128 + 16384 + inbox + 128 + 128;
+            if (smem > cap || (inbox / ULB_CTRL) % 16) continue;
+            out->UB = UB; out->nub = nub; out->nbg = nbg; out->ctas = ctas; out->Bsub = Bs;
+            out->nsplit = (B + Bs - 1) / Bs; out->smem = smem;
+            out->pack_bytes = (size_t)ndir * nub * 2 * H * 128;
+            out->xbuf_bytes = (size_t)ndir * nbg * 2 * nub * inbox;
+            return 0;
+        }
+        if (Bs <= UL_BC) break;
+    }
+    return -2;
+}
+
+template <int UB>
+int ul_launch_bwd(const UlbPlan& pl, UlParams p, const float* w_hh, cudaStream_t stream) {
+    {
+        const long long n = (long long)p.ndir * pl.nub * 2 * p.H * 64;
+        int blocks = (int)((n + 255) / 256);
+        if (blocks > 8192) blocks = 8192;
+        ul_pack_bwd_kernel<UB><<<blocks, 256, 0, stream>>>(w_hh, const_cast<uint8_t*>(p.wpack), p.H, p.ndir);
+        B200_LAUNCH_CHECK("ul_pack_bwd_kernel");
+    }
+    const void* fn = (const void*)bilstm_bwd_umma_kernel<UB>;
+    B200_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    int per_sm = 0;
+    const int threads = 32 * (ULB_EPI_WARPS + 2 + ULB_CTRL);
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, pl.smem));
+    B200_REQUIRE((long long)per_sm * sm_count() >= pl.ctas, "bilstm(umma bwd): %d CTAs cannot be co-resident (%d/SM x %d SMs)",
+                 pl.ctas, per_sm, sm_count());
+    for (int sp = 0; sp < pl.nsplit; ++sp) {
+        p.b0 = sp * pl.Bsub;
+        p.Bend = p.b0 + pl.Bsub < p.B ? p.b0 + pl.Bsub : p.B;
+        B200_CUDA(cudaMemsetAsync(p.counters, 0, UL_COUNTER_BYTES, stream));
+        void* args[] = {&p};
+        B200_CUDA(cudaLaunchCooperativeKernel(fn, dim3(pl.ctas), dim3(threads), args, pl.smem, stream));
+        count_launch();
+    }
+    return B200_OK;
+}
+
 }  // namespace
+
+bool lstm_umma_bwd_supported(int B, int H, int ndir) {
+    UlbPlan pl;
+    return ulb_plan(B, H, ndir, &pl) == 0;
+}
+
+int lstm_umma_bwd(float* gates, const float* w_hh, const float* cstate, const float* dout, int B, int T, int H, int ndir,
+                  void* workspace, size_t workspace_bytes, long long* trace, int flags, cudaStream_t stream) {
+    UlbPlan pl;
+    B200_REQUIRE(ulb_plan(B, H, ndir, &pl) == 0, "bilstm(umma bwd): unsupported shape B=%d H=%d ndir=%d", B, H, ndir);
+    B200_REQUIRE(workspace_bytes >= lstm_umma_workspace_bytes(B, H, ndir), "bilstm(umma bwd): workspace too small");
+    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+    UlParams p;
+    p.gates = gates; p.cst = const_cast<float*>(cstate); p.out = const_cast<float*>(dout);
+    p.wpack = ws;
+    p.xbuf = ws + ul_align(pl.pack_bytes);
+    p.counters = reinterpret_cast<unsigned*>(ws + ul_align(pl.pack_bytes) + ul_align(pl.xbuf_bytes));
+    p.err_flag = reinterpret_cast<int*>(p.counters + (UL_COUNTER_BYTES / 4 - 4));
+    p.trace = trace;
+    p.flags = flags;
+    p.B = B; p.T = T; p.H = H; p.ndir = ndir; p.UB = pl.UB; p.nub = pl.nub; p.nbg = pl.nbg; p.NA = 0; p.NC = ULB_CTRL;
+    p.b0 = 0; p.Bend = B;
+    if (pl.UB == 16) return ul_launch_bwd<16>(pl, p, w_hh, stream);
+    return ul_launch_bwd<8>(pl, p, w_hh, stream);
+}
 
 bool lstm_umma_fwd_supported(int B, int H, int ndir) {
     UlPlan pl;
@@ -392,8 +755,11 @@ bool lstm_umma_fwd_supported(int B, int H, int ndir) {
 
 size_t lstm_umma_workspace_bytes(int B, int H, int ndir) {
     UlPlan pl;
-    if (ul_plan(B, H, ndir, &pl) != 0) return 0;
-    return ul_align(pl.pack_bytes) + ul_align(pl.xbuf_bytes) + UL_COUNTER_BYTES;
+    UlbPlan pb;
+    size_t f = 0, b = 0;
+    if (ul_plan(B, H, ndir, &pl) == 0) f = ul_align(pl.pack_bytes) + ul_align(pl.xbuf_bytes) + UL_COUNTER_BYTES;
+    if (ulb_plan(B, H, ndir, &pb) == 0) b = ul_align(pb.pack_bytes) + ul_align(pb.xbuf_bytes) + UL_COUNTER_BYTES;
+    return f > b ? f : b;
 }
 
 int lstm_umma_plan(int B, int H, int ndir, int* unit_block, int* batch_block, int* n_ctas) {

@@ -30,6 +30,15 @@ class DataParallel:
             dist.init_process_group(backend=backend, rank=self.rank, world_size=self.world)
             self.backend = backend
 
+    @classmethod
+    def single(cls):
+        """A disabled communicator (world 1) regardless of the torchrun environment: the single-GPU reference of a
+        data-parallel step."""
+        o = cls.__new__(cls)
+        o.world, o.rank, o.enabled, o.backend = 1, 0, False, None
+        o.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        return o
+
     def shard(self, *tensors):
         """Rank r takes rows r::world of each [B_global, ...] tensor (lengths sorted desc => equal work)."""
         if not self.enabled:

@@ -32,6 +32,8 @@ SIGNATURES = {
     "b200asr_ctc_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "b200asr_ctc_fwd_bwd": (c_int, [_P, c_longlong, c_longlong, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P,
                                     _P, _P, c_size_t, _P]),
+    "b200asr_ctc_grad": (c_int, [_P, c_longlong, c_longlong, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P,
+                                 _P, _P, c_size_t, _P]),
     "b200asr_bilstm_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "b200asr_bilstm_plan": (c_int, [c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "b200asr_bilstm_uses_tensor_cores": (c_int, [c_int, c_int, c_int]),

@@ -89,9 +89,11 @@ class RNNLayer(nn.Module):
         if self.sample_style not in ["drop", "concat"]:
             raise ValueError("Unsupported Sample Style: " + self.sample_style)
         self.module = module.upper()
-        if self.module != "LSTM":
-            raise NotImplementedError("only module 'LSTM' is on the accelerated path (GRU: SURVEY.md 8(f) rank 4)")
-        self.layer = nn.LSTM(input_dim, dim, bidirectional=bidirection, num_layers=1, batch_first=True)
+        if self.module not in ("LSTM", "GRU"):
+            raise NotImplementedError("RNN module %s (the reference accepts LSTM and GRU, src/module.py:112-113)" % module)
+        # LSTM: parameter container only, the recurrence runs in the persistent sm_100a kernels.  GRU (SURVEY.md 8(f)
+        # rank 4, no BASELINE config uses it): the library cuDNN layer, same state_dict keys as the reference.
+        self.layer = getattr(nn, self.module)(input_dim, dim, bidirectional=bidirection, num_layers=1, batch_first=True)
         if self.layer_norm:
             self.ln = nn.LayerNorm(rnn_out_dim)
         if self.dropout > 0:
@@ -106,7 +108,10 @@ class RNNLayer(nn.Module):
         return ps
 
     def forward(self, input_x, x_len):
-        output = ops.bilstm(input_x, self.lstm_params(), self.ndir)
+        if self.module == "LSTM":
+            output = ops.bilstm(input_x, self.lstm_params(), self.ndir)
+        else:
+            output, _ = self.layer(input_x)
         if self.layer_norm:
             output = self.ln(output)
         if self.dropout > 0:

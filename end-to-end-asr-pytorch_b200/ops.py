@@ -1,5 +1,6 @@
 """torch.autograd wrappers around the C-ABI kernels (host-side plumbing; the arithmetic is in csrc/)."""
 import ctypes
+import os
 
 import torch
 from torch.autograd import Function
@@ -216,10 +217,16 @@ def bilstm(x, lstm_params, ndir):
 
 # ----------------------------------------------------------------------------------------------------------
 class LogSoftmaxFn(Function):
-    """log_softmax over the last dim (src/asr.py:96) + greedy argmax ids as a by-product."""
+    """log_softmax over the last dim (src/asr.py:96) + greedy argmax ids as a by-product.
+
+    `ctc_head=True` declares that the ONLY differentiable consumer of the result is the CTC loss (ops.CTCLoss), as in
+    the reference's train step (bin/train_asr.py:123-124).  ATen's CTC backward - and ours - returns
+    exp(lp) - occupancy, whose class sum is zero, i.e. it already IS the logit gradient: the
+    log-softmax backward  dx = g - exp(lp) * sum_c g  is then the identity and its 12*T*V-byte pass is skipped.
+    B200ASR_CHECK_CTC_HEAD=1 runs the full backward and checks the claim."""
 
     @staticmethod
-    def forward(ctx, logits):
+    def forward(ctx, logits, ctc_head=False):
         lib = L.load()
         x = _f32c(logits)
         V = x.shape[-1]
@@ -229,29 +236,41 @@ class LogSoftmaxFn(Function):
         with L.timed("log_softmax_fwd", 8 * n * V):
             L.check(lib.b200asr_log_softmax_fwd(L.ptr(x), L.ptr(y), None, L.ptr(am), n, V, L.stream()),
                     "log_softmax_fwd")
+        ctx.ctc_head = bool(ctc_head)
         ctx.save_for_backward(y)
         ctx.mark_non_differentiable(am)
         return y, am
 
     @staticmethod
     def backward(ctx, g, _gam):
-        lib = L.load()
         (y,) = ctx.saved_tensors
+        if ctx.ctc_head and not _CHECK_CTC_HEAD:
+            return g, None
+        lib = L.load()
         g = _f32c(g)
         V = y.shape[-1]
         n = y.numel() // V
         dx = torch.empty_like(y)
         with L.timed("log_softmax_bwd", 12 * n * V):
             L.check(lib.b200asr_log_softmax_bwd(L.ptr(y), L.ptr(g), L.ptr(dx), n, V, L.stream()), "log_softmax_bwd")
-        return dx
+        if ctx.ctc_head:
+            err = float((dx - g).abs().max()) / max(float(g.abs().max()), 1e-30)
+            if err > 1e-4:
+                raise L.B200AsrError("log_softmax(ctc_head=True): upstream gradient is not a CTC gradient "
+                                     "(identity-backward error %.2e)" % err)
+        return dx, None
 
 
-def log_softmax(logits):
-    return LogSoftmaxFn.apply(logits)
+_CHECK_CTC_HEAD = os.environ.get("B200ASR_CHECK_CTC_HEAD", "0") == "1"
+
+
+def log_softmax(logits, ctc_head=False):
+    return LogSoftmaxFn.apply(logits, ctc_head)
 
 
 class CTCLossFn(Function):
-    """sum_b weight_b * nll_b with the gradient produced in the same kernel call (forward + backward fused).
+    """sum_b weight_b * nll_b.  Forward = the alpha/beta lattice kernels (nll); backward = ONE gradient kernel that
+    already multiplies by weight_b and by the upstream scalar, so no scaling pass over [T,B,V] follows.
 
     log_probs: [T,B,V] view of [B,T,V] memory (or any layout with unit class stride), like the reference passes
     `ctc_output.transpose(0,1)` (bin/train_asr.py:123-124).
@@ -272,24 +291,33 @@ class CTCLossFn(Function):
         tl = torch.as_tensor(target_lengths, dtype=torch.int64).to(dev).contiguous()
         w = _f32c(weights.to(dev))
         nll = torch.empty(B, device=dev, dtype=torch.float32)
-        # gradient buffer laid out like log_probs' memory
-        grad = torch.empty_strided(log_probs.shape, log_probs.stride(), device=dev, dtype=torch.float32)
         ws_bytes = lib.b200asr_ctc_workspace_bytes(B, T, Lmax)
         ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
-        # algorithmic bytes: read the log-probs and write the gradient once each (+ nll)
-        with L.timed("ctc_fwd_bwd", 8 * T * V * B + 4 * B):
+        with L.timed("ctc_alpha_beta", 4 * B):
             L.check(lib.b200asr_ctc_fwd_bwd(L.ptr(log_probs), log_probs.stride(1), log_probs.stride(0),
                                             L.ptr(targets), L.ptr(il), L.ptr(tl), B, T, V, Lmax, blank, L.ptr(nll),
-                                            L.ptr(w), L.ptr(grad), L.ptr(ws), ws_bytes, L.stream()), "ctc_fwd_bwd")
-        ctx.save_for_backward(grad)
+                                            L.ptr(w), None, L.ptr(ws), ws_bytes, L.stream()), "ctc_fwd_bwd")
+        ctx.save_for_backward(log_probs, targets, il, tl, w, nll, ws)
+        ctx.blank = blank
         ctx.mark_non_differentiable(nll)
         loss = (nll * w).sum()
         return loss, nll
 
     @staticmethod
     def backward(ctx, gloss, _gnll):
-        (grad,) = ctx.saved_tensors
-        return grad.mul_(gloss), None, None, None, None, None   # stash consumed in place
+        lib = L.load()
+        log_probs, targets, il, tl, w, nll, ws = ctx.saved_tensors
+        T, B, V = log_probs.shape
+        # gradient buffer laid out like log_probs' memory
+        grad = torch.empty_strided(log_probs.shape, log_probs.stride(), device=log_probs.device, dtype=torch.float32)
+        up = _f32c(gloss.reshape(1))
+        # algorithmic bytes: read the log-probs and write the gradient once each
+        with L.timed("ctc_grad", 8 * T * V * B):
+            L.check(lib.b200asr_ctc_grad(L.ptr(log_probs), log_probs.stride(1), log_probs.stride(0), L.ptr(targets),
+                                         L.ptr(il), L.ptr(tl), B, T, V, targets.shape[1], ctx.blank, L.ptr(nll),
+                                         L.ptr(w), L.ptr(up), L.ptr(grad), L.ptr(ws), ws.numel(), L.stream()),
+                    "ctc_grad")
+        return grad, None, None, None, None, None
 
 
 class CTCLoss(torch.nn.Module):

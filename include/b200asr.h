@@ -80,6 +80,14 @@ B200ASR_API int b200asr_ctc_fwd_bwd(const float* log_probs, long long stride_b, 
                         const long long* input_lengths, const long long* target_lengths, int B, int T, int V,
                         int L_max, int blank, float* nll, const float* grad_scale, float* grad, void* workspace,
                         size_t workspace_bytes, b200asr_stream stream);
+/* The gradient half alone, for callers that learn the upstream scale only in their backward pass (autograd): run
+ * b200asr_ctc_fwd_bwd with grad = NULL in the forward (nll + the alpha/beta lattices stay in `workspace`), then this
+ * with the SAME workspace.  `upstream` (device scalar, may be NULL) multiplies every element, so no separate scaling
+ * pass over the [T,B,V] gradient is needed.  Out-of-range labels are clamped into [0,V) (torch raises on them). */
+B200ASR_API int b200asr_ctc_grad(const float* log_probs, long long stride_b, long long stride_t, const long long* targets,
+                     const long long* input_lengths, const long long* target_lengths, int B, int T, int V,
+                     int L_max, int blank, const float* nll, const float* grad_scale, const float* upstream,
+                     float* grad, void* workspace, size_t workspace_bytes, b200asr_stream stream);
 
 /* ---- K7/K8: persistent (Bi)LSTM recurrence -----------------------------------------------------------------
  * replaces the time loop inside torch.nn.LSTM as used by src/module.py:112-113,129-132 (one layer,

@@ -36,6 +36,15 @@ def tiny_model_cfg(kind):
         enc = dict(enc, sample_rate=[1, 1], proj=[True, False], sample_style="drop")
         dec = dict(dec, layer=2)
         return dict(ctc_weight=0.0, encoder=enc, attention=att, decoder=dec)
+    if kind == "vgg":      # configs[0]'s prenet (config/libri/asr_example.yaml): VGG extractor, T not a multiple of 4
+        enc = dict(prenet="vgg", module="LSTM", bidirection=True, dim=[32], dropout=[0], layer_norm=[False],
+                   proj=[True], sample_rate=[1], sample_style="drop")
+        return dict(ctc_weight=0.0, encoder=enc, attention=att, decoder=dec)
+    if kind == "dot":      # scaled-dot attention, 2 heads, value projection, layer norm, GRU encoder layer
+        enc = dict(prenet="", module="GRU", bidirection=True, dim=[32, 32], dropout=[0, 0],
+                   layer_norm=[True, False], proj=[False, True], sample_rate=[1, 2], sample_style="drop")
+        att = dict(mode="dot", dim=16, num_head=2, v_proj=True, temperature=0.5, loc_kernel_size=5, loc_kernel_num=4)
+        return dict(ctc_weight=0.5, encoder=enc, attention=att, decoder=dec)
     raise KeyError(kind)
 
 
@@ -183,6 +192,8 @@ def main():
     golden_model("hybrid", 21, 3, 24, 8, 12, 5)
     golden_model("cnn", 31, 2, 40, 8, 12, 5)
     golden_model("att", 41, 3, 16, 8, 12, 6)
+    golden_model("vgg", 51, 2, 26, 40, 12, 5)
+    golden_model("dot", 61, 3, 20, 8, 12, 5)
 
 
 if __name__ == "__main__":

@@ -128,8 +128,11 @@ def test_ctc_golden_cases(pkg):
         assert np.max(np.abs(lp.grad[:, 0].cpu().numpy() - g["c%d_grad" % i])) < 1e-5
 
 
+@pytest.mark.parametrize("head", [False, True])
 @pytest.mark.parametrize("B,T,V,Lmax", [(4, 50, 31, 20), (3, 37, 500, 9), (6, 149, 5000, 40), (2, 300, 31, 141)])
-def test_ctc_random_vs_aten_cpu(pkg, B, T, V, Lmax):
+def test_ctc_random_vs_aten_cpu(pkg, B, T, V, Lmax, head):
+    """head=True: the CTC-head contract of ops.log_softmax (its backward is the identity because the CTC gradient in
+    ATen's convention already is the logit gradient) must give the same logit gradient."""
     gen = torch.Generator().manual_seed(B * 1000 + T)
     logits = torch.randn(B, T, V, generator=gen)
     tl = torch.randint(1, Lmax, (B,), generator=gen)
@@ -142,9 +145,11 @@ def test_ctc_random_vs_aten_cpu(pkg, B, T, V, Lmax):
         if tl[b] > 2:
             txt[b, 1] = txt[b, 0]
     x = logits.to(DEV).requires_grad_(True)
-    lp, _ = pkg.ops.log_softmax(x)
-    loss = pkg.CTCLoss(blank=0)(lp.transpose(0, 1), txt.to(DEV), il.to(DEV), tl.to(DEV))
+    lp, _ = pkg.ops.log_softmax(x, ctc_head=head)
+    loss = pkg.CTCLoss(blank=0)(lp.transpose(0, 1), txt.to(DEV), il.to(DEV), tl.to(DEV)) * 0.3   # upstream scale
     loss.backward()
+    loss = loss / 0.3
+    x.grad /= 0.3
     xr = logits.clone().requires_grad_(True)
     lpr = F.log_softmax(xr, -1)
     ref = F.ctc_loss(lpr.transpose(0, 1), txt, il, tl, blank=0, reduction="mean", zero_infinity=False)
@@ -409,4 +414,38 @@ def test_grad_norm_and_adadelta_vs_torch(pkg):
     L.check(lib.b200asr_grad_norm(L.ptr(g), n, L.ptr(norm), L.ptr(scratch), L.stream()))
     L.check(lib.b200asr_adadelta_step(L.ptr(p), L.ptr(g), L.ptr(sq), L.ptr(acc), n, 1.0, 0.9, 1e-8, 0.0,
                                       L.ptr(norm), 5.0, L.stream()))
+    assert torch.isnan(norm).item() and torch.equal(p, before)
+
+
+def test_grad_norm_and_adam_vs_torch(pkg):
+    """The fused clip + Adam update (csrc/optim.cu) against torch.optim.Adam after clip_grad_norm_, 3 steps with bias
+    correction, then the NaN-skip rule of src/solver.py:86-89."""
+    L = pkg.lib
+    lib = L.load()
+    torch.manual_seed(3)
+    n = 70001
+    p0 = torch.randn(n)
+    p = p0.clone().to(DEV)
+    m = torch.zeros(n, device=DEV)
+    v = torch.zeros(n, device=DEV)
+    norm = torch.zeros(1, device=DEV)
+    scratch = torch.empty(lib.b200asr_grad_norm_scratch_bytes(), dtype=torch.uint8, device=DEV)
+    pr = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([pr], lr=1e-3, betas=(0.9, 0.999), eps=1e-8)
+    for it in range(3):
+        g0 = torch.randn(n) * (0.01 if it == 1 else 3.0)         # step 1 is below the clip threshold
+        g = g0.clone().to(DEV)
+        L.check(lib.b200asr_grad_norm(L.ptr(g), n, L.ptr(norm), L.ptr(scratch), L.stream()))
+        L.check(lib.b200asr_adam_step(L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), n, 1e-3, 0.9, 0.999, 1e-8, 0.0, it + 1,
+                                      L.ptr(norm), 5.0, L.stream()))
+        pr.grad = g0.clone()
+        tn = torch.nn.utils.clip_grad_norm_([pr], 5.0)
+        opt.step()
+        assert abs(norm.item() - tn.item()) < 1e-5 * tn.item()
+        assert rel_err(p.cpu().numpy(), pr.detach().numpy(), floor=1e-3) < 1e-5
+    before = p.clone()
+    g[7] = float("nan")
+    L.check(lib.b200asr_grad_norm(L.ptr(g), n, L.ptr(norm), L.ptr(scratch), L.stream()))
+    L.check(lib.b200asr_adam_step(L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), n, 1e-3, 0.9, 0.999, 1e-8, 0.0, 4,
+                                  L.ptr(norm), 5.0, L.stream()))
     assert torch.isnan(norm).item() and torch.equal(p, before)

@@ -25,8 +25,10 @@ def _build(pkg, g, kind):
     return model.to(DEV), cfg
 
 
-@pytest.mark.parametrize("kind", ["ctc", "hybrid", "cnn", "att"])
+@pytest.mark.parametrize("kind", ["ctc", "hybrid", "cnn", "att", "vgg", "dot"])
 def test_train_step_matches_reference(pkg, kind):
+    """"vgg" = configs[0]'s VGG prenet (T % 4 != 0); "dot" = scaled-dot attention with 2 heads + value projection,
+    LayerNorm and a GRU encoder: the yaml-schema branches outside the four north-star kernels (library ops)."""
     g = load_golden("model_%s.npz" % kind)
     model, cfg = _build(pkg, g, kind)
     model.train()
@@ -67,7 +69,7 @@ def test_train_step_matches_reference(pkg, kind):
     assert abs(np.sqrt(sq) - float(g["grad_norm"])) < 1e-4 * float(g["grad_norm"])
 
 
-@pytest.mark.parametrize("kind", ["hybrid", "att"])
+@pytest.mark.parametrize("kind", ["hybrid", "att", "vgg", "dot"])
 def test_greedy_inference_ids_bit_exact(pkg, kind):
     g = load_golden("model_%s.npz" % kind)
     model, cfg = _build(pkg, g, kind)

@@ -88,29 +88,30 @@ def _P(g):
     return {k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd.")}
 
 
-@pytest.mark.parametrize("kind", ["ctc", "hybrid", "cnn", "att"])
+@pytest.mark.parametrize("kind", ["ctc", "hybrid", "cnn", "att", "vgg"])
 def test_ref_port_matches_reference_model(kind):
     g = load_golden("model_%s.npz" % kind)
     P = {k: v.clone().requires_grad_(True) for k, v in _P(g).items()}
     cfg = tiny_model_cfg(kind)
     res = ref_port.forward_losses(P, cfg, torch.from_numpy(g["feat"]), torch.from_numpy(g["feat_len"]),
                                   torch.from_numpy(g["txt"]))
+    tol = 1e-4 if kind == "vgg" else 1e-5     # oneDNN's conv2d picks thread-count dependent algorithms
     assert np.array_equal(res["encode_len"].numpy(), g["encode_len"])
     if "ctc_output" in g:
         assert rel_err(res["ctc_output"].detach().numpy(), g["ctc_output"]) < 1e-5
         assert np.array_equal(res["ctc_output"].argmax(-1).numpy(), g["ctc_argmax"])
         assert abs(float(res["ctc_loss"]) - float(g["ctc_loss"])) < 1e-5
     if "att_output" in g:
-        assert rel_err(res["att_output"].detach().numpy(), g["att_output"]) < 1e-5
-        assert rel_err(res["att_seq"].detach().numpy(), g["att_seq"]) < 1e-5
+        assert rel_err(res["att_output"].detach().numpy(), g["att_output"]) < tol
+        assert rel_err(res["att_seq"].detach().numpy(), g["att_seq"]) < tol
         assert np.array_equal(res["att_output"].argmax(-1).numpy(), g["att_argmax"])
     res["total_loss"].backward()
-    assert abs(float(res["total_loss"]) - float(g["total_loss"])) < 1e-5
+    assert abs(float(res["total_loss"]) - float(g["total_loss"])) < tol
     for k, p in P.items():
         if ("grad." + k) in g:
             assert rel_err(p.grad.numpy(), g["grad." + k], floor=1e-4) < 1e-3, k
     norm, _ = ref_port.grad_norm_clip([p.grad for p in P.values() if p.grad is not None])
-    assert abs(float(norm) - float(g["grad_norm"])) < 1e-5
+    assert abs(float(norm) - float(g["grad_norm"])) < tol
 
 
 def test_lstm_np_matches_reference_layer():
