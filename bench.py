@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time the eager step instead of the CUDA-graph replay")
+    ap.add_argument("--no-micro", action="store_true", help="skip the fbank/CTC micro-benchmark (BASELINE configs[4])")
+    ap.add_argument("--no-also", action="store_true", help="multi-GPU runs: skip the extra cfgD (BASELINE configs[3]) timing")
     ap.add_argument("--no-parity", action="store_true", help="skip the same-run parity check against the CPU path")
     ap.add_argument("--parity-workloads", default="auto",
                     help="comma list of workloads parity-checked at full size after the timed regions "
@@ -301,6 +303,84 @@ def parity_check(pkg, step_fn, cfg, waves, lens, txt, dev, n_ref=8):
     return out
 
 
+def micro_bench(pkg, dev, peak):
+    """BASELINE.json configs[4]: mel-fbank (+delta+CMVN) and the CTC kernels on 1000 synthetic utterances of 2-30 s
+    (batches of 100, zero padded to the batch maximum), L2 flushed (256 MB write) before every timed launch, CUDA
+    events per C-ABI launch.  Algorithmic bytes per SURVEY.md 8(d): fbank 4N + 160m, delta+CMVN 4m(40+120), CTC
+    2*4*T'*V (+4*T'*V logits read for the log-softmax that feeds it).  Returns {kernel: {ms, GB/s, frac of HBM peak}}."""
+    cfg = pkg.synthetic.load_config("cfgB")
+    tr, _ = pkg.create_transform(dict(cfg["data"]["audio"]), device=dev)
+    fe = tr.frontend
+    g = torch.Generator().manual_seed(0)
+    lens = torch.randint(32000, 480001, (1000,), generator=g).sort(descending=True)[0]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    T = pkg.lib.TIMER
+    acc = {}
+
+    def run(fn, names):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        for _ in range(3):
+            flush.zero_()
+            T.reset()
+            T.enabled = True
+            fn()
+            torch.cuda.synchronize()
+            T.enabled = False
+            for k, d in T.summary().items():
+                if k in names:
+                    acc.setdefault(k, []).append((d["ms"], d["bytes"]))
+
+    for i in range(0, 1000, 100):
+        l = lens[i:i + 100]
+        wave = torch.zeros(100, int(l[0]), device=dev)
+        for b in range(100):
+            wave[b, :int(l[b])] = 0.05 * torch.randn(int(l[b]), device=dev)
+        run(lambda: fe(wave, l), ("fbank_fwd", "delta_cmvn_fwd"))
+        del wave
+    out = {}
+    for V, Lr in ((31, (20, 130)), (5000, (6, 45))):
+        for i in range(0, 1000, 100):
+            l = lens[i:i + 100]
+            Tp = ((l - 400) // 160 + 1) // 4
+            Tm = int(Tp.max())
+            logits = torch.randn(100, Tm, V, device=dev, requires_grad=True)
+            tl = torch.minimum(torch.randint(Lr[0], Lr[1], (100,), generator=g), (Tp // 3).clamp(min=1))
+            txt = torch.zeros(100, int(tl.max()), dtype=torch.long)
+            for b in range(100):
+                txt[b, :tl[b]] = torch.randint(1, V, (int(tl[b]),), generator=g)
+            txt, Td, tld = txt.to(dev), Tp.to(dev), tl.to(dev)
+            crit = pkg.CTCLoss(blank=0)
+
+            def step():
+                logits.grad = None
+                lp, _ = pkg.ops.log_softmax(logits, ctc_head=True)
+                crit(lp.transpose(0, 1), txt, Td, tld).backward()
+            run(step, ("log_softmax_fwd", "ctc_alpha_beta", "ctc_grad"))
+            del logits
+        for k in ("log_softmax_fwd", "ctc_alpha_beta", "ctc_grad"):
+            acc["%s_V%d" % (k, V)] = acc.pop(k, [])
+    for k, rows in acc.items():
+        if not rows:
+            continue
+        # per batch: median of its 3 timed launches; totals over the 10 batches
+        n = len(rows) // 3
+        ms = sum(sorted(r[0] for r in rows[3 * j:3 * j + 3])[1] for j in range(n))
+        by = sum(rows[3 * j][1] for j in range(n))
+        out[k] = {"ms_per_1000_utt": ms, "algorithmic_gbs": by / (ms * 1e-3) / 1e9, "frac_hbm": by / (ms * 1e-3) / 1e9 / peak}
+    for V in (31, 5000):
+        ks = ["log_softmax_fwd_V%d" % V, "ctc_alpha_beta_V%d" % V, "ctc_grad_V%d" % V]
+        if all(k in out for k in ks):
+            ms = sum(out[k]["ms_per_1000_utt"] for k in ks)
+            by = out[ks[0]]["algorithmic_gbs"] * out[ks[0]]["ms_per_1000_utt"] * 1e6 * 0.5 + \
+                out[ks[2]]["algorithmic_gbs"] * out[ks[2]]["ms_per_1000_utt"] * 1e6      # 4T'V (logits) + 8T'V
+            out["ctc_total_V%d" % V] = {"ms_per_1000_utt": ms, "algorithmic_gbs": by / (ms * 1e-3) / 1e9,
+                                        "frac_hbm": by / (ms * 1e-3) / 1e9 / peak,
+                                        "note": "logits -> log-softmax -> alpha/beta -> logit gradient; 12*T'*V bytes"}
+    return out
+
+
 def main():
     args = parse_args()
     pkg = importlib.import_module(PKG)
@@ -312,7 +392,7 @@ def main():
     config = {"workload": "%s: %s" % (args.workload, pkg.synthetic.WORKLOADS[args.workload]),
               "global_batch": per_gpu * world, "per_gpu_batch": per_gpu, "n_samples": args.n_samples,
               "frames": 1 + (args.n_samples - 400) // 160, "vocab": vocab,
-              "parallelism": "dp%d (utterance shards + 1 NCCL grad all-reduce)" % world,
+              "parallelism": "dp%d (utterance shards; per-layer NCCL grad all-reduce buckets overlapped with backward)" % world,
               "l2": "inputs+activations per step (>1 GB) exceed the 126 MB L2; no explicit flush",
               "gemm": "3xTF32 error-compensated cuBLAS (tcgen05) for the input-projection / weight-grad GEMMs; fp32-accurate"}
 
@@ -430,6 +510,33 @@ def main():
                "h2d_bytes_per_step": int(waves_pin.numel() * 4 + txt_pin.numel() * 8) * world,
                "d2h_bytes_per_step": 4 * world, "ms_per_step": ems / args.steps}
 
+    # ---- BASELINE configs[3] (CNN + BiLSTM 5x640, global batch 32 x N) measured in the same multi-GPU launch ----
+    also = None
+    if world > 1 and args.workload == "cfgB" and not args.batch and not args.no_also:
+        log("also: cfgD (BASELINE configs[3]), 32 utterances per GPU")
+        cfg_d = pkg.synthetic.load_config("cfgD")
+        vocab_d = cfg_d["data"]["corpus"]["vocab_size"]
+        bs_d = cfg_d["data"]["corpus"]["batch_size"]
+        st = pkg.trainer.TrainStep(cfg_d, vocab_d, device=dev, dp=dp, seed=0)
+        torch.distributed.broadcast(st.optimizer.buf.flat, 0)
+        wv, ln, tx = pkg.synthetic.make_batch(vocab_d, bs_d, args.n_samples, seed=2000 + rank)
+        nt = dp.all_reduce_scalar(float((tx != 0).sum()), dev)
+        tmx = torch.tensor([tx.shape[1]], device=dev)
+        torch.distributed.all_reduce(tmx, op=torch.distributed.ReduceOp.MAX)
+        if int(tmx) > tx.shape[1]:
+            tx = torch.nn.functional.pad(tx, (0, int(tmx) - tx.shape[1]))
+        wv, ln, tx = wv.to(dev), ln.to(dev), tx.to(dev)
+        fn_d = lambda: st(wv, ln, tx, global_batch=bs_d * world, global_tokens=nt)
+        for _ in range(3):
+            fn_d()
+        nd = max(3, min(args.steps, 10))
+        ms_d, loss_d, _ = timed(fn_d, nd)
+        also = {"cfgD": {"workload": "cfgD: " + pkg.synthetic.WORKLOADS["cfgD"], "value": bs_d * world * nd / (ms_d / 1e3),
+                         "unit": UNIT, "ms_per_step": ms_d / nd, "global_batch": bs_d * world, "steps": nd,
+                         "loss": loss_d}}
+        del st
+        torch.cuda.empty_cache()
+    dp.close()
     if rank != 0:
         return 0
     # ---- same-run parity at the benchmark's full size (CTC-loss rel-err is half of BASELINE.json's metric) ----
@@ -457,6 +564,15 @@ def main():
                 torch.cuda.empty_cache()
             log("parity %s: %s" % (w, json.dumps(parity[w])))
     peak, peak_src = peaks()
+    micro = None
+    if world == 1 and not args.no_micro:
+        log("micro-benchmark (BASELINE configs[4]: fbank + CTC on 1000 utterances of 2-30 s)")
+        try:
+            del step_fn
+        except NameError:
+            pass
+        torch.cuda.empty_cache()
+        micro = micro_bench(pkg, dev, peak)
     kernels = {}
     top, top_ms = None, -1.0
     for name, d in summary.items():
@@ -501,7 +617,7 @@ def main():
             "loss": loss, "gpu_launches": int(round(launches_per_step * args.steps)), "clocks": clocks, "e2e": e2e,
             "roofline": roofline, "kernels": kernels, "cuda_graph": bool(use_graph),
             "eager_ms_per_step": eager_ms / args.steps, "own_kernel_ms_per_step": own_ms,
-            "library_ms_per_step": eager_ms / args.steps - own_ms, "parity": parity,
+            "library_ms_per_step": eager_ms / args.steps - own_ms, "parity": parity, "also": also, "micro": micro,
             "note": "kernels/roofline come from the eager pass (CUDA events around each C-ABI launch); value and "
                     "e2e replay the same step as one CUDA graph when cuda_graph is true; gpu_launches counts this "
                     "library's kernels per step x steps"}

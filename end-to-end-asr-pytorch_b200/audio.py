@@ -141,7 +141,8 @@ class FbankFrontEnd(torch.nn.Module):
         lib = L.load()
         if self.window.device != wave.device:
             self.to(wave.device)
-        wave = wave.to(torch.float32).contiguous()
+        pcm16 = wave.dtype == torch.int16            # 16-bit PCM: converted on the fly by the kernel (sample / 32768)
+        wave = wave.contiguous() if pcm16 else wave.to(torch.float32).contiguous()
         B, N = wave.shape
         wl = torch.as_tensor(wave_len).to(device=wave.device, dtype=torch.int32).contiguous()
         if t_max is None:
@@ -149,8 +150,8 @@ class FbankFrontEnd(torch.nn.Module):
         fb = torch.empty((B, t_max, self.num_mel), device=wave.device, dtype=torch.float32)
         nfr = torch.empty(B, device=wave.device, dtype=torch.int32)
         # algorithmic bytes: read the waveform once, write the mel features once
-        with L.timed("fbank_fwd", 4 * int(wave.numel()) + 4 * B * t_max * self.num_mel):
-            L.check(lib.b200asr_fbank_fwd(
+        with L.timed("fbank_fwd", (2 if pcm16 else 4) * int(wave.numel()) + 4 * B * t_max * self.num_mel):
+            L.check((lib.b200asr_fbank_fwd_pcm16 if pcm16 else lib.b200asr_fbank_fwd)(
                 L.ptr(wave), L.ptr(wl), B, N, self.win_size, self.win_shift, self.n_fft, self.preemph,
                 int(self.remove_dc), L.ptr(self.window), self.num_mel, L.ptr(self.mel_start), L.ptr(self.mel_count),
                 L.ptr(self.mel_off), L.ptr(self.mel_w), int(self.mel_w.numel()), int(self.use_log), _FLT_EPS,

@@ -21,6 +21,7 @@ constexpr int FB_MAX_MELW = 2048;
 
 struct FbankParams {
     const float* wave;
+    const short* wave16;  // 16-bit PCM input (sample / 32768, like torchaudio.load's normalisation) when non-null
     const int* wave_len;
     int B, n_max;
     int win, shift;
@@ -117,7 +118,9 @@ __global__ void __launch_bounds__(FB_WARPS * 32) fbank_kernel(FbankParams p) {
             for (int i = lane; i < p.n_mel; i += 32) o[i] = 0.f;
             continue;
         }
-        const float* x = p.wave + (long long)b * p.n_max + (long long)f * p.shift;
+        const long long xoff = (long long)b * p.n_max + (long long)f * p.shift;
+        const float* x = p.wave + xoff;
+        const short* x16 = p.wave16 + xoff;
 
         // 1. load the frame, remove the DC offset (per frame mean)
         float v[FB_NFFT / 32];
@@ -125,7 +128,7 @@ __global__ void __launch_bounds__(FB_WARPS * 32) fbank_kernel(FbankParams p) {
 #pragma unroll
         for (int i = 0; i < FB_NFFT / 32; ++i) {
             const int j = lane + 32 * i;
-            v[i] = (j < p.win) ? __ldg(x + j) : 0.f;
+            v[i] = (j < p.win) ? (p.wave16 ? (float)__ldg(x16 + j) * (1.0f / 32768.0f) : __ldg(x + j)) : 0.f;
             sum += v[i];
         }
         float mean = 0.f;
@@ -311,11 +314,38 @@ __global__ void __launch_bounds__(DC_COLS* DC_ROWS) delta_norm_kernel(DeltaParam
 
 using namespace b200asr;
 
+static int fbank_run(const float* wave, const short* wave16, const int* wave_len, int B, int n_max, int win_size,
+                     int win_shift, int n_fft, float preemph, int remove_dc, const float* window, int n_mel,
+                     const int* mel_start, const int* mel_count, const int* mel_off, const float* mel_w,
+                     int mel_w_total, int use_log, float log_floor, float* fbank, int t_max, int* n_frames,
+                     b200asr_stream stream);
+
 extern "C" int b200asr_fbank_fwd(const float* wave, const int* wave_len, int B, int n_max, int win_size,
                                  int win_shift, int n_fft, float preemph, int remove_dc, const float* window,
                                  int n_mel, const int* mel_start, const int* mel_count, const int* mel_off,
                                  const float* mel_w, int mel_w_total, int use_log, float log_floor, float* fbank,
                                  int t_max, int* n_frames, b200asr_stream stream) {
+    B200_REQUIRE(wave, "fbank: null pointer");
+    return fbank_run(wave, nullptr, wave_len, B, n_max, win_size, win_shift, n_fft, preemph, remove_dc, window, n_mel,
+                     mel_start, mel_count, mel_off, mel_w, mel_w_total, use_log, log_floor, fbank, t_max, n_frames, stream);
+}
+
+extern "C" int b200asr_fbank_fwd_pcm16(const short* pcm, const int* wave_len, int B, int n_max, int win_size,
+                                       int win_shift, int n_fft, float preemph, int remove_dc, const float* window,
+                                       int n_mel, const int* mel_start, const int* mel_count, const int* mel_off,
+                                       const float* mel_w, int mel_w_total, int use_log, float log_floor,
+                                       float* fbank, int t_max, int* n_frames, b200asr_stream stream) {
+    B200_REQUIRE(pcm, "fbank: null pointer");
+    return fbank_run(reinterpret_cast<const float*>(pcm), pcm, wave_len, B, n_max, win_size, win_shift, n_fft, preemph,
+                     remove_dc, window, n_mel, mel_start, mel_count, mel_off, mel_w, mel_w_total, use_log, log_floor,
+                     fbank, t_max, n_frames, stream);
+}
+
+static int fbank_run(const float* wave, const short* wave16, const int* wave_len, int B, int n_max, int win_size,
+                     int win_shift, int n_fft, float preemph, int remove_dc, const float* window, int n_mel,
+                     const int* mel_start, const int* mel_count, const int* mel_off, const float* mel_w,
+                     int mel_w_total, int use_log, float log_floor, float* fbank, int t_max, int* n_frames,
+                     b200asr_stream stream) {
     B200_REQUIRE(n_fft == FB_NFFT, "fbank: only a 512-point padded window is supported (got %d)", n_fft);
     B200_REQUIRE(win_size >= 2 && win_size <= FB_NFFT, "fbank: window size %d not in [2,512]", win_size);
     B200_REQUIRE(win_shift > 0, "fbank: window shift must be > 0");
@@ -326,7 +356,7 @@ extern "C" int b200asr_fbank_fwd(const float* wave, const int* wave_len, int B, 
     B200_REQUIRE(wave && wave_len && window && mel_start && mel_count && mel_off && mel_w && fbank && n_frames,
                  "fbank: null pointer");
     FbankParams p;
-    p.wave = wave; p.wave_len = wave_len; p.B = B; p.n_max = n_max; p.win = win_size; p.shift = win_shift;
+    p.wave = wave; p.wave16 = wave16; p.wave_len = wave_len; p.B = B; p.n_max = n_max; p.win = win_size; p.shift = win_shift;
     p.preemph = preemph; p.remove_dc = remove_dc; p.window = window; p.n_mel = n_mel; p.mel_start = mel_start;
     p.mel_count = mel_count; p.mel_off = mel_off; p.mel_w = mel_w; p.mel_w_total = mel_w_total;
     p.log_floor = log_floor; p.use_log = use_log; p.out = fbank; p.t_max = t_max; p.n_frames = n_frames;

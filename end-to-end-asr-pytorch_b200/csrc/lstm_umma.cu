@@ -63,8 +63,12 @@ __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_re
 __device__ __forceinline__ void red_relaxed_add_u32(unsigned* p, unsigned v) {
     asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// Poll with RELAXED loads (an acquire load per iteration costs a gpu-scope fence each time) and acquire once at the end.
-__device__ __forceinline__ void ul_spin_until(const unsigned* ctr, unsigned target, int* err_flag) {
+// Consumer side of the exchange.  The producer orders its data stores before the flag with a gpu-scope fence; the
+// consumer polls the flag with RELAXED gpu-scope loads (served at the L2 coherence point) and then only ISSUES A BULK
+// COPY, whose reads are performed by the TMA unit at L2 - this thread never reads the data through its own L1, and the
+// copy is control-dependent on the polled value.  `strict` adds the formal acquire (one more L2 round trip) and the
+// generic->async proxy fence of the PTX memory model (~1.4k cycles per step together); both variants are tested.
+__device__ __forceinline__ void ul_spin_until(const unsigned* ctr, unsigned target, int* err_flag, bool strict = false) {
     const long long t0 = clock64();
     while (ld_relaxed_u32(ctr) < target) {
         if (clock64() - t0 > (1LL << 33)) {  // ~4 s: a peer died; abort instead of hanging the GPU
@@ -73,7 +77,10 @@ __device__ __forceinline__ void ul_spin_until(const unsigned* ctr, unsigned targ
             __trap();
         }
     }
-    (void)ld_acquire_u32(ctr);      // one acquire once the flag is up
+    if (strict) {
+        (void)ld_acquire_u32(ctr);
+        fence_proxy_async();
+    }
 }
 __device__ __forceinline__ void ul_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -190,10 +197,9 @@ __global__ void __launch_bounds__(32 * (UBP + 2 + UL_MAX_CTRL), 1) bilstm_fwd_um
                 // ago: every producer ran the same MMAs before it could publish)
                 if (step > 0) mbar_wait(mma_done, (uint32_t)((step - 1) & 1));
                 for (int i = 0, a = c; a < NA; a += NC, ++i) {
-                    ul_spin_until(ctr0 + a, (unsigned)(step + 1) * per_step[i], p.err_flag);
+                    ul_spin_until(ctr0 + a, (unsigned)(step + 1) * per_step[i], p.err_flag, (p.flags & 1) != 0);
                     if (a == 0) UL_TRACE(10);
                     if (a == NA - 1) UL_TRACE(15);
-                    if (!(p.flags & 1)) fence_proxy_async();
                     const uint8_t* src = xb + (size_t)(step & 1) * ((size_t)NA * UL_ATOM_A) + (size_t)a * UL_ATOM_A;
                     mbar_expect_tx(&full[a], UL_ATOM_A);
                     bulk_g2s(sA + (size_t)a * UL_ATOM_A, src, UL_ATOM_A, &full[a]);
@@ -290,11 +296,25 @@ __global__ void __launch_bounds__(32 * (UBP + 2 + UL_MAX_CTRL), 1) bilstm_fwd_um
             if (step + 1 < T) {
                 // publish h_step as element (A row, k = ug) of the next A operand, fp16 hi / lo
                 uint8_t* dstimg = xb + (size_t)(step & 1) * ((size_t)NA * UL_ATOM_A);
-                if (unit < UB) {
+                {
                     __half hi, lo;
                     split_f16(hq, hi, lo);
-                    *reinterpret_cast<__half*>(dstimg + pub_hi) = hi;
-                    *reinterpret_cast<__half*>(dstimg + pub_lo) = lo;
+                    if ((UB & 3) == 0) {
+                        // the four lanes of a unit quad hold k = ug .. ug+3 of the same A row: one 8-byte store each
+                        // for the hi and the lo row instead of four 2-byte ones
+                        uint32_t wh = __half_as_ushort(hi), wl = __half_as_ushort(lo);
+                        wh |= __shfl_down_sync(0xffffffffu, wh, 1) << 16;
+                        wl |= __shfl_down_sync(0xffffffffu, wl, 1) << 16;
+                        const uint32_t wh2 = __shfl_down_sync(0xffffffffu, wh, 2);
+                        const uint32_t wl2 = __shfl_down_sync(0xffffffffu, wl, 2);
+                        if (tq == 0 && unit < UB) {
+                            *reinterpret_cast<uint2*>(dstimg + pub_hi) = make_uint2(wh, wh2);
+                            *reinterpret_cast<uint2*>(dstimg + pub_lo) = make_uint2(wl, wl2);
+                        }
+                    } else if (unit < UB) {
+                        *reinterpret_cast<__half*>(dstimg + pub_hi) = hi;
+                        *reinterpret_cast<__half*>(dstimg + pub_lo) = lo;
+                    }
                 }
                 __syncwarp();
                 if (lane == 0) ul_arrive(pub);
@@ -436,9 +456,8 @@ __global__ void __launch_bounds__(32 * (ULB_EPI_WARPS + 2 + ULB_CTRL), 1) bilstm
             for (int step = 0; step + 1 < T; ++step) {
                 // my epilogue warps summed the inbox of `step` before they released the A tile of `step`
                 mbar_wait(&mma_done[NB - 1], (uint32_t)(step & 1));
-                ul_spin_until(ctr, (unsigned)(step + 1) * (unsigned)nub, p.err_flag);
+                ul_spin_until(ctr, (unsigned)(step + 1) * (unsigned)nub, p.err_flag, (p.flags & 1) != 0);
                 if (c == 0) UL_TRACE(10);
-                if (!(p.flags & 1)) fence_proxy_async();
                 const uint8_t* src = reinterpret_cast<const uint8_t*>(xb + (size_t)(step & 1) * xelems +
                                                                       (size_t)ub * nub * UL_BC * UB) + (size_t)c * chunk;
                 mbar_expect_tx(in_full, chunk);

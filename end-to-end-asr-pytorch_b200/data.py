@@ -8,6 +8,7 @@ process runs the fused front-end kernels on the GPU (Solver.fetch_data).  The ha
 count."""
 from functools import partial
 
+import numpy as np
 import torch
 from torch.nn.utils.rnn import pad_sequence
 from torch.utils.data import DataLoader, Dataset
@@ -21,7 +22,17 @@ HALF_BATCHSIZE_TEXT_LEN = 150
 
 
 def read_waveform(path):
-    """[N] fp32 in [-1, 1].  torchaudio / soundfile when usable (flac), else scipy (wav)."""
+    """[N] waveform of one file.  16-bit PCM wav files are returned AS int16 (half the pinned-host and H2D bytes; the
+    fbank kernel converts sample / 32768 on the fly - bit-identical to the fp32 path); anything else as fp32 in
+    [-1, 1] through soundfile (flac) / scipy."""
+    if str(path).lower().endswith(".wav"):
+        try:
+            from scipy.io import wavfile
+            _, data = wavfile.read(str(path))
+            if data.dtype == np.int16:
+                return torch.from_numpy(np.ascontiguousarray(data if data.ndim == 1 else data[:, 0]))
+        except Exception:
+            pass
     try:
         import soundfile as sf
         x, _ = sf.read(str(path), dtype="float32")
@@ -36,6 +47,8 @@ def collect_wave_batch(batch, num_frames, mode):
     if type(batch[0]) is not tuple:
         batch = batch[0]                                   # bucketed: [[(file, txt), ...]]
     waves = [read_waveform(b[0]) if not torch.is_tensor(b[0]) else b[0] for b in batch]
+    if any(w.dtype != torch.int16 for w in waves):         # mixed sources: everything as fp32 in [-1, 1]
+        waves = [w.to(torch.float32) / 32768.0 if w.dtype == torch.int16 else w for w in waves]
     if num_frames(len(waves[0])) > HALF_BATCHSIZE_AUDIO_LEN and mode == "train":
         batch, waves = batch[:len(batch) // 2], waves[:len(batch) // 2]
     names = [str(b[0]).split("/")[-1].split(".")[0] if not torch.is_tensor(b[0]) else "syn%d" % i

@@ -79,8 +79,84 @@ class DataParallel:
         if self.enabled:
             dist.barrier()
 
-    def attach(self, optimizer, n_buckets=1):
-        """Make `optimizer.step()` all-reduce the flat gradient before the norm/clip/update."""
-        if self.enabled:
-            optimizer.pre_reduce = lambda flat: self.all_reduce_(flat, n_buckets)
+    def attach(self, optimizer, model=None):
+        """Make the gradient exchange part of the step.
+
+        With `model`: the flat gradient buffer is cut into per-layer BUCKETS (every encoder layer; everything after the
+        encoder - CTC head, embedding, decoder, attention - is one bucket) and each bucket's NCCL all-reduce is launched
+        from a post-accumulate hook the moment the LAST gradient of that bucket has been written by autograd.  The
+        backward pass produces the decoder / attention / CTC-head gradients first and the encoder layers top-down, so
+        all but the first encoder layer's exchange overlaps the rest of the backward.
+        `optimizer.step()` launches whatever has not fired (parameters without gradients) and waits for all of them.
+        Without `model`: one all-reduce of the whole buffer inside `optimizer.step()`."""
+        if not self.enabled:
+            return optimizer
+        if model is None:
+            optimizer.pre_reduce = lambda flat: self.all_reduce_(flat, 1)
+            return optimizer
+        buf = optimizer.buf
+        index = {id(p): i for i, p in enumerate(buf.params)}
+        groups = {}
+        for name, p in model.named_parameters():
+            if id(p) not in index:
+                continue
+            parts = name.split(".")
+            key = ".".join(parts[:3]) if parts[0] == "encoder" else "head"
+            groups.setdefault(key, []).append(index[id(p)])
+        self._buckets = []
+        for key, ids in groups.items():
+            ids.sort()
+            lo = buf.offsets[ids[0]]
+            hi = buf.offsets[ids[-1]] + (buf.params[ids[-1]].numel() + 3) // 4 * 4
+            self._buckets.append({"key": key, "ids": set(ids), "lo": lo, "hi": hi, "seen": 0, "work": None})
+        # the buckets must tile the buffer (parameters are registered module by module)
+        self._buckets.sort(key=lambda b: b["lo"])
+        pos = 0
+        for b in self._buckets:
+            assert b["lo"] == pos, "gradient buckets are not contiguous: %s" % b["key"]
+            pos = b["hi"]
+        assert pos == buf.total
+        by_param = {}
+        for b in self._buckets:
+            for i in b["ids"]:
+                by_param[i] = b
+
+        def launch(b):
+            if b["work"] is None:
+                b["work"] = dist.all_reduce(buf.grad[b["lo"]:b["hi"]], op=dist.ReduceOp.SUM, async_op=True)
+
+        def make_hook(i):
+            b = by_param[i]
+
+            def hook(param):
+                # autograd may have replaced .grad by a fresh tensor: fold it back into the flat buffer first
+                o = buf.offsets[i]
+                if param.grad is not None and param.grad.data_ptr() != buf.grad.data_ptr() + 4 * o:
+                    view = buf.grad[o:o + param.numel()].view(param.shape)
+                    view.copy_(param.grad)
+                    param.grad = view
+                b["seen"] += 1
+                if b["seen"] == len(b["ids"]):
+                    launch(b)
+            return hook
+
+        for i, p in enumerate(buf.params):
+            p.register_post_accumulate_grad_hook(make_hook(i))
+
+        def finish(flat):
+            for b in self._buckets:
+                launch(b)
+            for b in self._buckets:
+                b["work"].wait()
+                b["work"], b["seen"] = None, 0
+            return flat
+
+        optimizer.pre_reduce = finish
         return optimizer
+
+    def close(self):
+        """Tear the communicator down (call before interpreter exit: NCCL warns - and can hang - otherwise)."""
+        if self.enabled and dist.is_initialized():
+            dist.barrier()
+            dist.destroy_process_group()
+            self.enabled = False

@@ -24,6 +24,8 @@ SIGNATURES = {
     "b200asr_device_sm_count": (c_int, []),
     "b200asr_fbank_fwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_float, c_int, _P, c_int, _P, _P, _P, _P,
                                   c_int, c_int, c_float, _P, c_int, _P, _P]),
+    "b200asr_fbank_fwd_pcm16": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_float, c_int, _P, c_int, _P, _P, _P, _P,
+                                  c_int, c_int, c_float, _P, c_int, _P, _P]),
     "b200asr_delta_cmvn_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "b200asr_delta_cmvn_fwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, _P, _P, c_size_t,
                                        _P]),

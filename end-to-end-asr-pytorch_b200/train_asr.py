@@ -51,7 +51,7 @@ class Solver(BaseSolver):
         self.optimizer = Optimizer([{"params": self.model.parameters()}], **self.config["hparas"])
         if self.dp.enabled:
             torch.distributed.broadcast(self.optimizer.buf.flat, 0)
-            self.dp.attach(self.optimizer)
+            self.dp.attach(self.optimizer, self.model)
         self.verbose(self.optimizer.create_msg())
         self.load_ckpt()
 

@@ -23,7 +23,7 @@ class TrainStep:
         self.model.train()
         self.ctc_loss = ops.CTCLoss(blank=0, zero_infinity=False)
         self.optimizer = Optimizer([{"params": self.model.parameters()}], **config["hparas"])
-        self.dp.attach(self.optimizer)
+        self.dp.attach(self.optimizer, self.model)
         self.step_id = 0
         self.last = {}
         self.graph = None

@@ -50,6 +50,13 @@ B200ASR_API int b200asr_fbank_fwd(const float* wave, const int* wave_len, int B,
                       const int* mel_start, const int* mel_count, const int* mel_off, const float* mel_w,
                       int mel_w_total, int use_log, float log_floor, float* fbank, int t_max, int* n_frames,
                       b200asr_stream stream);
+/* same kernel fed with 16-bit PCM [B, n_max] (what the corpus files hold, src/data.py:14-43 -> torchaudio.load): the
+ * int16 -> fp32 conversion (sample / 32768) happens on the fly, so the host-to-device copy is half as large */
+B200ASR_API int b200asr_fbank_fwd_pcm16(const short* pcm, const int* wave_len, int B, int n_max, int win_size, int win_shift,
+                      int n_fft, float preemph, int remove_dc, const float* window, int n_mel,
+                      const int* mel_start, const int* mel_count, const int* mel_off, const float* mel_w,
+                      int mel_w_total, int use_log, float log_floor, float* fbank, int t_max, int* n_frames,
+                      b200asr_stream stream);
 
 /* ---- K2+K3: delta / delta-delta + per-utterance CMVN + channel-major interleave ---------------------------
  * replaces src/audio.py:51-54,57-77 (Delta), :25-27 (CMVN, unbiased std, eps added to std), :85-89

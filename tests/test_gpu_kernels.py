@@ -36,6 +36,21 @@ def test_fbank_sample_wav_vs_reference_golden(pkg):
         assert float(np.max(np.abs(y[0].cpu().numpy() - g["sample_feat_d%d" % order]))) < 1e-3
 
 
+def test_fbank_pcm16_ingest_equals_fp32_path(pkg):
+    """16-bit PCM fed straight to the kernel (sample / 32768 on the fly) is bit-identical to the fp32 path, ragged batch."""
+    g = load_golden("frontend.npz")
+    pcm = torch.from_numpy(g["sample_pcm"])
+    batch = torch.zeros(2, pcm.numel(), dtype=torch.int16)
+    batch[0] = pcm
+    batch[1, :30000] = pcm[5000:35000]
+    lens = [pcm.numel(), 30000]
+    tr, _ = _frontend(pkg)
+    y16, n16 = tr.batch(batch.to(DEV), lens)
+    y32, n32 = tr.batch((batch.float() / 32768.0).to(DEV), lens)
+    assert torch.equal(n16, n32) and torch.equal(y16, y32)
+    assert float(np.max(np.abs(y16[0].cpu().numpy() - g["sample_feat_d2"]))) < 1e-3
+
+
 def test_fbank_ragged_batch_vs_reference_golden(pkg):
     g = load_golden("frontend.npz")
     waves = [g["syn%d_wave" % i] for i in (3, 2, 1, 0)]           # 16000, 7013, 4000, 400 samples
