@@ -14,7 +14,7 @@ from .lib import B200AsrError, load as load_library
 from .audio import create_transform, FbankFrontEnd
 from .asr import ASR, Encoder, Decoder, Attention
 from .ops import CTCLoss
-from . import audio, module, asr, optim, dist, synthetic, trainer, util, text, data, corpus, option, solver, train_asr, test_asr
+from . import audio, module, asr, optim, dist, synthetic, trainer, util, text, data, corpus, option, solver, train_asr, test_asr, ctc
 from .optim import Optimizer
 from .trainer import TrainStep
 

@@ -96,6 +96,17 @@ B200ASR_API int b200asr_ctc_grad(const float* log_probs, long long stride_b, lon
                      int L_max, int blank, const float* nll, const float* grad_scale, const float* upstream,
                      float* grad, void* workspace, size_t workspace_bytes, b200asr_stream stream);
 
+/* ---- CTC prefix scoring (joint CTC/attention beam search) ---------------------------------
+ * replaces CTCPrefixScore.cheap_compute (src/ctc.py:81-116), called from src/decode.py:129-131 once per hypothesis
+ * and step on the host.  Scores N hypotheses x C candidate tokens in one launch.
+ *   log_probs  [T, V]      CTC log-probs of the utterance          r_prev   [N, T, 2]  state of each prefix
+ *   last_char  [N], prefix_len [N] (int32)                         candidates [N, C] (int32, ids in [0,V))
+ *   psi [N, C] out: log P(prefix + c, ...)                         r_out [N, C, T, 2] out: state of prefix + c
+ * float32, the reference's finite log-zero (-1e8), numpy.logaddexp formula.  Out-of-range ids are the caller's bug. */
+B200ASR_API int b200asr_ctc_prefix_score(const float* log_probs, int T, int V, const float* r_prev, const int* last_char,
+                             const int* prefix_len, const int* candidates, int N, int C, int blank, int eos,
+                             float* psi, float* r_out, b200asr_stream stream);
+
 /* ---- K7/K8: persistent (Bi)LSTM recurrence -----------------------------------------------------------------
  * replaces the time loop inside torch.nn.LSTM as used by src/module.py:112-113,129-132 (one layer,
  * batch_first, zero initial state, run over the padded frames).  ndir = 1 or 2 (direction 1 = reverse time).

@@ -182,12 +182,40 @@ def golden_ctc():
     print("ctc_cases.npz", len(specs), "cases")
 
 
+def golden_prefix():
+    """CTCPrefixScore (src/ctc.py:12-116) driven like src/decode.py:93-131: empty prefix, then three extensions, each
+    with a candidate list that contains <eos> and the prefix's last token."""
+    from src.ctc import CTCPrefixScore                                          # the reference's numpy scorer
+    g = torch.Generator().manual_seed(77)
+    T, V = 37, 12
+    x = torch.randn(1, T, V, generator=g).log_softmax(-1)
+    sc = CTCPrefixScore(x)
+    out = {"x": x.numpy()}
+    r_prev = sc.init_state()
+    out["r_init"] = r_prev.copy()
+    prefix = []
+    for step, (cands, pick) in enumerate([([3, 1, 5, 7], 0), ([3, 5, 1, 9, 2], 1), ([5, 1, 4, 11], 0),
+                                          ([1, 5, 6, 10, 8, 3], 3)]):
+        psi, r = sc.cheap_compute(prefix, r_prev, cands)
+        out["s%d_prefix" % step] = np.asarray(prefix, np.int64)
+        out["s%d_cands" % step] = np.asarray(cands, np.int64)
+        out["s%d_rprev" % step] = r_prev.copy()
+        out["s%d_psi" % step] = psi.copy()
+        out["s%d_r" % step] = r.copy()
+        prefix = prefix + [cands[pick]]
+        r_prev = r[pick]
+    out["n_steps"] = np.int64(4)
+    np.savez_compressed(os.path.join(OUT, "ctc_prefix.npz"), **out)
+    print("ctc_prefix.npz")
+
+
 def main():
     ref_shim.install()
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)
     golden_frontend()
     golden_ctc()
+    golden_prefix()
     golden_model("ctc", 11, 3, 24, 8, 12, 5)
     golden_model("hybrid", 21, 3, 24, 8, 12, 5)
     golden_model("cnn", 31, 2, 40, 8, 12, 5)

@@ -284,3 +284,37 @@ def cross_entropy(logits, target, ignore_index=0):
     grad[rows, target] -= 1.0
     grad = grad * keep[:, None] / n
     return loss, grad
+
+
+# ------------------------------------------------------------------------------------------------ CTC prefix scoring
+def ctc_prefix_init(x, blank=0, logzero=-100000000.0):
+    """CTCPrefixScore.init_state (src/ctc.py:27-35): x [T,V] log-probs -> r [T,2] (non-blank, blank)."""
+    x = np.asarray(x, np.float32)
+    r = np.full((x.shape[0], 2), logzero, dtype=np.float32)
+    r[:, 1] = np.cumsum(x[:, blank].astype(np.float64)).astype(np.float32)
+    return r
+
+
+def ctc_prefix_cheap(x, g, r_prev, candidates, blank=0, eos=1, logzero=-100000000.0):
+    """CTCPrefixScore.cheap_compute (src/ctc.py:81-116), float32 like the reference: (psi [C], r [C,T,2])."""
+    x = np.asarray(x, np.float32)
+    r_prev = np.asarray(r_prev, np.float32)
+    T = x.shape[0]
+    cand = list(candidates)
+    C = len(cand)
+    r = np.full((T, 2, C), logzero, dtype=np.float32)
+    start = max(1, len(g))
+    if len(g) == 0:
+        r[0, 0, :] = x[0, cand]
+    psi = r[start - 1, 0, :].copy()
+    sum_prev = np.logaddexp(r_prev[:, 0], r_prev[:, 1])
+    phi = np.repeat(sum_prev[:, None], C, axis=1)
+    if len(g) > 0 and g[-1] in cand:
+        phi[:, cand.index(g[-1])] = r_prev[:, 1]
+    for t in range(start, T):
+        r[t, 0, :] = np.logaddexp(r[t - 1, 0, :], phi[t - 1]) + x[t, cand]
+        r[t, 1, :] = np.logaddexp(r[t - 1, 1, :], r[t - 1, 0, :]) + x[t, blank]
+        psi = np.logaddexp(psi, phi[t - 1] + x[t, cand])
+    if eos in cand:
+        psi[cand.index(eos)] = sum_prev[-1]
+    return psi, np.rollaxis(r, 2)

@@ -464,3 +464,21 @@ def test_grad_norm_and_adam_vs_torch(pkg):
     L.check(lib.b200asr_adam_step(L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), n, 1e-3, 0.9, 0.999, 1e-8, 0.0, 4,
                                   L.ptr(norm), 5.0, L.stream()))
     assert torch.isnan(norm).item() and torch.equal(p, before)
+
+
+def test_ctc_prefix_score_vs_reference_scorer(pkg):
+    """GPU CTCPrefixScore (one launch for all hypotheses x candidates) against the reference's numpy scorer."""
+    g = load_golden("ctc_prefix.npz")
+    x = torch.from_numpy(g["x"]).to(DEV)
+    sc = pkg.ctc.CTCPrefixScore(x)
+    assert rel_err(sc.init_state().cpu().numpy(), g["r_init"]) < 1e-6
+    n = int(g["n_steps"])
+    for s in range(n):                                        # the reference's one-hypothesis call
+        psi, r = sc.cheap_compute(list(g["s%d_prefix" % s]), g["s%d_rprev" % s], list(g["s%d_cands" % s]))
+        assert rel_err(psi, g["s%d_psi" % s]) < 1e-5
+        assert rel_err(r, g["s%d_r" % s]) < 1e-5
+    # batched: steps 0 and 2 have 4 candidates each -> two hypotheses in one launch
+    psi, r = sc.cheap_compute_batch([list(g["s0_prefix"]), list(g["s2_prefix"])],
+                                    [g["s0_rprev"], g["s2_rprev"]], [list(g["s0_cands"]), list(g["s2_cands"])])
+    assert rel_err(psi[0].cpu().numpy(), g["s0_psi"]) < 1e-5 and rel_err(psi[1].cpu().numpy(), g["s2_psi"]) < 1e-5
+    assert rel_err(r[1].cpu().numpy(), g["s2_r"]) < 1e-5

@@ -154,3 +154,14 @@ def test_cross_entropy_np():
     ref.backward()
     assert abs(loss - float(ref)) < 1e-10
     assert np.max(np.abs(grad - xt.grad.numpy())) < 1e-12
+
+
+def test_ctc_prefix_oracle_matches_reference_scorer():
+    """oracle_np.ctc_prefix_* against the reference's CTCPrefixScore run by oracle/make_golden.py (src/ctc.py:12-116)."""
+    g = load_golden("ctc_prefix.npz")
+    x = g["x"][0]
+    assert rel_err(onp.ctc_prefix_init(x), g["r_init"]) < 1e-6
+    for s in range(int(g["n_steps"])):
+        psi, r = onp.ctc_prefix_cheap(x, list(g["s%d_prefix" % s]), g["s%d_rprev" % s], list(g["s%d_cands" % s]))
+        assert rel_err(psi, g["s%d_psi" % s]) < 1e-6
+        assert rel_err(r, g["s%d_r" % s]) < 1e-6
