@@ -35,6 +35,7 @@
 #include "common.cuh"
 #include "lstm_umma.h"
 #include "../../include/b200asr.h"
+#include "../../include/b200asr_debug.h"
 
 namespace b200asr {
 

@@ -42,7 +42,33 @@ def gate_perm(H, device):
 # TF32/BF16.  GEMM_MODE "tf32x3" splits every operand into a TF32-representable high part and an fp32 residual
 # (b200asr_split_tf32) and sums three TF32 tensor-core GEMMs  A_lo.B_hi + A_hi.B_lo + A_hi.B_hi  in fp32
 # (relative error ~1e-6, i.e. fp32 class); "fp32" uses cuBLAS SGEMM (CUDA cores).
-GEMM_MODE = "tf32x3"
+# GEMM_MODE "umma" (default): the K-major products  x . W^T (+ bias)  and their input gradients  dY . W  run in this
+# library's own tcgen05 kernel (csrc/gemm.cu: raw fp32 tiles are the TF32 hi operands, residual tiles made on the fly
+# in shared memory, one TMEM accumulator, bias in the epilogue).  The weight gradients  dY^T . X  (contraction over the
+# B*T rows, both operands MN-major) stay plain library GEMMs in every mode.
+GEMM_MODE = os.environ.get("B200ASR_GEMM", "umma")
+
+
+def gemm_tn(a, w, bias=None, out=None, accumulate=False):
+    """out[M,N] (= or +=) a[M,K] @ w[N,K]^T (+ bias[N]) on the tensor cores at fp32-class accuracy (csrc/gemm.cu)."""
+    lib = L.load()
+    a, w = _f32c(a), _f32c(w)
+    M, K = a.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty((M, N), device=a.device, dtype=torch.float32)
+        accumulate = False
+    assert out.stride(1) == 1 and out.shape == (M, N)
+    b = _f32c(bias) if bias is not None else None
+    # algorithmic bytes: both operands and the result once; flops 2*M*N*K (x3 tensor-core products)
+    with L.timed("gemm3x_tn", 4 * (M * K + N * K + M * N * (2 if accumulate else 1))):
+        L.check(lib.b200asr_gemm3x_tn(L.ptr(a), L.ptr(w), L.ptr(b), L.ptr(out), M, N, K, out.stride(0),
+                                      int(bool(accumulate)), L.stream()), "gemm3x_tn")
+    return out
+
+
+def _use_umma(K):
+    return GEMM_MODE == "umma" and K % 4 == 0
 
 
 class Split:
@@ -117,7 +143,7 @@ def mm1(a, b, out=None, bias=None, accumulate=False):
 
 
 def _gemm_ops():
-    return (Split, mm3) if GEMM_MODE == "tf32x3" else (Plain, mm1)
+    return (Split, mm3) if GEMM_MODE in ("tf32x3", "umma") else (Plain, mm1)
 
 
 class BiLSTMFn(Function):
@@ -138,14 +164,18 @@ class BiLSTMFn(Function):
         H = params[1].shape[1]
         dev = x.device
         perm = gate_perm(H, dev)
-        xs = Op(x.view(B * T, I))
+        umma = _use_umma(I)
+        xs = None if umma else Op(x.view(B * T, I))
         gates = torch.empty((ndir, B, T, H, 4), device=dev, dtype=torch.float32)
         w_ih_p = []
         for d in range(ndir):
             w_ih, w_hh, b_ih, b_hh = params[4 * d:4 * d + 4]
             wp = w_ih.detach().index_select(0, perm)
             bp = (b_ih.detach() + b_hh.detach()).index_select(0, perm)
-            mm(xs, Op(wp).t(), out=gates[d].view(B * T, 4 * H), bias=bp)
+            if umma:
+                gemm_tn(x.view(B * T, I), wp, bias=bp, out=gates[d].view(B * T, 4 * H))
+            else:
+                mm(xs, Op(wp).t(), out=gates[d].view(B * T, 4 * H), bias=bp)
             w_ih_p.append(wp)
         del xs
         w_hh = torch.stack([_f32c(params[4 * d + 1].detach()) for d in range(ndir)]).contiguous()
@@ -191,7 +221,10 @@ class BiLSTMFn(Function):
         for d in range(ndir):
             dG = Op(gates[d].view(B * T, 4 * H))  # d(loss)/d(pre-activation), unit-major columns
             if need_dx:
-                mm(dG, Op(w_ih_p[d]), out=dx2, accumulate=(d > 0))
+                if _use_umma(4 * H):
+                    gemm_tn(gates[d].view(B * T, 4 * H), w_ih_p[d].t().contiguous(), out=dx2, accumulate=(d > 0))
+                else:
+                    mm(dG, Op(w_ih_p[d]), out=dx2, accumulate=(d > 0))
             dw_ih = torch.empty((4 * H, I), device=dev, dtype=torch.float32)
             dw_ih.index_copy_(0, perm, mm(dG.t(), xs))
             db = torch.empty((4 * H,), device=dev, dtype=torch.float32)
@@ -497,8 +530,11 @@ class Linear3xFn(Function):
         Op, mm = _gemm_ops()
         shp = x.shape
         x2 = _f32c(x).reshape(-1, shp[-1])
-        y = mm(Op(x2), Op(weight.detach()).t(), bias=bias.detach() if bias is not None else None,
-               out=torch.empty((x2.shape[0], weight.shape[0]), device=x.device, dtype=torch.float32))
+        if _use_umma(x2.shape[1]):
+            y = gemm_tn(x2, weight.detach(), bias=bias.detach() if bias is not None else None)
+        else:
+            y = mm(Op(x2), Op(weight.detach()).t(), bias=bias.detach() if bias is not None else None,
+                   out=torch.empty((x2.shape[0], weight.shape[0]), device=x.device, dtype=torch.float32))
         ctx.save_for_backward(x2, weight)
         ctx.shp = shp
         ctx.has_bias = bias is not None
@@ -508,9 +544,14 @@ class Linear3xFn(Function):
     def backward(ctx, gy):
         Op, mm = _gemm_ops()
         x2, weight = ctx.saved_tensors
-        g2 = Op(_f32c(gy).reshape(-1, weight.shape[0]))
-        dx = mm(g2, Op(weight.detach())).view(ctx.shp) if ctx.needs_input_grad[0] else None
-        dw = mm(g2.t(), Op(x2)) if ctx.needs_input_grad[1] else None
+        gy2 = _f32c(gy).reshape(-1, weight.shape[0])
+        dx = None
+        if ctx.needs_input_grad[0]:
+            if _use_umma(weight.shape[0]):
+                dx = gemm_tn(gy2, weight.detach().t().contiguous()).view(ctx.shp)
+            else:
+                dx = mm(Op(gy2), Op(weight.detach())).view(ctx.shp)
+        dw = mm(Op(gy2).t(), Op(x2)) if ctx.needs_input_grad[1] else None
         db = gy.reshape(-1, weight.shape[0]).sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
         return dx, dw, db
 

@@ -131,13 +131,6 @@ B200ASR_API int b200asr_bilstm_fwd(float* gates, const float* w_hh, float* cstat
 B200ASR_API int b200asr_bilstm_bwd(float* gates, const float* w_hh, const float* cstate, const float* dout, int B, int T,
                        int H, int ndir, void* workspace, size_t workspace_bytes, b200asr_stream stream);
 
-/* debug: when non-NULL, CTA 0 of the next b200asr_bilstm_fwd calls records clock64 stamps into [T][16] int64 */
-B200ASR_API void b200asr_debug_set_lstm_trace(long long* device_buffer);
-/* debug/test: 0 (default) = tcgen05 step GEMMs where the shape allows, else 3xTF32 mma.sync wherever the planner finds
- * a 16-row-tile decomposition, else fp32 FMA; 1 = always the packed-fp32-FMA step kernels; 3 = never tcgen05 (the
- * mma.sync generation).  All are fp32-class and parity-tested.
- * Upper bits (mode >> 4) are measurement switches used by tools/time_lstm.py and tools/trace_lstm.py. */
-B200ASR_API void b200asr_debug_set_lstm_mode(int mode);
 
 /* ---- K13: one LSTM cell step (decoder, src/asr.py:214-221) -------------------------------------------------
  * preact [B, 4H] gate-major (i,f,g,o) = x.W_ih^T + h.W_hh^T + biases; gates [B,4H] activated (stash).        */
@@ -187,6 +180,17 @@ B200ASR_API int b200asr_adadelta_step(float* param, const float* grad, float* sq
 B200ASR_API int b200asr_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
                       float beta1, float beta2, float eps, float weight_decay, int step, const float* grad_norm,
                       float max_norm, b200asr_stream stream);
+
+/* ---- K6 / K9 / K11: dense  x . W^T (+ bias)  on the tensor cores at fp32-class accuracy ------------------------------
+ * replaces the input projection inside nn.LSTM (src/module.py:112-113,131), the CTC head (src/asr.py:29,96) and the
+ * proj_k / char_trans / pj Linear layers (src/asr.py:177,220,242-243; src/module.py:123,155) and their input gradients.
+ *   C[M,N] (+)= A[M,K] . B[N,K]^T + bias[N]      A, B row-major with K contiguous (16-byte aligned, K % 4 == 0),
+ *   C row-major with leading dimension ldc >= N; bias may be NULL; accumulate != 0 adds to the existing C.
+ * tcgen05.mma kind::tf32 with error compensation: raw fp32 tiles are the TF32 hi operands (the tensor core truncates),
+ * the residual tiles are produced on the fly in shared memory; three products per K block into one TMEM accumulator. */
+B200ASR_API int b200asr_gemm3x_supported(int M, int N, int K);
+B200ASR_API int b200asr_gemm3x_tn(const float* A, const float* B, const float* bias, float* C, int M, int N, int K, int ldc,
+                      int accumulate, b200asr_stream stream);
 
 /* ---- K6 helper: split fp32 into a TF32-representable high part and the fp32 residual ---------------------------
  * hi = x rounded to TF32, lo = x - hi; used to run the input-projection (src/module.py:131, inside nn.LSTM) and the

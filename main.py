@@ -3,9 +3,12 @@
 """Same command line as the reference's main.py (/root/reference/main.py:13-47), driving the B200-native Solver.
     python main.py --config config/b200/cfgB_ctc_char.yaml [--njobs 0] [--seed 0] [--load ckpt]
     torchrun --nproc-per-node 8 --master-addr 127.0.0.1 main.py --config ...      (data parallel, one process per GPU)
---test runs greedy decoding (decode.beam_size 1); --cpu / --lm select reference workloads outside this hot path."""
+--test runs greedy decoding (decode.beam_size 1); --cpu hands the whole command line to the reference checkout
+(B200ASR_REFERENCE, default /root/reference) - this package has no CPU path; --lm is outside this hot path."""
 import argparse
 import importlib
+import os
+import sys
 
 import numpy as np
 import torch
@@ -36,8 +39,20 @@ def main():
     setattr(paras, "gpu", not paras.cpu)
     setattr(paras, "pin_memory", not paras.no_pin)
     setattr(paras, "verbose", not paras.no_msg)
-    if paras.cpu or paras.lm or paras.cudnn_ctc:
-        raise SystemExit("--cpu / --lm / --cudnn-ctc select reference paths outside the B200 hot path")
+    if paras.cpu:
+        # `--cpu` keeps routing to the REFERENCE implementation (the baseline run, main.py:30,45 there).
+        # It is not part of this repository: point B200ASR_REFERENCE at a checkout (default /root/reference).
+        ref = os.environ.get("B200ASR_REFERENCE", "/root/reference")
+        if not os.path.isfile(os.path.join(ref, "main.py")):
+            raise SystemExit("--cpu runs the reference's own CPU path, but no reference checkout was found at %s "
+                             "(set B200ASR_REFERENCE); this package has no CPU fallback" % ref)
+        import runpy
+        sys.path.insert(0, ref)
+        os.chdir(ref)
+        sys.argv[0] = os.path.join(ref, "main.py")
+        return runpy.run_path(sys.argv[0], run_name="__main__")
+    if paras.lm or paras.cudnn_ctc:
+        raise SystemExit("--lm / --cudnn-ctc select reference paths outside the B200 hot path")
     config = yaml.load(open(paras.config, "r"), Loader=yaml.FullLoader)
     np.random.seed(paras.seed)
     torch.manual_seed(paras.seed)

@@ -482,3 +482,26 @@ def test_ctc_prefix_score_vs_reference_scorer(pkg):
                                     [g["s0_rprev"], g["s2_rprev"]], [list(g["s0_cands"]), list(g["s2_cands"])])
     assert rel_err(psi[0].cpu().numpy(), g["s0_psi"]) < 1e-5 and rel_err(psi[1].cpu().numpy(), g["s2_psi"]) < 1e-5
     assert rel_err(r[1].cpu().numpy(), g["s2_r"]) < 1e-5
+
+
+@pytest.mark.parametrize("M,N,K,acc", [(3000, 2048, 1024, False), (300, 31, 120, False), (129, 257, 64, True),
+                                      (1000, 5000, 2048, False), (77, 300, 2048, True), (5, 8, 4, False)])
+def test_gemm3x_umma_is_fp32_class(pkg, M, N, K, acc):
+    """csrc/gemm.cu (tcgen05 kind::tf32, raw tiles as hi + on-the-fly residual tiles, TMEM accumulator) must be as
+    accurate as an fp32 SGEMM against an fp64 product - incl. M / N / K tails, bias, accumulate and ldc > N."""
+    torch.manual_seed(M + N)
+    a = torch.randn(M, K, device=DEV)
+    b = torch.randn(N, K, device=DEV) * 0.05
+    bias = torch.randn(N, device=DEV)
+    ldc = N + (4 if acc else 0)
+    buf = torch.randn(M, ldc, device=DEV)
+    out = buf[:, :N]
+    c0 = out.clone()
+    ref = a.double() @ b.double().t() + bias.double() + (c0.double() if acc else 0)
+    pkg.ops.gemm_tn(a, b, bias=bias, out=out, accumulate=acc)
+    sg = torch.addmm(bias, a, b.t()) + (c0 if acc else 0)                       # cuBLAS SGEMM (TF32 off)
+    e3 = scaled_err(out.cpu().numpy(), ref.cpu().numpy())
+    e1 = scaled_err(sg.cpu().numpy(), ref.cpu().numpy())
+    assert e3 < 3e-6 and e3 < 20 * max(e1, 1e-7), (e3, e1)
+    if acc:
+        assert torch.equal(buf[:, N:], buf[:, N:])                              # padding columns untouched (no NaN)

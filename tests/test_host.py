@@ -15,6 +15,9 @@ def test_library_exports_every_declared_symbol(pkg):
     ge.build()
     lib = pkg.load_library()
     header = open(os.path.join(ROOT, "include", "b200asr.h")).read()
+    public = set(re.findall(r"\b(b200asr_[a-z0-9_]+)\s*\(", header))
+    assert not any("debug" in n for n in public)          # test / measurement switches live in b200asr_debug.h
+    header += open(os.path.join(ROOT, "include", "b200asr_debug.h")).read()
     declared = set(re.findall(r"\b(b200asr_[a-z0-9_]+)\s*\(", header))
     assert len(declared) >= 20
     for name in declared:
