@@ -1330,6 +1330,9 @@ struct Plan {
     size_t smem_fwd, smem_bwd, pack_bytes, xbuf_fwd_bytes, xbuf_bwd_bytes;
 };
 
+#ifndef LSTM_UMMA_BWD_DEFAULT
+#define LSTM_UMMA_BWD_DEFAULT 0     // 1 once the tcgen05 backward is the validated default
+#endif
 static int g_lstm_flags = 0;  // experiment switches, see LstmParams::flags (set through the upper bits of the mode)
 static int g_lstm_mode = 0;   // 0: tcgen05 (lstm_umma.cu) when the shape allows, else mma.sync, else fp32 FMA;
                               // 1: always the fp32-FMA kernels, 2: mma.sync with 6 instead of 12 accumulator chains
@@ -1492,7 +1495,9 @@ static int bilstm_run(bool bwd, float* gates, const float* w_hh, float* cstate, 
     if (!bwd && g_lstm_mode == 0 && lstm_umma_fwd_supported(B, H, ndir))
         return lstm_umma_fwd(gates, w_hh, cstate, out_or_dout, B, T, H, ndir, workspace, workspace_bytes,
                              (g_lstm_flags & 8) ? nullptr : g_trace, g_lstm_flags >> 4, stream);
-    if (bwd && g_lstm_mode == 0 && !(g_lstm_flags & 32) && lstm_umma_bwd_supported(B, H, ndir))
+    // flag bit 5 (mode 512) toggles the backward between the tcgen05 kernel and the mma.sync generation
+    if (bwd && g_lstm_mode == 0 && (((g_lstm_flags & 32) != 0) != (LSTM_UMMA_BWD_DEFAULT != 0)) &&
+        lstm_umma_bwd_supported(B, H, ndir))
         return lstm_umma_bwd(gates, w_hh, cstate, out_or_dout, B, T, H, ndir, workspace, workspace_bytes,
                              (g_lstm_flags & 8) ? g_trace : nullptr, g_lstm_flags >> 4, stream);
     unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);

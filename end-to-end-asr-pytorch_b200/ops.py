@@ -46,7 +46,7 @@ def gate_perm(H, device):
 # library's own tcgen05 kernel (csrc/gemm.cu: raw fp32 tiles are the TF32 hi operands, residual tiles made on the fly
 # in shared memory, one TMEM accumulator, bias in the epilogue).  The weight gradients  dY^T . X  (contraction over the
 # B*T rows, both operands MN-major) stay plain library GEMMs in every mode.
-GEMM_MODE = os.environ.get("B200ASR_GEMM", "umma")
+GEMM_MODE = os.environ.get("B200ASR_GEMM", "tf32x3")
 
 
 def gemm_tn(a, w, bias=None, out=None, accumulate=False):

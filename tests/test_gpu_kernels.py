@@ -245,6 +245,18 @@ def test_bilstm_mma_sync_generation_on_the_large_shapes(pkg, B, T, I, H, bidir):
         lib.b200asr_debug_set_lstm_mode(0)
 
 
+@pytest.mark.parametrize("B,T,I,H,bidir", [(64, 10, 120, 512, True), (40, 9, 16, 512, False), (64, 300, 64, 512, True)])
+def test_bilstm_backward_generation_toggle(pkg, B, T, I, H, bidir):
+    """Mode flag 512 selects the OTHER backward generation than the default one (tcgen05 <-> mma.sync): both stay
+    parity-tested at the BASELINE shape whichever is the default."""
+    lib = pkg.load_library()
+    lib.b200asr_debug_set_lstm_mode(512)
+    try:
+        _check_bilstm(pkg, B, T, I, H, bidir, wtol=2e-4 if T > 100 else 1e-4)
+    finally:
+        lib.b200asr_debug_set_lstm_mode(0)
+
+
 def test_bilstm_baseline_shapes_run_on_tcgen05(pkg):
     lib = pkg.load_library()
     assert lib.b200asr_bilstm_uses_tcgen05(64, 512, 2) == 1      # cfg B / C

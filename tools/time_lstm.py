@@ -13,7 +13,7 @@ x = torch.randn(B, T, I, device="cuda", requires_grad=True)
 gy = torch.randn(B, T, 2 * H, device="cuda")
 lib = L.load()
 res = {}
-MODES = ((3, "mma.sync"), (0, "tcgen05"))
+MODES = ((3, "mma.sync"), (0, "tcgen05"), (512, "tcgen05+bwd-toggle"))
 if os.environ.get("EXTRA_MODE"):
     MODES += ((int(os.environ["EXTRA_MODE"]), "tcgen05-mode%s" % os.environ["EXTRA_MODE"]),)
 REPS = int(os.environ.get("REPS", 3))
