@@ -394,7 +394,9 @@ def main():
               "frames": 1 + (args.n_samples - 400) // 160, "vocab": vocab,
               "parallelism": "dp%d (utterance shards; per-layer NCCL grad all-reduce buckets overlapped with backward)" % world,
               "l2": "inputs+activations per step (>1 GB) exceed the 126 MB L2; no explicit flush",
-              "gemm": "3xTF32 error-compensated cuBLAS (tcgen05) for the input-projection / weight-grad GEMMs; fp32-accurate"}
+              "gemm": "K-major projections + input gradients: own tcgen05 3xTF32 kernel when B200ASR_GEMM=umma, else (and "
+                      "for the weight gradients) 3xTF32 error-compensated cuBLAS; fp32-accurate",
+              "lstm": "tcgen05 fp16 hi/lo 2x2-block split product (forward; backward per LSTM_UMMA_BWD_DEFAULT)"}
 
     # ------------------------------------------------------------------------------- reference (CPU) arm
     if args.impl == "reference":
@@ -587,30 +589,45 @@ def main():
     if top is not None:
         k = kernels[top]
         d = summary[top]
-        # DRAM traffic / algorithmic bytes measured with `ncu --set full` on the same kernels at (B=64, H=512, T=64),
-        # profiles/r01d_ncu_bilstm_*.txt: fwd (75.5+44.1) MB vs 109.1 MB, bwd (109.1+32.2) MB vs 218.1 MB
-        ratio = {"bilstm_fwd": 1.10, "bilstm_bwd": 0.65}.get(top)
+        # DRAM traffic per launch = (dram bytes / algorithmic bytes) measured with `ncu --set full` on the SHIPPED kernels
+        # (profiles/r02_ncu_traffic.json, written from this round's captures by tools/ncu_summary.py) x this launch's
+        # algorithmic bytes; null when no capture of that kernel is committed
+        ratios = {}
+        try:
+            with open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")) as f:
+                ratios = json.load(f)
+        except Exception:
+            pass
+        ratio = (ratios.get(top) or {}).get("dram_over_algorithmic")
         alg_per_launch = d["bytes"] / d["launches"]
         roofline = {"kernel": top, "bound": "hbm", "achieved": k["algorithmic_gbs"], "peak": peak, "unit": "GB/s",
                     "frac": k["frac_hbm"], "traffic": (ratio * alg_per_launch) if ratio else None,
                     "algorithmic_bytes_per_launch": alg_per_launch, "peak_source": peak_src,
-                    "note": "traffic = ncu dram bytes (profiles/r01c) scaled to this launch size. The LSTM step "
-                            "kernels are bound by the step GEMM issue rate + the per-step cross-SM exchange, not HBM (SURVEY.md 7): "
-                            "see binding_bound"}
+                    "traffic_source": (ratios.get(top) or {}).get("source"),
+                    "note": "The LSTM step kernels are bound by the per-step latency chain (gpu-scope fence -> flag -> "
+                            "poll -> bulk copy -> tcgen05 MMAs -> TMEM load -> pointwise), not by HBM (SURVEY.md 7, "
+                            "AI ~ 170 FLOP/B): see binding_bound"}
         if top.startswith("bilstm"):
-            # recurrent GEMM flops: 2*B*H*4H per step and direction (the backward's dG.W product is the same count).
-            # Peaks measured on this pool (profiles/r01d_micro_*): packed fp32 FMA 58 TFLOP/s (100 FMA/clk/SM);
-            # warp-level mma.sync tf32 278 TFLOP/s raw (478 MAC/clk/SM) = 92.7 TFLOP/s fp32-equivalent at 3 MMAs/MAC
             H = cfg["model"]["encoder"]["dim"][0]
             nbytes_per_step_dir = 24 * per_gpu * H
             steps_dirs = d["bytes"] / ((2 if top.endswith("bwd") else 1) * nbytes_per_step_dir)
             flops = steps_dirs * 2.0 * per_gpu * H * 4 * H
             tf = flops / (d["ms"] * 1e-3) / 1e12
-            on_tc = lib.b200asr_bilstm_uses_tensor_cores(per_gpu, H, 2) == 1
-            pk = 92.7 if on_tc else 58.0
-            roofline["binding_bound"] = {"bound": "mma_sync_3xtf32" if on_tc else "fp32_fma", "achieved": tf,
-                                         "peak": pk, "unit": "TFLOP/s (fp32-equivalent)", "frac": tf / pk,
-                                         "us_per_recurrent_step": 1e3 * d["ms"] / (steps_dirs / 2.0)}
+            us_step = 1e3 * d["ms"] / (steps_dirs / 2.0)
+            if lib.b200asr_bilstm_uses_tcgen05(per_gpu, H, 2) == 1:
+                # tensor floor of one step: H/16 MMAs (M 64, N 128) x 64 cycles, measured by tools/micro/umma_probe.cu
+                # (2192 cycles for 32 MMAs incl. completion latency) at the SM clock of this run
+                mhz = (clocks or {}).get("sm_mhz") or 1965.0
+                floor_us = (H / 16.0) * 68.5 / mhz
+                roofline["binding_bound"] = {"bound": "tcgen05 step latency chain", "us_per_recurrent_step": us_step,
+                                             "tensor_floor_us_per_step": floor_us, "frac": floor_us / us_step,
+                                             "achieved": tf, "unit": "TFLOP/s (fp32-equivalent recurrent flops)"}
+            else:
+                on_tc = lib.b200asr_bilstm_uses_tensor_cores(per_gpu, H, 2) == 1
+                pk = 92.7 if on_tc else 58.0
+                roofline["binding_bound"] = {"bound": "mma_sync_3xtf32" if on_tc else "fp32_fma", "achieved": tf,
+                                             "peak": pk, "unit": "TFLOP/s (fp32-equivalent)", "frac": tf / pk,
+                                             "us_per_recurrent_step": us_step}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,

@@ -188,12 +188,13 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// row-major fp32 matrix [rows, K] -> tensor map with boxes of 32 (K) x box_rows, 128-byte swizzle
-int make_map(CUtensorMap* map, const float* ptr, int rows, int K, int box_rows) {
+// row-major fp32 matrix [rows, K] with row pitch ld (floats; rows may overlap when ld < K: the im2col view of a
+// strided convolution) -> tensor map with boxes of 32 (K) x box_rows, 128-byte swizzle
+int make_map(CUtensorMap* map, const float* ptr, int rows, int K, int ld, int box_rows) {
     EncodeTiledFn enc = encode_fn();
     B200_REQUIRE(enc != nullptr, "gemm: cuTensorMapEncodeTiled is not available from this driver");
     const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)K * sizeof(float)};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
     const cuuint32_t box[2] = {(cuuint32_t)G_BK, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
@@ -215,16 +216,22 @@ extern "C" int b200asr_gemm3x_supported(int M, int N, int K) {
 
 extern "C" int b200asr_gemm3x_tn(const float* A, const float* B, const float* bias, float* C, int M, int N, int K,
                                  int ldc, int accumulate, b200asr_stream stream) {
+    return b200asr_gemm3x_tn_ld(A, K, B, bias, C, M, N, K, ldc, accumulate, stream);
+}
+
+extern "C" int b200asr_gemm3x_tn_ld(const float* A, int lda, const float* B, const float* bias, float* C, int M, int N,
+                                    int K, int ldc, int accumulate, b200asr_stream stream) {
     B200_REQUIRE(A && B && C, "gemm3x_tn: null pointer");
+    B200_REQUIRE(lda > 0 && (lda % 4) == 0, "gemm3x_tn: lda %d must be a positive multiple of 4", lda);
     B200_REQUIRE(b200asr_gemm3x_supported(M, N, K), "gemm3x_tn: unsupported sizes M=%d N=%d K=%d (K %% 4 must be 0)", M,
                  N, K);
     B200_REQUIRE(ldc >= N, "gemm3x_tn: ldc %d < N %d", ldc, N);
     B200_REQUIRE(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) == 0,
                  "gemm3x_tn: operands must be 16-byte aligned");
     CUtensorMap ma, mb;
-    int rc = make_map(&ma, A, M, K, G_BM);
+    int rc = make_map(&ma, A, M, K, lda, G_BM);
     if (rc != B200_OK) return rc;
-    rc = make_map(&mb, B, N, K, G_BN);
+    rc = make_map(&mb, B, N, K, K, G_BN);
     if (rc != B200_OK) return rc;
     const size_t smem = (size_t)G_STAGES * G_STAGE_BYTES + 256;
     B200_CUDA(cudaFuncSetAttribute(gemm3x_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

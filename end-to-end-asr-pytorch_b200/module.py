@@ -66,8 +66,9 @@ class CNNExtractor(nn.Module):
 
     def forward(self, feature, feat_len):
         feat_len = feat_len // 4
-        feature = self.extractor(feature.transpose(1, 2)).transpose(1, 2)
-        return feature, feat_len
+        for conv in self.extractor:             # tensor-core GEMM over the in-place im2col view (ops.Conv1dK4S2Fn)
+            feature = ops.conv1d_k4s2p1(feature, conv)
+        return feature.contiguous(), feat_len
 
 
 class RNNLayer(nn.Module):

@@ -71,6 +71,79 @@ def _use_umma(K):
     return GEMM_MODE == "umma" and K % 4 == 0
 
 
+def gemm_tn_ld(a_base, lda, M, K, w, bias=None):
+    """Like gemm_tn but A is given as (base tensor, row pitch lda in floats, M rows of K floats): rows may overlap."""
+    lib = L.load()
+    w = _f32c(w)
+    N = w.shape[0]
+    out = torch.empty((M, N), device=w.device, dtype=torch.float32)
+    b = _f32c(bias) if bias is not None else None
+    with L.timed("gemm3x_tn", 4 * (M * lda + N * K + M * N)):
+        L.check(lib.b200asr_gemm3x_tn_ld(L.ptr(a_base), lda, L.ptr(w), L.ptr(b), L.ptr(out), M, N, K, N, 0, L.stream()),
+                "gemm3x_tn_ld")
+    return out
+
+
+class Conv1dK4S2Fn(Function):
+    """Conv1d(C -> O, kernel 4, stride 2, padding 1) over [B, T, C] (CNNExtractor, src/module.py:75-78) as ONE
+    tensor-core GEMM: with one zero row in front of every utterance, output frame t reads the 4*C CONTIGUOUS floats that
+    start at padded row 2t, so the im2col matrix is just the padded buffer viewed with row pitch 2*C (overlapping rows)
+    and the TMA tensor map reads it in place.  Input gradient = GEMM + an overlap-add of the two window halves."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x = _f32c(x)
+        B, T, C = x.shape
+        O = weight.shape[0]
+        Tout = T // 2
+        Tp = 2 * (Tout + 1)                                   # padded rows per utterance (even)
+        xp = torch.zeros((B, Tp, C), device=x.device, dtype=torch.float32)
+        xp[:, 1:T + 1] = x
+        wm = weight.detach().permute(0, 2, 1).reshape(O, 4 * C).contiguous()    # K index = tap * C + channel
+        M = B * (Tp // 2) - 1                                 # the last row of the view would read past the buffer
+        yf = torch.empty((B * (Tp // 2), O), device=x.device, dtype=torch.float32)
+        yf[M:] = 0
+        yf[:M] = gemm_tn_ld(xp, 2 * C, M, 4 * C, wm, bias.detach() if bias is not None else None)
+        ctx.save_for_backward(xp, wm)
+        ctx.dims = (B, T, C, O, Tout, Tp, M)
+        ctx.has_bias = bias is not None
+        return yf.view(B, Tp // 2, O)[:, :Tout]
+
+    @staticmethod
+    def backward(ctx, dy):
+        xp, wm = ctx.saved_tensors
+        B, T, C, O, Tout, Tp, M = ctx.dims
+        half = Tp // 2
+        dyf = torch.zeros((B, half, O), device=dy.device, dtype=torch.float32)
+        dyf[:, :Tout] = dy
+        dy2 = dyf.view(B * half, O)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dcols = gemm_tn(dy2, wm.t().contiguous()).view(B, half, 2, 2 * C)      # [.., 0]: rows 2t,2t+1  [.., 1]: 2t+2,2t+3
+            dxp = torch.zeros((B, half + 1, 2 * C), device=dy.device, dtype=torch.float32)
+            dxp[:, :half] += dcols[:, :, 0]
+            dxp[:, 1:] += dcols[:, :, 1]
+            dx = dxp.view(B, Tp + 2, C)[:, 1:T + 1].contiguous()
+        dw = db = None
+        if ctx.needs_input_grad[1]:
+            cols = xp.view(-1).as_strided((M, 4 * C), (2 * C, 1)).contiguous()
+            Op, mm = _gemm_ops()
+            dwm = mm(Op(dy2[:M]).t(), Op(cols))                                      # [O, 4C]
+            dw = dwm.view(O, 4, C).permute(0, 2, 1).contiguous()
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy.reshape(-1, O).sum(0)
+        return dx, dw, db
+
+
+def conv1d_k4s2p1(x, conv):
+    """[B,T,C] -> [B,T//2,O] through the tensor-core GEMM when available, else the library convolution."""
+    C = x.shape[-1]
+    if (x.is_cuda and _use_umma(4 * C) and conv.kernel_size == (4,) and conv.stride == (2,) and conv.padding == (1,)
+            and x.shape[1] >= 2 and (2 * C) % 4 == 0):
+        return Conv1dK4S2Fn.apply(x, conv.weight, conv.bias)
+    return conv(x.transpose(1, 2)).transpose(1, 2)
+
+
 class Split:
     """fp32 matrix as (hi, lo) with hi exactly representable in TF32."""
 

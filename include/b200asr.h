@@ -191,6 +191,11 @@ B200ASR_API int b200asr_adam_step(float* param, const float* grad, float* exp_av
 B200ASR_API int b200asr_gemm3x_supported(int M, int N, int K);
 B200ASR_API int b200asr_gemm3x_tn(const float* A, const float* B, const float* bias, float* C, int M, int N, int K, int ldc,
                       int accumulate, b200asr_stream stream);
+/* same with an explicit row pitch lda (floats, multiple of 4) of A.  lda < K is allowed: overlapping rows are the im2col
+ * view of a strided 1-D convolution over a [time, channels] buffer (CNNExtractor, src/module.py:75-78: kernel 4, stride 2
+ * -> K = 4*C, lda = 2*C), so the convolution runs in this kernel without materialising the windows. */
+B200ASR_API int b200asr_gemm3x_tn_ld(const float* A, int lda, const float* B, const float* bias, float* C, int M, int N, int K,
+                         int ldc, int accumulate, b200asr_stream stream);
 
 /* ---- K6 helper: split fp32 into a TF32-representable high part and the fp32 residual ---------------------------
  * hi = x rounded to TF32, lo = x - hi; used to run the input-projection (src/module.py:131, inside nn.LSTM) and the

@@ -8,6 +8,7 @@ torch.manual_seed(0)
 ref = torch.nn.LSTM(I, H, bidirectional=True, batch_first=True)
 params = [p.detach().cuda().requires_grad_(True) for p in ref.parameters()]
 x = torch.randn(B, T, I, device="cuda", requires_grad=True)
+pkg.lib.load().b200asr_debug_set_lstm_mode(int(os.environ.get("MODE", "0")))
 for it in range(3):
     y = pkg.ops.bilstm(x, params, 2)
     y.backward(torch.ones_like(y))
