@@ -517,3 +517,56 @@ def test_gemm3x_umma_is_fp32_class(pkg, M, N, K, acc):
     assert e3 < 3e-6 and e3 < 20 * max(e1, 1e-7), (e3, e1)
     if acc:
         assert torch.equal(buf[:, N:], buf[:, N:])                              # padding columns untouched (no NaN)
+
+
+@pytest.mark.parametrize("B,T,C,O", [(3, 41, 120, 640), (2, 10, 640, 640)])
+def test_conv1d_k4s2_through_the_gemm_kernel(pkg, B, T, C, O):
+    """CNNExtractor's Conv1d(k=4, s=2, p=1) as one tcgen05 GEMM over the in-place im2col view (overlapping rows,
+    lda = 2C < K = 4C) against the library convolution in fp64: output, input gradient, weight / bias gradients."""
+    torch.manual_seed(C + T)
+    conv = torch.nn.Conv1d(C, O, 4, stride=2, padding=1)
+    x = torch.randn(B, T, C)
+    xr = x.double().requires_grad_(True)
+    ref = torch.nn.functional.conv1d(xr.transpose(1, 2), conv.weight.detach().double(), conv.bias.detach().double(),
+                                     stride=2, padding=1).transpose(1, 2)
+    gy = torch.randn(B, T // 2, O)
+    ref.backward(gy.double())
+    cd = torch.nn.Conv1d(C, O, 4, stride=2, padding=1).to(DEV)
+    cd.load_state_dict(conv.state_dict())
+    xd = x.to(DEV).requires_grad_(True)
+    mode, pkg.ops.GEMM_MODE = pkg.ops.GEMM_MODE, "umma"
+    try:
+        y = pkg.ops.conv1d_k4s2p1(xd, cd)
+        assert y.shape == ref.shape and scaled_err(y.detach().cpu().numpy(), ref.detach().numpy()) < 1e-5
+        y.backward(gy.to(DEV))
+    finally:
+        pkg.ops.GEMM_MODE = mode
+    assert scaled_err(xd.grad.cpu().numpy(), xr.grad.numpy()) < 1e-5
+    wref = torch.autograd.grad(torch.nn.functional.conv1d(x.double().transpose(1, 2), conv.weight.double(),
+                                                          conv.bias.double(), stride=2, padding=1).transpose(1, 2),
+                               [conv.weight, conv.bias], gy.double())
+    assert scaled_err(cd.weight.grad.cpu().numpy(), wref[0].numpy()) < 1e-5
+    assert scaled_err(cd.bias.grad.cpu().numpy(), wref[1].numpy()) < 1e-5
+
+
+def test_linear_and_lstm_projection_through_the_gemm_kernel(pkg):
+    """GEMM_MODE 'umma': Linear3xFn and the BiLSTM input projection / input gradient through csrc/gemm.cu."""
+    mode, pkg.ops.GEMM_MODE = pkg.ops.GEMM_MODE, "umma"
+    try:
+        _check_bilstm(pkg, 8, 13, 40, 320, True)
+        torch.manual_seed(3)
+        lin = torch.nn.Linear(256, 1000)
+        x = torch.randn(4, 70, 256)
+        xr = x.double().requires_grad_(True)
+        ref = torch.nn.functional.linear(xr, lin.weight.detach().double(), lin.bias.detach().double())
+        g = torch.randn(4, 70, 1000)
+        ref.backward(g.double())
+        lin_d = torch.nn.Linear(256, 1000).to(DEV)
+        lin_d.load_state_dict(lin.state_dict())
+        xd = x.to(DEV).requires_grad_(True)
+        y = pkg.ops.Linear3xFn.apply(xd, lin_d.weight, lin_d.bias)
+        assert scaled_err(y.detach().cpu().numpy(), ref.detach().numpy()) < 1e-5
+        y.backward(g.to(DEV))
+        assert scaled_err(xd.grad.cpu().numpy(), xr.grad.numpy()) < 1e-5
+    finally:
+        pkg.ops.GEMM_MODE = mode
