@@ -1,7 +1,14 @@
-// K6 / K9 / K11: the dense "x . W^T (+ bias)" contractions of the step on the 5th-generation tensor cores, fp32 in and
-// out, fp32-class accuracy ("3xTF32"):   C[M,N] (+)= A[M,K] . B[N,K]^T + bias[N]     (both operands K-major)
+// K6 / K9 / K11: the dense contractions of the step on the 5th-generation tensor cores, fp32 in and out, fp32-class
+// accuracy ("3xTF32").  ONE kernel template serves the three operand arrangements of a layer y = x . W^T + b:
+//   tn :  C[M,N] (+)= A[M,K] . B[N,K]^T + bias      forward  (x . W^T): both operands K-major (K contiguous)
+//   nn :  C[M,N] (+)= A[M,K] . B[K,N]               input gradient (dY . W): B is MN-major (N contiguous)
+//   nt :  C[M,N] (+)= sum_r A[r,M]^T . B[r,N]       weight gradient (dY^T . X): the contraction runs over the B*T rows,
+//                                                    both operands MN-major; rows are addressed as (batch, time) so
+//                                                    that B can be read SHIFTED by one time step (dW_hh = dG^T . h_prev
+//                                                    without materialising h_prev: the row before the first / after the
+//                                                    last step of an utterance is out of bounds = zero-filled by TMA)
 //   reference call sites: the input projection inside nn.LSTM (src/module.py:112-113,131), the CTC head (src/asr.py:29,
-//   96), proj_k / char_trans / pj (src/asr.py:242-243,177,220; src/module.py:123,155) and their input gradients.
+//   96), proj_k / char_trans / pj (src/asr.py:242-243,177,220; src/module.py:123,155) and their autograd backward.
 //
 // tcgen05.mma kind::tf32 reads fp32 bit patterns from shared memory and IGNORES the low 13 mantissa bits (truncation,
 // verified on hardware by tools/micro/umma_probe.cu), so the raw fp32 tile IS the TF32 "hi" operand - no split pass,
@@ -9,10 +16,19 @@
 // shared-memory layout as the raw tile, so making it is a purely elementwise pass by 8 "splitter" warps.  Per 32-wide
 // K block the single-thread issuer then accumulates   A.B + A_lo.B + A.B_lo   in one TMEM accumulator (fp32).
 //
-// One 128 x 256 tile per CTA.  Warp roles: 0 = TMA producer (cp.async.bulk.tensor, 128-byte swizzle, out-of-bounds
-// rows / K tail zero-filled by the hardware), 1 = MMA issue + TMEM allocation, 2..9 = splitters; 2..5 also drain the
-// accumulator (tcgen05.ld 32x32b -> + bias [-> + C] -> 128-bit stores).  Two shared-memory stages of 96 KB
-// (A 16 + B 32 raw, the same again for the residuals).
+// One 128 x 256 tile per CTA (x split-K slices when the tile grid alone cannot fill the SMs: partial tiles go to a
+// workspace and a second small kernel sums them in a fixed order - deterministic).  Warp roles: 0 = TMA producer
+// (cp.async.bulk.tensor, 128-byte swizzle, out-of-bounds rows / K tail zero-filled by the hardware), 1 = MMA issue +
+// TMEM allocation, 2..9 = splitters, which also own the second accumulation level: the TMEM chain is cut every 4 K
+// blocks, the partial tile is drained (tcgen05.ld 32x32b) into 128 fp32 registers per thread and summed there, while
+// the tensor core fills the other of two TMEM buffers; the epilogue (+ bias [+ C], 128-bit stores) runs from those
+// registers.  Two shared-memory stages of 96 KB (A 16 + B 32 raw, the same again for the residuals).
+//
+// Shared-memory images.  K-major operand, R rows: R consecutive 128-byte rows (32 k each), 128-byte swizzle; one MMA
+// (8 k) advances the descriptor start by 32 bytes.  MN-major operand, R columns: R/32 boxes of [32 k][32 columns] =
+// 4096 bytes each (what a TMA box {32 columns, 32 rows} with SWIZZLE_128B produces); canonical UMMA layout
+// ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units with LBO = 4096 B (next 32 columns) and SBO = 1024 B (next 8 k);
+// one MMA (8 k) advances the start by 1024 bytes.
 #include <cuda.h>
 #include "common.cuh"
 #include "umma.cuh"
@@ -28,6 +44,20 @@ constexpr int G_B_BYTES = G_BN * G_BK * 4;      // 32 KB
 constexpr int G_STAGE_BYTES = 2 * (G_A_BYTES + G_B_BYTES);
 constexpr int G_SPLIT_WARPS = 8;
 constexpr int G_THREADS = 32 * (2 + G_SPLIT_WARPS);
+constexpr int G_BOX = 32 * G_BK * 4;            // one MN-major box: 32 columns x 32 k
+constexpr int G_MAX_SPLIT = 32;
+constexpr int G_CH = 4;                      // K blocks per TMEM accumulation chunk (see the drain warps)
+
+struct GemmArgs {
+    const float* bias;
+    float* C;
+    float* partial;        // [nsplit][M][N] when nsplit > 1
+    int M, N, ldc, accumulate, perm;
+    int KB;                // K blocks (of 32) in total
+    int kb_per_split;
+    int kbt;               // K blocks per batch entry (MN-major operands walk (batch, time)); KB = batches * kbt
+    int a_shift, b_shift;  // time shift of the rows read from A / B (nt form)
+};
 
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
     asm volatile(
@@ -36,27 +66,56 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
         : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                            uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::
+            "r"(smem_u32(smem_dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+        : "memory");
+}
 __device__ __forceinline__ void g_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ float tf32_residual(float x) {
     return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u);
 }
+// MN-major, SWIZZLE_128B matrix descriptor: leading byte offset = distance between 32-column boxes, stride byte offset =
+// distance between groups of 8 k.
+__device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t smem_addr) {
+    uint64_t d = static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>(G_BOX >> 4) << 16;
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
 
+template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(G_THREADS, 1)
-gemm3x_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                 const float* __restrict__ bias, float* __restrict__ C, int M, int N, int K, int ldc, int accumulate) {
+gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmArgs g) {
     extern __shared__ __align__(1024) uint8_t smem[];
     // stage s: [A raw | B raw | A lo | B lo]
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + G_STAGES * G_STAGE_BYTES);   // TMA landed
     uint64_t* split = full + G_STAGES;                                               // residual tiles written
     uint64_t* empty = split + G_STAGES;                                              // MMAs of the stage retired
-    uint64_t* acc_done = empty + G_STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
+    uint64_t* acc_full = empty + G_STAGES;                                           // [2] a chunk's MMAs retired
+    uint64_t* acc_free = acc_full + 2;                                               // [2] the chunk has been drained
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m0 = blockIdx.y * G_BM, n0 = blockIdx.x * G_BN;
-    const int KB = (K + G_BK - 1) / G_BK;
+    const int M = g.M, N = g.N;
+    const int kb0 = blockIdx.z * g.kb_per_split;
+    const int kb1 = min(g.KB, kb0 + g.kb_per_split);
+    const int nkb = kb1 - kb0;                                   // >= 1 by construction of the grid
+    const int nchunks = (nkb + G_CH - 1) / G_CH;
+    const int nvalid = min(G_BN, N - n0);
+    const int n_instr = (nvalid + 15) & ~15;                     // MMA N (multiple of 16, <= 256)
+    const int a_boxes = min(G_BM / 32, (M - m0 + 31) / 32);      // MN-major: 32-column boxes that hold real data
+    const int b_boxes = (nvalid + 31) / 32;
+    const uint32_t a_bytes = A_MN ? (uint32_t)a_boxes * G_BOX : (uint32_t)G_A_BYTES;
+    const uint32_t b_bytes = B_MN ? (uint32_t)b_boxes * G_BOX : (uint32_t)G_B_BYTES;
 
     if (tid == 0) {
         for (int s = 0; s < G_STAGES; ++s) {
@@ -64,10 +123,13 @@ gemm3x_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             mbar_init(&split[s], G_SPLIT_WARPS);
             mbar_init(&empty[s], 1);
         }
-        mbar_init(acc_done, 1);
+        for (int j = 0; j < 2; ++j) {
+            mbar_init(&acc_full[j], 1);
+            mbar_init(&acc_free[j], G_SPLIT_WARPS);
+        }
         mbar_fence_init();
     }
-    if (warp == 1) umma::tmem_alloc(tmem_slot, 256);
+    if (warp == 1) umma::tmem_alloc(tmem_slot, 512);
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
@@ -75,80 +137,131 @@ gemm3x_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int kb = 0; kb < KB; ++kb) {
-                const int s = kb % G_STAGES;
-                if (kb >= G_STAGES) mbar_wait(&empty[s], (uint32_t)(((kb / G_STAGES) - 1) & 1));
+            for (int i = 0; i < nkb; ++i) {
+                const int kb = kb0 + i;
+                const int s = i % G_STAGES;
+                if (i >= G_STAGES) mbar_wait(&empty[s], (uint32_t)(((i / G_STAGES) - 1) & 1));
                 uint8_t* st = smem + s * G_STAGE_BYTES;
-                mbar_expect_tx(&full[s], G_A_BYTES + G_B_BYTES);
-                tma_load_2d(st, &map_a, kb * G_BK, m0, &full[s]);
-                tma_load_2d(st + G_A_BYTES, &map_b, kb * G_BK, n0, &full[s]);
+                mbar_expect_tx(&full[s], a_bytes + b_bytes);
+                const int bt = kb / g.kbt, t0 = (kb - bt * g.kbt) * G_BK;
+                if (A_MN) {
+                    for (int j = 0; j < a_boxes; ++j)
+                        tma_load_3d(st + j * G_BOX, &map_a, m0 + 32 * j, t0 + g.a_shift, bt, &full[s]);
+                } else {
+                    tma_load_2d(st, &map_a, kb * G_BK, m0, &full[s]);
+                }
+                if (B_MN) {
+                    for (int j = 0; j < b_boxes; ++j)
+                        tma_load_3d(st + G_A_BYTES + j * G_BOX, &map_b, n0 + 32 * j, t0 + g.b_shift, bt, &full[s]);
+                } else {
+                    tma_load_2d(st + G_A_BYTES, &map_b, kb * G_BK, n0, &full[s]);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = umma::instr_desc(umma::FMT_TF32, G_BM, G_BN);
-            for (int kb = 0; kb < KB; ++kb) {
-                const int s = kb % G_STAGES;
-                mbar_wait(&split[s], (uint32_t)((kb / G_STAGES) & 1));
+            const uint32_t idesc = umma::instr_desc(umma::FMT_TF32, G_BM, n_instr) | (A_MN ? (1u << 15) : 0u) |
+                                   (B_MN ? (1u << 16) : 0u);
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % G_STAGES;
+                const int c = i / G_CH, j = i - c * G_CH, buf = c & 1;
+                if (j == 0 && c >= 2) {                       // the drain warps have read chunk c-2 out of this buffer
+                    mbar_wait(&acc_free[buf], (uint32_t)(((c >> 1) - 1) & 1));
+                    umma::fence_after_sync();
+                }
+                mbar_wait(&split[s], (uint32_t)((i / G_STAGES) & 1));
                 umma::fence_after_sync();
+                const uint32_t d = tmem + 256u * buf;
                 const uint32_t a = smem_u32(smem + s * G_STAGE_BYTES), b = a + G_A_BYTES;
                 const uint32_t alo = b + G_B_BYTES, blo = alo + G_A_BYTES;
 #pragma unroll
                 for (int k4 = 0; k4 < G_BK / 8; ++k4) {
-                    const uint64_t da = umma::desc_k_sw128(a + k4 * 32), db = umma::desc_k_sw128(b + k4 * 32);
-                    umma::mma_ss<umma::FMT_TF32>(tmem, da, db, idesc, (kb | k4) != 0);
-                    umma::mma_ss<umma::FMT_TF32>(tmem, umma::desc_k_sw128(alo + k4 * 32), db, idesc, 1);
-                    umma::mma_ss<umma::FMT_TF32>(tmem, da, umma::desc_k_sw128(blo + k4 * 32), idesc, 1);
+                    const uint64_t da = A_MN ? desc_mn_sw128(a + k4 * 1024) : umma::desc_k_sw128(a + k4 * 32);
+                    const uint64_t db = B_MN ? desc_mn_sw128(b + k4 * 1024) : umma::desc_k_sw128(b + k4 * 32);
+                    const uint64_t dal = A_MN ? desc_mn_sw128(alo + k4 * 1024) : umma::desc_k_sw128(alo + k4 * 32);
+                    const uint64_t dbl = B_MN ? desc_mn_sw128(blo + k4 * 1024) : umma::desc_k_sw128(blo + k4 * 32);
+                    umma::mma_ss<umma::FMT_TF32>(d, da, db, idesc, (j | k4) != 0);
+                    umma::mma_ss<umma::FMT_TF32>(d, dal, db, idesc, 1);
+                    umma::mma_ss<umma::FMT_TF32>(d, da, dbl, idesc, 1);
                 }
                 umma::commit(&empty[s]);
+                if (j == G_CH - 1 || i == nkb - 1) umma::commit(&acc_full[buf]);
             }
-            umma::commit(acc_done);
         }
     } else {
-        // ---------------------------------------------------------------- splitters: lo = x - trunc_tf32(x)
+        // ------------------------------------------- splitters (lo = x - trunc_tf32(x)) + second-level accumulation
+        // The tensor core ADDS into its fp32 accumulator with truncation (measured: a bias of ~2^-25.5 of the running
+        // sum per MMA, always towards zero, i.e. linear in K).  The TMEM chain is therefore cut into chunks of G_CH
+        // K blocks (48 MMAs); each chunk's partial tile is drained into registers and summed there with IEEE fp32
+        // adds, while the tensor core already fills the other TMEM buffer.
         const int st_tid = tid - 64;                                  // 0..255
-        for (int kb = 0; kb < KB; ++kb) {
-            const int s = kb % G_STAGES;
-            mbar_wait(&full[s], (uint32_t)((kb / G_STAGES) & 1));
+        const int q = warp & 3, half = (warp - 2) >> 2;               // TMEM lane quadrant, column half of the tile
+        const uint32_t t_base = tmem + ((uint32_t)(32 * q) << 16) + 128u * half;
+        float acc[128];
+#pragma unroll
+        for (int e = 0; e < 128; ++e) acc[e] = 0.f;
+        int next_drain = 0;
+        auto drain = [&](int c) {
+            const int buf = c & 1;
+            mbar_wait(&acc_full[buf], (uint32_t)((c >> 1) & 1));
+            umma::fence_after_sync();
+#pragma unroll
+            for (int gq = 0; gq < 4; ++gq) {
+                uint32_t v[32];
+                umma::ld_32x32b_x32(t_base + 256u * buf + 32u * gq, v);
+                umma::wait_ld();
+#pragma unroll
+                for (int e = 0; e < 32; ++e) acc[32 * gq + e] += __uint_as_float(v[e]);
+            }
+            umma::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) g_arrive(&acc_free[buf]);
+        };
+        // only the bytes that were loaded: A tile (or its valid boxes) and B tile (or its valid boxes)
+        const int a_vec = (int)(a_bytes / 16), b_vec = (int)(b_bytes / 16);
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % G_STAGES;
+            mbar_wait(&full[s], (uint32_t)((i / G_STAGES) & 1));
             const float4* src = reinterpret_cast<const float4*>(smem + s * G_STAGE_BYTES);
             float4* dst = reinterpret_cast<float4*>(smem + s * G_STAGE_BYTES + G_A_BYTES + G_B_BYTES);
 #pragma unroll 4
-            for (int i = st_tid; i < (G_A_BYTES + G_B_BYTES) / 16; i += 32 * G_SPLIT_WARPS) {
-                const float4 v = src[i];
-                dst[i] = make_float4(tf32_residual(v.x), tf32_residual(v.y), tf32_residual(v.z), tf32_residual(v.w));
+            for (int j = st_tid; j < a_vec; j += 32 * G_SPLIT_WARPS) {
+                const float4 v = src[j];
+                dst[j] = make_float4(tf32_residual(v.x), tf32_residual(v.y), tf32_residual(v.z), tf32_residual(v.w));
+            }
+#pragma unroll 4
+            for (int j = G_A_BYTES / 16 + st_tid; j < G_A_BYTES / 16 + b_vec; j += 32 * G_SPLIT_WARPS) {
+                const float4 v = src[j];
+                dst[j] = make_float4(tf32_residual(v.x), tf32_residual(v.y), tf32_residual(v.z), tf32_residual(v.w));
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) g_arrive(&split[s]);
+            // chunk i/G_CH - 1 retired at the latest when K block i-2 left the 2-stage ring: drain it now
+            if (i >= G_CH && (i % G_CH) == 1) drain(next_drain++);
         }
-        // ---------------------------------------------------------------- epilogue (warps 2..5: one TMEM quadrant each)
-        if (warp < 6) {
-            const int q = warp & 3;
-            mbar_wait(acc_done, 0);
-            umma::fence_after_sync();
+        while (next_drain < nchunks) drain(next_drain++);
+        // ---------------------------------------------------------------- epilogue: registers -> C
+        {
             const int row = m0 + 32 * q + lane;
-            const bool vec = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
-            for (int c0 = 0; c0 < G_BN; c0 += 32) {
-                if (n0 + c0 >= N) break;
-                uint32_t v[32];
+            const bool to_partial = gridDim.z > 1;
+            float* Cb = to_partial ? g.partial + (size_t)blockIdx.z * M * N : g.C;
+            const int ldc = to_partial ? N : g.ldc;
+            const int orow = (!to_partial && g.perm) ? (row & 3) * (M >> 2) + (row >> 2) : row;
+            const float* bias = to_partial ? nullptr : g.bias;
+            const int accumulate = to_partial ? 0 : g.accumulate;
+            const bool vec = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(Cb) & 15) == 0);
+            if (row < M) {
+                float* crow = Cb + (size_t)orow * ldc + n0 + 128 * half;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    uint32_t t8[8];
-                    umma::ld_32x32b_x8(tmem + ((uint32_t)(32 * q) << 16) + c0 + 8 * j, t8);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) v[8 * j + i] = t8[i];
-                }
-                umma::wait_ld();
-                if (row < M) {
-                    float* crow = C + (size_t)row * ldc + n0 + c0;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int n = n0 + c0 + 4 * j;
+                for (int j = 0; j < 32; ++j) {
+                    const int n = n0 + 128 * half + 4 * j;
+                    if (n < N) {
                         float o[4];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            o[i] = __uint_as_float(v[4 * j + i]);
-                            if (bias && n + i < N) o[i] += bias[n + i];
+                        for (int e = 0; e < 4; ++e) {
+                            o[e] = acc[4 * j + e];
+                            if (bias && n + e < N) o[e] += bias[n + e];
                         }
                         if (vec && n + 3 < N) {
                             float4* p4 = reinterpret_cast<float4*>(crow + 4 * j);
@@ -159,8 +272,8 @@ gemm3x_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                             *p4 = make_float4(o[0], o[1], o[2], o[3]);
                         } else {
 #pragma unroll
-                            for (int i = 0; i < 4; ++i)
-                                if (n + i < N) crow[4 * j + i] = accumulate ? crow[4 * j + i] + o[i] : o[i];
+                            for (int e = 0; e < 4; ++e)
+                                if (n + e < N) crow[4 * j + e] = accumulate ? crow[4 * j + e] + o[e] : o[e];
                         }
                     }
                 }
@@ -169,7 +282,22 @@ gemm3x_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
     umma::fence_before_sync();
     __syncthreads();
-    if (warp == 1) umma::tmem_dealloc(tmem, 256);
+    if (warp == 1) umma::tmem_dealloc(tmem, 512);
+}
+
+// C[perm(m)][n] (+)= bias[n] + sum_s partial[s][m][n]   (fixed summation order)
+__global__ void gemm3x_reduce_kernel(const float* __restrict__ partial, int nsplit, const float* __restrict__ bias,
+                                     float* __restrict__ C, int M, int N, int ldc, int accumulate, int perm) {
+    const long long total = (long long)M * N;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int m = (int)(i / N), n = (int)(i - (long long)m * N);
+        float s = partial[i];
+        for (int k = 1; k < nsplit; ++k) s += partial[(long long)k * total + i];
+        if (bias) s += bias[n];
+        const int orow = perm ? (m & 3) * (M >> 2) + (m >> 2) : m;
+        float* c = C + (size_t)orow * ldc + n;
+        *c = accumulate ? *c + s : s;
+    }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -188,9 +316,9 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// row-major fp32 matrix [rows, K] with row pitch ld (floats; rows may overlap when ld < K: the im2col view of a
-// strided convolution) -> tensor map with boxes of 32 (K) x box_rows, 128-byte swizzle
-int make_map(CUtensorMap* map, const float* ptr, int rows, int K, int ld, int box_rows) {
+// K-major operand: row-major fp32 matrix [rows, K] with row pitch ld (floats; rows may overlap when ld < K: the im2col
+// view of a strided convolution) -> 2-D tensor map with boxes of 32 (K) x box_rows, 128-byte swizzle
+int make_map_k(CUtensorMap* map, const float* ptr, int rows, int K, int ld, int box_rows) {
     EncodeTiledFn enc = encode_fn();
     B200_REQUIRE(enc != nullptr, "gemm: cuTensorMapEncodeTiled is not available from this driver");
     const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
@@ -204,6 +332,57 @@ int make_map(CUtensorMap* map, const float* ptr, int rows, int K, int ld, int bo
     return B200_OK;
 }
 
+// MN-major operand: element (batch b, time t, column c) at ptr[b * bstride + t * ld + c] -> 3-D tensor map (c, t, b)
+// with boxes of 32 columns x 32 rows x 1, 128-byte swizzle; reads outside [0,cols) x [0,T) are zero-filled
+int make_map_mn(CUtensorMap* map, const float* ptr, int cols, int T, int batches, long long ld, long long bstride) {
+    EncodeTiledFn enc = encode_fn();
+    B200_REQUIRE(enc != nullptr, "gemm: cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)T, (cuuint64_t)batches};
+    const cuuint64_t strides[2] = {(cuuint64_t)ld * sizeof(float), (cuuint64_t)(batches > 1 ? bstride : ld * (long long)T) * sizeof(float)};
+    const cuuint32_t box[3] = {32, (cuuint32_t)G_BK, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B200_REQUIRE(r == CUDA_SUCCESS, "gemm: cuTensorMapEncodeTiled failed (%d) for a [%d x %d x %d] operand", (int)r,
+                 batches, T, cols);
+    return B200_OK;
+}
+
+int pick_split(int M, int N, int KB) {
+    const int tiles = ((M + G_BM - 1) / G_BM) * ((N + G_BN - 1) / G_BN);
+    int s = sm_count() / tiles;
+    if (s > KB / 8) s = KB / 8;           // at least 8 K blocks per slice
+    if (s > G_MAX_SPLIT) s = G_MAX_SPLIT;
+    return s < 1 ? 1 : s;
+}
+
+template <bool A_MN, bool B_MN>
+int launch(const CUtensorMap& ma, const CUtensorMap& mb, GemmArgs g, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    int nsplit = pick_split(g.M, g.N, g.KB);
+    if (nsplit > 1 && (ws == nullptr || ws_bytes < (size_t)nsplit * g.M * g.N * sizeof(float))) nsplit = 1;
+    g.kb_per_split = (g.KB + nsplit - 1) / nsplit;
+    nsplit = (g.KB + g.kb_per_split - 1) / g.kb_per_split;       // no empty slices
+    g.partial = reinterpret_cast<float*>(ws);
+    const size_t smem = (size_t)G_STAGES * G_STAGE_BYTES + 256;
+    auto fn = gemm3x_kernel<A_MN, B_MN>;
+    B200_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((g.N + G_BN - 1) / G_BN, (g.M + G_BM - 1) / G_BM, nsplit);
+    fn<<<grid, G_THREADS, smem, stream>>>(ma, mb, g);
+    B200_LAUNCH_CHECK("gemm3x_kernel");
+    if (nsplit > 1) {
+        const long long total = (long long)g.M * g.N;
+        int blocks = (int)((total + 255) / 256);
+        if (blocks > 2368) blocks = 2368;
+        gemm3x_reduce_kernel<<<blocks, 256, 0, stream>>>(g.partial, nsplit, g.bias, g.C, g.M, g.N, g.ldc, g.accumulate,
+                                                         g.perm);
+        B200_LAUNCH_CHECK("gemm3x_reduce_kernel");
+    }
+    return B200_OK;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 }  // namespace
 }  // namespace b200asr
 
@@ -212,6 +391,14 @@ using namespace b200asr;
 extern "C" int b200asr_gemm3x_supported(int M, int N, int K) {
     // TMA: 16-byte aligned row pitch; at least one full tile's worth of work is not required (tails are zero-filled)
     return (M > 0 && N > 0 && K > 0 && (K % 4) == 0) ? 1 : 0;
+}
+
+extern "C" size_t b200asr_gemm3x_workspace_bytes(int M, int N) {
+    if (M <= 0 || N <= 0) return 0;
+    const int tiles = ((M + G_BM - 1) / G_BM) * ((N + G_BN - 1) / G_BN);
+    int s = sm_count() / tiles;
+    if (s > G_MAX_SPLIT) s = G_MAX_SPLIT;
+    return s > 1 ? (size_t)s * M * N * sizeof(float) : 0;
 }
 
 extern "C" int b200asr_gemm3x_tn(const float* A, const float* B, const float* bias, float* C, int M, int N, int K,
@@ -226,17 +413,57 @@ extern "C" int b200asr_gemm3x_tn_ld(const float* A, int lda, const float* B, con
     B200_REQUIRE(b200asr_gemm3x_supported(M, N, K), "gemm3x_tn: unsupported sizes M=%d N=%d K=%d (K %% 4 must be 0)", M,
                  N, K);
     B200_REQUIRE(ldc >= N, "gemm3x_tn: ldc %d < N %d", ldc, N);
-    B200_REQUIRE(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) == 0,
-                 "gemm3x_tn: operands must be 16-byte aligned");
+    B200_REQUIRE(aligned16(A) && aligned16(B), "gemm3x_tn: operands must be 16-byte aligned");
     CUtensorMap ma, mb;
-    int rc = make_map(&ma, A, M, K, lda, G_BM);
+    int rc = make_map_k(&ma, A, M, K, lda, G_BM);
     if (rc != B200_OK) return rc;
-    rc = make_map(&mb, B, N, K, K, G_BN);
+    rc = make_map_k(&mb, B, N, K, K, G_BN);
     if (rc != B200_OK) return rc;
-    const size_t smem = (size_t)G_STAGES * G_STAGE_BYTES + 256;
-    B200_CUDA(cudaFuncSetAttribute(gemm3x_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((N + G_BN - 1) / G_BN, (M + G_BM - 1) / G_BM);
-    gemm3x_tn_kernel<<<grid, G_THREADS, smem, (cudaStream_t)stream>>>(ma, mb, bias, C, M, N, K, ldc, accumulate);
-    B200_LAUNCH_CHECK("gemm3x_tn_kernel");
-    return B200_OK;
+    GemmArgs g = {};
+    g.bias = bias; g.C = C; g.M = M; g.N = N; g.ldc = ldc; g.accumulate = accumulate;
+    g.KB = (K + G_BK - 1) / G_BK; g.kbt = g.KB;
+    return launch<false, false>(ma, mb, g, nullptr, 0, (cudaStream_t)stream);
+}
+
+extern "C" int b200asr_gemm3x_nn(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int M,
+                                 int N, int K, int ldc, int accumulate, b200asr_stream stream) {
+    B200_REQUIRE(A && B && C, "gemm3x_nn: null pointer");
+    B200_REQUIRE(M > 0 && N > 0 && K > 0, "gemm3x_nn: bad sizes M=%d N=%d K=%d", M, N, K);
+    B200_REQUIRE(lda >= K && (lda % 4) == 0 && ldb >= N && (ldb % 4) == 0 && ldc >= N,
+                 "gemm3x_nn: row pitches must be multiples of 4 floats (lda %d ldb %d ldc %d)", lda, ldb, ldc);
+    B200_REQUIRE(aligned16(A) && aligned16(B), "gemm3x_nn: operands must be 16-byte aligned");
+    CUtensorMap ma, mb;
+    int rc = make_map_k(&ma, A, M, K, lda, G_BM);
+    if (rc != B200_OK) return rc;
+    rc = make_map_mn(&mb, B, N, K, 1, ldb, 0);
+    if (rc != B200_OK) return rc;
+    GemmArgs g = {};
+    g.bias = bias; g.C = C; g.M = M; g.N = N; g.ldc = ldc; g.accumulate = accumulate;
+    g.KB = (K + G_BK - 1) / G_BK; g.kbt = g.KB;
+    return launch<false, true>(ma, mb, g, nullptr, 0, (cudaStream_t)stream);
+}
+
+extern "C" int b200asr_gemm3x_nt(const float* A, long long lda, long long a_bstride, int a_shift, const float* B,
+                                 long long ldb, long long b_bstride, int b_shift, float* C, int M, int N, int T,
+                                 int batches, int ldc, int accumulate, int permute_rows, void* workspace,
+                                 size_t workspace_bytes, b200asr_stream stream) {
+    B200_REQUIRE(A && B && C, "gemm3x_nt: null pointer");
+    B200_REQUIRE(M > 0 && N > 0 && T > 0 && batches > 0, "gemm3x_nt: bad sizes M=%d N=%d T=%d batches=%d", M, N, T,
+                 batches);
+    B200_REQUIRE(lda >= M && (lda % 4) == 0 && ldb >= N && (ldb % 4) == 0 && (a_bstride % 4) == 0 &&
+                     (b_bstride % 4) == 0 && ldc >= N,
+                 "gemm3x_nt: pitches must be multiples of 4 floats (lda %lld ldb %lld)", lda, ldb);
+    B200_REQUIRE(aligned16(A) && aligned16(B), "gemm3x_nt: operands must be 16-byte aligned");
+    B200_REQUIRE(!permute_rows || (M % 4) == 0, "gemm3x_nt: the row permutation needs M %% 4 == 0");
+    B200_REQUIRE(a_shift >= -G_BK && a_shift <= G_BK && b_shift >= -G_BK && b_shift <= G_BK, "gemm3x_nt: bad shift");
+    CUtensorMap ma, mb;
+    int rc = make_map_mn(&ma, A, M, T, batches, lda, a_bstride);
+    if (rc != B200_OK) return rc;
+    rc = make_map_mn(&mb, B, N, T, batches, ldb, b_bstride);
+    if (rc != B200_OK) return rc;
+    GemmArgs g = {};
+    g.C = C; g.M = M; g.N = N; g.ldc = ldc; g.accumulate = accumulate; g.perm = permute_rows;
+    g.kbt = (T + G_BK - 1) / G_BK; g.KB = g.kbt * batches;
+    g.a_shift = a_shift; g.b_shift = b_shift;
+    return launch<true, true>(ma, mb, g, workspace, workspace_bytes, (cudaStream_t)stream);
 }

@@ -93,6 +93,18 @@ __device__ __forceinline__ void ld_32x32b_x8(uint32_t taddr, uint32_t (&v)[8]) {
                  : "r"(taddr)
                  : "memory");
 }
+// 32 lanes x 32 bit, x32: thread i of the warp reads 32 consecutive columns of lane (lane_base + i).
+__device__ __forceinline__ void ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,"
+        "%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
 // 16 lanes x 256 bit, x1: thread i holds (row i/4, cols 2(i%4), 2(i%4)+1) in v0,v1 and row i/4 + 8 in v2,v3.
 __device__ __forceinline__ void ld_16x256b_x1(uint32_t taddr, uint32_t (&v)[4]) {
     asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0,%1,%2,%3}, [%4];"

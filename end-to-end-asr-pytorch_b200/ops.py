@@ -84,6 +84,38 @@ def gemm_tn_ld(a_base, lda, M, K, w, bias=None):
     return out
 
 
+def gemm_nn(a, w, out=None, accumulate=False):
+    """out[M,N] (= or +=) a[M,K] @ w[K,N]: the input gradient dY . W with W read in place (MN-major operand)."""
+    lib = L.load()
+    a, w = _f32c(a), _f32c(w)
+    M, K = a.shape
+    N = w.shape[1]
+    if out is None:
+        out = torch.empty((M, N), device=a.device, dtype=torch.float32)
+        accumulate = False
+    assert out.stride(1) == 1 and out.shape == (M, N)
+    with L.timed("gemm3x_nn", 4 * (M * K + N * K + M * N * (2 if accumulate else 1))):
+        L.check(lib.b200asr_gemm3x_nn(L.ptr(a), K, L.ptr(w), N, None, L.ptr(out), M, N, K, out.stride(0),
+                                      int(bool(accumulate)), L.stream()), "gemm3x_nn")
+    return out
+
+
+def gemm_nt(a, b, M, N, T, batches=1, lda=None, a_bstride=0, ldb=None, b_bstride=0, b_shift=0, permute_rows=False):
+    """out[M,N] = sum over (batch, t) of a[batch, t, :M]^T b[batch, t + b_shift, :N]: the weight gradient dY^T . X.
+    `a` / `b` are tensors whose data pointer is element (0, 0, 0); pitches are in floats (default: dense [T, M] / [T, N])."""
+    lib = L.load()
+    lda = M if lda is None else lda
+    ldb = N if ldb is None else ldb
+    out = torch.empty((M, N), device=a.device, dtype=torch.float32)
+    ws_bytes = lib.b200asr_gemm3x_workspace_bytes(M, N)
+    ws = torch.empty(max(ws_bytes, 16), device=a.device, dtype=torch.uint8)
+    with L.timed("gemm3x_nt", 4 * (batches * T * (M + N) + M * N)):
+        L.check(lib.b200asr_gemm3x_nt(L.ptr(a), lda, a_bstride, 0, L.ptr(b), ldb, b_bstride, b_shift, L.ptr(out), M, N,
+                                      T, batches, N, 0, int(bool(permute_rows)), L.ptr(ws), ws_bytes, L.stream()),
+                "gemm3x_nt")
+    return out
+
+
 class Conv1dK4S2Fn(Function):
     """Conv1d(C -> O, kernel 4, stride 2, padding 1) over [B, T, C] (CNNExtractor, src/module.py:75-78) as ONE
     tensor-core GEMM: with one zero row in front of every utterance, output frame t reads the 4*C CONTIGUOUS floats that
@@ -119,16 +151,14 @@ class Conv1dK4S2Fn(Function):
         dy2 = dyf.view(B * half, O)
         dx = None
         if ctx.needs_input_grad[0]:
-            dcols = gemm_tn(dy2, wm.t().contiguous()).view(B, half, 2, 2 * C)      # [.., 0]: rows 2t,2t+1  [.., 1]: 2t+2,2t+3
+            dcols = gemm_nn(dy2, wm).view(B, half, 2, 2 * C)      # [.., 0]: rows 2t,2t+1  [.., 1]: 2t+2,2t+3
             dxp = torch.zeros((B, half + 1, 2 * C), device=dy.device, dtype=torch.float32)
             dxp[:, :half] += dcols[:, :, 0]
             dxp[:, 1:] += dcols[:, :, 1]
             dx = dxp.view(B, Tp + 2, C)[:, 1:T + 1].contiguous()
         dw = db = None
         if ctx.needs_input_grad[1]:
-            cols = xp.view(-1).as_strided((M, 4 * C), (2 * C, 1)).contiguous()
-            Op, mm = _gemm_ops()
-            dwm = mm(Op(dy2[:M]).t(), Op(cols))                                      # [O, 4C]
+            dwm = gemm_nt(dy2, xp, O, 4 * C, M, ldb=2 * C)                          # [O, 4C], windows read in place
             dw = dwm.view(O, 4, C).permute(0, 2, 1).contiguous()
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = dy.reshape(-1, O).sum(0)
@@ -287,17 +317,30 @@ class BiLSTMFn(Function):
             L.check(lib.b200asr_bilstm_bwd(L.ptr(gates), L.ptr(w_hh), L.ptr(cst), L.ptr(dout), B, T, H, ndir,
                                            L.ptr(ws), ws_bytes, L.stream()), "bilstm_bwd")
         perm = gate_perm(H, dev)
-        xs = Op(x.view(B * T, I))
         need_dx = ctx.needs_input_grad[0]
         dx2 = torch.empty((B * T, I), device=dev, dtype=torch.float32) if need_dx else None
         grads = []
+        if _use_umma(I) and H % 4 == 0:
+            # own tensor-core kernels throughout: dX = dG . W (W in place), dW_ih = dG^T . X, dW_hh = dG^T . h_prev with
+            # h_prev read from the layer output shifted by one step (never materialised); rows written through the gate
+            # permutation by the epilogue
+            for d in range(ndir):
+                g2 = gates[d].view(B * T, 4 * H)
+                if need_dx:
+                    gemm_nn(g2, w_ih_p[d], out=dx2, accumulate=(d > 0))
+                dw_ih = gemm_nt(g2, x, 4 * H, I, B * T, permute_rows=True)
+                hd = out[:, :, d * H:(d + 1) * H]
+                dw_hh = gemm_nt(g2, hd, 4 * H, H, T, batches=B, a_bstride=T * 4 * H, ldb=ndir * H,
+                                b_bstride=T * ndir * H, b_shift=(-1 if d == 0 else 1), permute_rows=True)
+                db = torch.empty((4 * H,), device=dev, dtype=torch.float32)
+                db.index_copy_(0, perm, g2.sum(0))
+                grads += [dw_ih, dw_hh, db, db.clone()]
+            return (dx2.view(B, T, I) if need_dx else None, None, *grads)
+        xs = Op(x.view(B * T, I))
         for d in range(ndir):
             dG = Op(gates[d].view(B * T, 4 * H))  # d(loss)/d(pre-activation), unit-major columns
             if need_dx:
-                if _use_umma(4 * H):
-                    gemm_tn(gates[d].view(B * T, 4 * H), w_ih_p[d].t().contiguous(), out=dx2, accumulate=(d > 0))
-                else:
-                    mm(dG, Op(w_ih_p[d]), out=dx2, accumulate=(d > 0))
+                mm(dG, Op(w_ih_p[d]), out=dx2, accumulate=(d > 0))
             dw_ih = torch.empty((4 * H, I), device=dev, dtype=torch.float32)
             dw_ih.index_copy_(0, perm, mm(dG.t(), xs))
             db = torch.empty((4 * H,), device=dev, dtype=torch.float32)
@@ -619,12 +662,18 @@ class Linear3xFn(Function):
         x2, weight = ctx.saved_tensors
         gy2 = _f32c(gy).reshape(-1, weight.shape[0])
         dx = None
+        umma = _use_umma(weight.shape[0]) and _use_umma(weight.shape[1])
         if ctx.needs_input_grad[0]:
-            if _use_umma(weight.shape[0]):
-                dx = gemm_tn(gy2, weight.detach().t().contiguous()).view(ctx.shp)
+            if umma:
+                dx = gemm_nn(gy2, weight.detach()).view(ctx.shp)
             else:
                 dx = mm(Op(gy2), Op(weight.detach())).view(ctx.shp)
-        dw = mm(Op(gy2).t(), Op(x2)) if ctx.needs_input_grad[1] else None
+        dw = None
+        if ctx.needs_input_grad[1]:
+            if umma:
+                dw = gemm_nt(gy2, x2, weight.shape[0], weight.shape[1], gy2.shape[0])
+            else:
+                dw = mm(Op(gy2).t(), Op(x2))
         db = gy.reshape(-1, weight.shape[0]).sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
         return dx, dw, db
 

@@ -196,6 +196,24 @@ B200ASR_API int b200asr_gemm3x_tn(const float* A, const float* B, const float* b
  * -> K = 4*C, lda = 2*C), so the convolution runs in this kernel without materialising the windows. */
 B200ASR_API int b200asr_gemm3x_tn_ld(const float* A, int lda, const float* B, const float* bias, float* C, int M, int N, int K,
                          int ldc, int accumulate, b200asr_stream stream);
+/* input gradient  dX = dY . W  (autograd backward of the Linear / LSTM input projection above):
+ *   C[M,N] (+)= A[M,K] . B[K,N] + bias[N]       A row-major with K contiguous (pitch lda), B row-major with N contiguous
+ * (pitch ldb): the weight matrix is read in place as an MN-major tensor-core operand - no transposed copy. */
+B200ASR_API int b200asr_gemm3x_nn(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int M, int N,
+                      int K, int ldc, int accumulate, b200asr_stream stream);
+/* weight gradient  dW = dY^T . X  (autograd backward of the same layers; contraction over the batch*time rows):
+ *   C[m,n] (+)= sum_{b < batches} sum_{t < T}  A[b][t + a_shift][m] * B[b][t + b_shift][n]
+ * element (b, t, c) of an operand lives at ptr[b * bstride + t * ld + c] (both operands MN-major); rows outside [0, T)
+ * read as zero, so  b_shift = -1 / +1  contracts dG[t] with the hidden state of the PREVIOUS step of the forward /
+ * reverse direction (dW_hh of nn.LSTM) straight from the layer output.  permute_rows != 0 writes row m of the result
+ * to row (m % 4) * (M / 4) + m / 4: from the kernels' unit-major gate order back to PyTorch's gate-major rows.
+ * Small M x N with a long contraction is cut into split-K slices over all SMs (partials in `workspace`, summed in a
+ * fixed order by a second launch); workspace may be NULL (no split).                                              */
+B200ASR_API size_t b200asr_gemm3x_workspace_bytes(int M, int N);
+B200ASR_API int b200asr_gemm3x_nt(const float* A, long long lda, long long a_bstride, int a_shift, const float* B,
+                      long long ldb, long long b_bstride, int b_shift, float* C, int M, int N, int T, int batches,
+                      int ldc, int accumulate, int permute_rows, void* workspace, size_t workspace_bytes,
+                      b200asr_stream stream);
 
 /* ---- K6 helper: split fp32 into a TF32-representable high part and the fp32 residual ---------------------------
  * hi = x rounded to TF32, lo = x - hi; used to run the input-projection (src/module.py:131, inside nn.LSTM) and the

@@ -570,3 +570,60 @@ def test_linear_and_lstm_projection_through_the_gemm_kernel(pkg):
         assert scaled_err(xd.grad.cpu().numpy(), xr.grad.numpy()) < 1e-5
     finally:
         pkg.ops.GEMM_MODE = mode
+
+
+@pytest.mark.parametrize("M,N,K,acc", [(3000, 2048, 1024, False), (300, 120, 2048, False), (129, 260, 64, True),
+                                      (77, 300, 2048, True), (5, 8, 4, False)])
+def test_gemm3x_nn_is_fp32_class(pkg, M, N, K, acc):
+    """Input-gradient form C (+)= A[M,K] . B[K,N]: B read in place as an MN-major tensor-core operand."""
+    torch.manual_seed(M + N + 1)
+    a = torch.randn(M, K, device=DEV)
+    b = torch.randn(K, N, device=DEV) * 0.05
+    out = torch.randn(M, N, device=DEV)
+    c0 = out.clone()
+    ref = a.double() @ b.double() + (c0.double() if acc else 0)
+    pkg.ops.gemm_nn(a, b, out=out, accumulate=acc)
+    sg = a @ b + (c0 if acc else 0)
+    e3 = scaled_err(out.cpu().numpy(), ref.cpu().numpy())
+    e1 = scaled_err(sg.cpu().numpy(), ref.cpu().numpy())
+    assert e3 < 3e-6 and e3 < 20 * max(e1, 1e-7), (e3, e1)
+
+
+@pytest.mark.parametrize("M,N,T,batches,shift,perm", [
+    (2048, 120, 5000, 1, 0, True),        # dW_ih of layer 0: long contraction, one narrow column tile -> split-K
+    (2048, 512, 37, 8, -1, True),         # dW_hh, forward direction: h_prev = output shifted by one step, per utterance
+    (2048, 512, 37, 8, 1, True),          # dW_hh, reverse direction
+    (300, 31, 700, 1, 0, False),          # CTC head (V = 31): M / N tails
+    (100, 260, 64, 3, 0, False),          # two column tiles, the second almost empty
+    (2560, 640, 20000, 1, 0, True),       # cfg D size class: 20 x 3 tiles, long K, no split
+])
+def test_gemm3x_nt_is_fp32_class(pkg, M, N, T, batches, shift, perm):
+    """Weight-gradient form C = sum_(b,t) A[b,t,:]^T B[b,t+shift,:] (both operands MN-major, TMA zero fill outside
+    [0,T), row permutation in the epilogue, deterministic split-K) against fp64."""
+    torch.manual_seed(M + N + T)
+    ldb = (N + 3) // 4 * 4 + 4                     # padded pitch: the operand is a column slice of a wider buffer
+    a = torch.randn(batches, T, M, device=DEV)
+    bfull = torch.randn(batches, T, ldb, device=DEV)
+    b = bfull[:, :, :N]
+    bs = torch.zeros(batches, T, N, device=DEV, dtype=torch.float64)
+    if shift == 0:
+        bs[:] = b.double()
+    elif shift < 0:
+        bs[:, 1:] = b[:, :-1].double()
+    else:
+        bs[:, :-1] = b[:, 1:].double()
+    ref = torch.einsum("btm,btn->mn", a.double(), bs)
+    sg = torch.einsum("btm,btn->mn", a, bs.float())
+    if perm:
+        idx = torch.arange(M, device=DEV)
+        dst = (idx % 4) * (M // 4) + idx // 4
+        r2 = torch.empty_like(ref); r2[dst] = ref; ref = r2
+        s2 = torch.empty_like(sg); s2[dst] = sg; sg = s2
+    out = pkg.ops.gemm_nt(a, bfull, M, N, T, batches=batches, a_bstride=T * M, ldb=ldb, b_bstride=T * ldb,
+                          b_shift=shift, permute_rows=perm)
+    out2 = pkg.ops.gemm_nt(a, bfull, M, N, T, batches=batches, a_bstride=T * M, ldb=ldb, b_bstride=T * ldb,
+                           b_shift=shift, permute_rows=perm)
+    assert torch.equal(out, out2)                                               # deterministic (split-K in fixed order)
+    e3 = scaled_err(out.cpu().numpy(), ref.cpu().numpy())
+    e1 = scaled_err(sg.cpu().numpy(), ref.cpu().numpy())
+    assert e3 < 3e-6 and e3 < 20 * max(e1, 1e-7), (e3, e1)

@@ -47,7 +47,10 @@ def test_train_step_matches_reference(pkg, kind):
         assert abs(ctc.item() - float(g["ctc_loss"])) < 1e-4 * abs(float(g["ctc_loss"]))
         total = total + ctc * model.ctc_weight
     if att_out is not None:
-        assert rel_err(att_out.detach().cpu().numpy(), g["att_output"]) < 1e-4
+        # raw logits: 1e-4 relative, with the abs floor for near-zero elements tied to the tensor's scale (the tiny
+        # random-init models have |logit| <= 0.1, where a fixed 1e-3 floor would test fp32 rounding noise of cuDNN)
+        assert rel_err(att_out.detach().cpu().numpy(), g["att_output"],
+                       floor=max(1e-3, 0.05 * float(np.abs(g["att_output"]).max()))) < 1e-4
         assert rel_err(att_seq.detach().cpu().numpy(), g["att_seq"], floor=1e-4) < 1e-4
         assert np.array_equal(att_out.argmax(-1).cpu().numpy(), g["att_argmax"])
         b, t, _ = att_out.shape
