@@ -394,9 +394,10 @@ def main():
               "frames": 1 + (args.n_samples - 400) // 160, "vocab": vocab,
               "parallelism": "dp%d (utterance shards; per-layer NCCL grad all-reduce buckets overlapped with backward)" % world,
               "l2": "inputs+activations per step (>1 GB) exceed the 126 MB L2; no explicit flush",
-              "gemm": "K-major projections + input gradients: own tcgen05 3xTF32 kernel when B200ASR_GEMM=umma, else (and "
-                      "for the weight gradients) 3xTF32 error-compensated cuBLAS; fp32-accurate",
-              "lstm": "tcgen05 fp16 hi/lo 2x2-block split product (forward; backward per LSTM_UMMA_BWD_DEFAULT)"}
+              "gemm": "own tcgen05 3xTF32 kernel in three operand forms (x.W^T, dY.W, dY^T.X incl. shifted h_prev reads, split-K, "
+                      "gate permutation in the epilogue), two-level accumulation (TMEM chunks of 128 k summed in fp32 "
+                      "registers); B200ASR_GEMM=tf32x3 selects the cuBLAS 3xTF32 composition; fp32-accurate",
+              "lstm": "tcgen05 fp16 hi/lo 2x2-block split product, forward and backward (H = 256 / 512; H = 640 backward: mma.sync 3xTF32)"}
 
     # ------------------------------------------------------------------------------- reference (CPU) arm
     if args.impl == "reference":

@@ -26,9 +26,9 @@
 //
 // Shared-memory images.  K-major operand, R rows: R consecutive 128-byte rows (32 k each), 128-byte swizzle; one MMA
 // (8 k) advances the descriptor start by 32 bytes.  MN-major operand, R columns: R/32 boxes of [32 k][32 columns] =
-// 4096 bytes each (what a TMA box {32 columns, 32 rows} with SWIZZLE_128B produces); canonical UMMA layout
-// ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units with LBO = 4096 B (next 32 columns) and SBO = 1024 B (next 8 k);
-// one MMA (8 k) advances the start by 1024 bytes.
+// 4096 bytes each (a TMA box {32 columns, 32 rows}); for 32-bit types the tensor core wants the 128-byte swizzle with
+// a 32-byte base (TMA SWIZZLE_128B_ATOM_32B <-> descriptor layout SWIZZLE_128B_BASE32B), LBO = 4096 B (next 32
+// columns), SBO = 512 B (next 4 k); one MMA (8 k) advances the start by 1024 bytes.
 #include <cuda.h>
 #include "common.cuh"
 #include "umma.cuh"
@@ -80,14 +80,16 @@ __device__ __forceinline__ void g_arrive(uint64_t* bar) {
 __device__ __forceinline__ float tf32_residual(float x) {
     return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u);
 }
-// MN-major, SWIZZLE_128B matrix descriptor: leading byte offset = distance between 32-column boxes, stride byte offset =
-// distance between groups of 8 k.
+// MN-major matrix descriptor for a 32-bit type: the tensor core transposes 32-bit MN-major operands at 32-byte
+// granularity, so the layout type is SWIZZLE_128B_BASE32B (= 1: 32-byte chunks swizzled within the 128-byte row, pattern
+// period 4 rows - what a TMA load with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B produces).  Leading byte offset = distance
+// between 32-column boxes, stride byte offset = distance between groups of 4 k (512 bytes).
 __device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t smem_addr) {
     uint64_t d = static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
     d |= static_cast<uint64_t>(G_BOX >> 4) << 16;
-    d |= static_cast<uint64_t>(1024 >> 4) << 32;
+    d |= static_cast<uint64_t>(512 >> 4) << 32;
     d |= static_cast<uint64_t>(1) << 46;
-    d |= static_cast<uint64_t>(2) << 61;
+    d |= static_cast<uint64_t>(1) << 61;
     return d;
 }
 
@@ -342,8 +344,8 @@ int make_map_mn(CUtensorMap* map, const float* ptr, int cols, int T, int batches
     const cuuint32_t box[3] = {32, (cuuint32_t)G_BK, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     B200_REQUIRE(r == CUDA_SUCCESS, "gemm: cuTensorMapEncodeTiled failed (%d) for a [%d x %d x %d] operand", (int)r,
                  batches, T, cols);
     return B200_OK;
@@ -450,7 +452,8 @@ extern "C" int b200asr_gemm3x_nt(const float* A, long long lda, long long a_bstr
     B200_REQUIRE(A && B && C, "gemm3x_nt: null pointer");
     B200_REQUIRE(M > 0 && N > 0 && T > 0 && batches > 0, "gemm3x_nt: bad sizes M=%d N=%d T=%d batches=%d", M, N, T,
                  batches);
-    B200_REQUIRE(lda >= M && (lda % 4) == 0 && ldb >= N && (ldb % 4) == 0 && (a_bstride % 4) == 0 &&
+    // (a pitch smaller than the row length = overlapping rows: the in-place im2col view of a strided convolution)
+    B200_REQUIRE(lda > 0 && (lda % 4) == 0 && ldb > 0 && (ldb % 4) == 0 && (a_bstride % 4) == 0 &&
                      (b_bstride % 4) == 0 && ldc >= N,
                  "gemm3x_nt: pitches must be multiples of 4 floats (lda %lld ldb %lld)", lda, ldb);
     B200_REQUIRE(aligned16(A) && aligned16(B), "gemm3x_nt: operands must be 16-byte aligned");

@@ -37,16 +37,16 @@ def gate_perm(H, device):
 
 
 # ----------------------------------------------------------------------------------------------------------
-# Dense contractions of the LSTM layers (K6 and the weight gradients).  They are plain GEMMs, so they go to the
-# tensor cores through cuBLAS - but fp32 parity (1e-4 on logits after 4 recurrent layers) rules out single-pass
-# TF32/BF16.  GEMM_MODE "tf32x3" splits every operand into a TF32-representable high part and an fp32 residual
-# (b200asr_split_tf32) and sums three TF32 tensor-core GEMMs  A_lo.B_hi + A_hi.B_lo + A_hi.B_hi  in fp32
-# (relative error ~1e-6, i.e. fp32 class); "fp32" uses cuBLAS SGEMM (CUDA cores).
-# GEMM_MODE "umma" (default): the K-major products  x . W^T (+ bias)  and their input gradients  dY . W  run in this
-# library's own tcgen05 kernel (csrc/gemm.cu: raw fp32 tiles are the TF32 hi operands, residual tiles made on the fly
-# in shared memory, one TMEM accumulator, bias in the epilogue).  The weight gradients  dY^T . X  (contraction over the
-# B*T rows, both operands MN-major) stay plain library GEMMs in every mode.
-GEMM_MODE = os.environ.get("B200ASR_GEMM", "tf32x3")
+# Dense contractions of the step (K6 / K9 / K11 and their autograd backward).  fp32 parity (1e-4 on logits after 4
+# recurrent layers) rules out single-pass TF32/BF16, so every product is error-compensated "3xTF32" (fp32 class).
+# GEMM_MODE "umma" (default): this library's own tcgen05 kernel (csrc/gemm.cu) in its three operand forms -
+#   gemm_tn  x . W^T (+ bias)   forward;   gemm_nn  dY . W   input gradient (W in place);   gemm_nt  dY^T . X   weight
+#   gradient (contraction over the B*T rows, h_prev read shifted from the layer output, gate permutation in the epilogue).
+#   Raw fp32 tiles are the TF32 hi operands, residual tiles are made on the fly in shared memory, and the TMEM
+#   accumulation chain is cut every 128 k and summed in fp32 registers (the tensor core's own adds truncate).
+# GEMM_MODE "tf32x3": the same arithmetic as three cuBLAS TF32 GEMMs on operands split by b200asr_split_tf32 (kept as a
+#   cross-check and for shapes whose row pitch is not a multiple of 4 floats); "fp32": cuBLAS SGEMM on the CUDA cores.
+GEMM_MODE = os.environ.get("B200ASR_GEMM", "umma")
 
 
 def gemm_tn(a, w, bias=None, out=None, accumulate=False):

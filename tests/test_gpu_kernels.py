@@ -257,6 +257,19 @@ def test_bilstm_backward_generation_toggle(pkg, B, T, I, H, bidir):
         lib.b200asr_debug_set_lstm_mode(0)
 
 
+@pytest.mark.parametrize("B,T,I,H,bidir", [(64, 10, 120, 512, True), (32, 11, 24, 640, True), (40, 9, 16, 512, False),
+                                           (8, 13, 40, 320, True), (64, 300, 64, 512, True)])
+def test_bilstm_exchange_protocol_toggle(pkg, B, T, I, H, bidir):
+    """Mode flags 1024 (forward) / 2048 (backward) select the OTHER state-exchange protocol of the tcgen05 kernels than
+    the default one (data-is-the-flag polling <-> fence + counter + bulk copy): both stay parity-tested."""
+    lib = pkg.load_library()
+    lib.b200asr_debug_set_lstm_mode(1024 + 2048)
+    try:
+        _check_bilstm(pkg, B, T, I, H, bidir, wtol=2e-4 if T > 100 else 1e-4)
+    finally:
+        lib.b200asr_debug_set_lstm_mode(0)
+
+
 def test_bilstm_baseline_shapes_run_on_tcgen05(pkg):
     lib = pkg.load_library()
     assert lib.b200asr_bilstm_uses_tcgen05(64, 512, 2) == 1      # cfg B / C
@@ -547,6 +560,16 @@ def test_conv1d_k4s2_through_the_gemm_kernel(pkg, B, T, C, O):
                                [conv.weight, conv.bias], gy.double())
     assert scaled_err(cd.weight.grad.cpu().numpy(), wref[0].numpy()) < 1e-5
     assert scaled_err(cd.bias.grad.cpu().numpy(), wref[1].numpy()) < 1e-5
+
+
+def test_bilstm_and_linear_with_the_library_gemm_mode(pkg):
+    """GEMM_MODE 'tf32x3' (three cuBLAS TF32 GEMMs on b200asr_split_tf32 operands) stays a supported cross-check."""
+    mode, pkg.ops.GEMM_MODE = pkg.ops.GEMM_MODE, "tf32x3"
+    try:
+        _check_bilstm(pkg, 8, 13, 40, 320, True)
+        _check_bilstm(pkg, 64, 10, 120, 512, True)
+    finally:
+        pkg.ops.GEMM_MODE = mode
 
 
 def test_linear_and_lstm_projection_through_the_gemm_kernel(pkg):

@@ -2,14 +2,13 @@
 # Round-2 profiling recipe (run under gpurun, one GPU): launch list of an eager cfg-B step + `ncu --set full` captures
 # of the shipped kernels.  Summaries: python tools/ncu_summary.py gpurun_out/r02_*.ncu-rep  (works without a GPU).
 mkdir -p gpurun_out
-MODE=${MODE:-0}
 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/r02_launches.csv \
     python bench.py --steps 1 --warmup 1 --no-graph --no-cpu-baseline --no-e2e --no-parity --no-micro \
     > gpurun_out/r02_launch_bench.log 2>&1
-T=128 MODE=$MODE timeout 600 ncu --set full --clock-control none --import-source on \
-    -k regex:'bilstm_(fwd|bwd)_(umma|mma)_kernel|gemm3x_tn' -s 8 -c 6 -f -o gpurun_out/r02_lstm_gemm \
+T=128 timeout 900 ncu --set full --clock-control none --import-source on \
+    -k regex:'bilstm_(fwd|bwd)_umma_kernel|gemm3x_kernel' -s 12 -c 8 -f -o gpurun_out/r02_lstm_gemm \
     python tools/profile_lstm.py > gpurun_out/r02_ncu_lstm.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on \
-    -k regex:'ctc_grad|ctc_alpha|fbank_kernel|delta_norm|log_softmax_fwd|locattn' -s 10 -c 10 -f -o gpurun_out/r02_misc \
+timeout 900 ncu --set full --clock-control none --import-source on \
+    -k regex:'ctc_grad|ctc_alpha|ctc_warp|fbank_kernel|delta_|log_softmax_fwd|locattn' -s 10 -c 10 -f -o gpurun_out/r02_misc \
     python tools/profile_kernels.py > gpurun_out/r02_ncu_misc.log 2>&1
 ls -la gpurun_out/*.ncu-rep

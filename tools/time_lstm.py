@@ -13,7 +13,9 @@ x = torch.randn(B, T, I, device="cuda", requires_grad=True)
 gy = torch.randn(B, T, 2 * H, device="cuda")
 lib = L.load()
 res = {}
-MODES = ((3, "mma.sync"), (0, "tcgen05"), (512, "tcgen05+bwd-toggle"))
+MODES = ((3, "mma.sync"), (0, "tcgen05"), (512, "tcgen05+bwd-toggle"), (3072, "tcgen05+exchange-toggle"))
+if os.environ.get("ONLY_MODES"):
+    MODES = tuple(m for m in MODES if str(m[0]) in os.environ["ONLY_MODES"].split(","))
 if os.environ.get("EXTRA_MODE"):
     MODES += ((int(os.environ["EXTRA_MODE"]), "tcgen05-mode%s" % os.environ["EXTRA_MODE"]),)
 REPS = int(os.environ.get("REPS", 3))
