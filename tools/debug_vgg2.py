@@ -25,12 +25,13 @@ for name, dev, cudnn in (("cpu", "cpu", True), ("cuda", "cuda", True), ("cuda-no
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     m = build().to(dev)
-    xi = x.to(dev).requires_grad_(True)
+    xi = x.detach().clone().to(dev).requires_grad_(True)
     y = m(xi)
     if "dy" not in res: res["dy"] = torch.randn(y.shape)
     y.backward(res["dy"].to(dev))
     res[name] = {k: p.grad.detach().cpu() for k, p in m.named_parameters()}
     res[name]["y"] = y.detach().cpu(); res[name]["dx"] = xi.grad.detach().cpu()
+print("zeros in y(cpu): %d of %d" % (int((res["cpu"]["y"] == 0).sum()), res["cpu"]["y"].numel()))
 for name in ("cuda", "cuda-nocudnn"):
     for k in res["cpu"]:
         a, b = res[name][k], res["cpu"][k]
