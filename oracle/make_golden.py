@@ -209,6 +209,83 @@ def golden_prefix():
     print("ctc_prefix.npz")
 
 
+PLUMBING_UTTS = [("3830-12529-0005", 63040, "THE QUICK BROWN FOX JUMPS OVER"), ("3830-12529-0006", 56000, "THE LAZY DOG SLEEPS"),
+                 ("3830-12529-0007", 48000, "HELLO WORLD"), ("3830-12529-0008", 40000, "SPEECH")]
+
+
+def plumbing_tree(root, pcm, ext="flac"):
+    """LibriSpeech-shaped tree (corpus/librispeech.py:19-25,37) of 4 utterances cut from the sample wav: 16-bit PCM wav
+    data under the extension the dataset class globs for (SURVEY.md 8(c) shim 3) + a made-up transcript file."""
+    from scipy.io import wavfile
+    d = os.path.join(root, "LibriSpeech", "dev-clean", "3830", "12529")
+    os.makedirs(d, exist_ok=True)
+    with open(os.path.join(d, "3830-12529.trans.txt"), "w") as f:
+        for name, n, text in PLUMBING_UTTS:
+            f.write("%s %s\n" % (name, text))
+            with open(os.path.join(d, "%s.%s" % (name, ext)), "wb") as w:
+                wavfile.write(w, 16000, np.asarray(pcm[:n], dtype=np.int16))
+    return os.path.join(root, "LibriSpeech")
+
+
+def plumbing_config(cfg, path, vocab_file):
+    """The edits configs[0] needs on asr_example.yaml to run on the fixture (the same for the reference and for the
+    repo's config/b200/cfgA_example_vgg.yaml)."""
+    cfg["data"]["corpus"].update(path=path, train_split=["dev-clean"], dev_split=["dev-clean"], batch_size=2)
+    cfg["data"]["text"] = {"mode": "character", "vocab_file": vocab_file}
+    cfg["hparas"].update(max_step=2, curriculum=1)
+    return cfg
+
+
+def golden_plumbing():
+    """BASELINE configs[0]: the reference's own Solver (main.py:76-79 with --cpu) on the fixture, 2 train steps from
+    seed-0 weights; the attention loss and grad-norm of each step are the golden values."""
+    import argparse
+    import tempfile
+    import yaml
+    import bin.train_asr as ref_train
+    from bin.train_asr import Solver
+    # validation (step 1) draws attention maps through matplotlib, which is not installed: a blank image instead
+    ref_train.feat_to_fig = lambda feat: (torch.zeros(8, 8, 3), "HWC")
+    pcm = np.load(os.path.join(OUT, "frontend.npz"))["sample_pcm"]
+    tmp = tempfile.mkdtemp(prefix="b200asr_plumbing_")
+    path = plumbing_tree(tmp, pcm, "flac")
+    cfg = yaml.load(open(os.path.join(ref_shim.REF_ROOT, "config", "libri", "asr_example.yaml")), Loader=yaml.FullLoader)
+    cfg = plumbing_config(cfg, path, os.path.join(OUT, "character.vocab"))
+    own = yaml.load(open(os.path.join(os.path.dirname(OUT), "..", "config", "b200", "cfgA_example_vgg.yaml")),
+                    Loader=yaml.FullLoader)
+    own = plumbing_config(own, path, os.path.join(OUT, "character.vocab"))
+    assert own == cfg, "config/b200/cfgA_example_vgg.yaml drifted from the reference's asr_example.yaml"
+    paras = argparse.Namespace(config="asr_example.yaml", name="plumbing", logdir=os.path.join(tmp, "log"),
+                               ckpdir=os.path.join(tmp, "ckpt"), outdir=os.path.join(tmp, "out"), load=None, seed=0,
+                               cudnn_ctc=False, njobs=0, cpu=True, no_pin=True, test=False, no_msg=True, lm=False,
+                               amp=False, reserve_gpu=0, jit=False, gpu=False, pin_memory=False, verbose=False)
+    torch.set_num_threads(8)
+    np.random.seed(0)
+    solver = Solver(cfg, paras, "train")
+    solver.load_data()
+    torch.manual_seed(0)                     # the weights are a function of this seed alone (tests re-seed the same way)
+    solver.set_model()
+    losses, norms, names = [], [], []
+    real_backward, real_fetch = solver.backward, solver.fetch_data
+
+    def backward(loss):
+        losses.append(float(loss))
+        n = real_backward(loss)
+        norms.append(float(n))
+        return n
+
+    def fetch(data):
+        names.append(list(data[0]))
+        return real_fetch(data)
+
+    solver.backward, solver.fetch_data = backward, fetch
+    solver.exec()
+    out = {"loss": np.asarray(losses, np.float64), "grad_norm": np.asarray(norms, np.float64),
+           "names": np.asarray([",".join(n) for n in names]), "n_params": np.int64(sum(p.numel() for p in solver.model.parameters()))}
+    np.savez_compressed(os.path.join(OUT, "plumbing.npz"), **out)
+    print("plumbing.npz", losses, norms, names)
+
+
 def main():
     ref_shim.install()
     os.makedirs(OUT, exist_ok=True)
@@ -222,6 +299,7 @@ def main():
     golden_model("att", 41, 3, 16, 8, 12, 6)
     golden_model("vgg", 51, 2, 26, 40, 12, 5)
     golden_model("dot", 61, 3, 20, 8, 12, 5)
+    golden_plumbing()
 
 
 if __name__ == "__main__":

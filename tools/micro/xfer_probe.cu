@@ -58,9 +58,10 @@ __device__ __forceinline__ void bulk_g2s_mc(void* smem_dst, const void* gmem_src
         : "memory");
 }
 
-// mode: 0 A, 1 B, 2 C, 3 D, 4 E, 5 F, 6 M
+// mode: 0 A, 1 B, 2 C, 3 D, 4 E, 5 F, 6 M, 7 A', 8 E'
 __global__ void __launch_bounds__(THREADS, 1) probe(const uint8_t* shared_buf, const uint8_t* private_buf, unsigned* ctr,
-                                                    long long* out, int mode) {
+                                                    long long* out, int mode_in) {
+    int mode = mode_in;
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bar;
     __shared__ long long t_start;
@@ -74,7 +75,16 @@ __global__ void __launch_bounds__(THREADS, 1) probe(const uint8_t* shared_buf, c
     __syncthreads();
     if (mode == 6) cg::this_cluster().sync();
     long long acc = 0, worst = 0;
+    const bool rewrite = mode >= 7;                 // 7 = A, 8 = E, but every CTA REWRITES its 2 KB slice of the group buffer
+    if (rewrite) mode = mode == 7 ? 0 : 4;          // before each repetition (freshly written lines, like the real exchange)
     for (int r = 0; r < REPS; ++r) {
+        if (rewrite) {
+            uint8_t* mine = const_cast<uint8_t*>(src) + (size_t)(blockIdx.x % GROUP) * 2048;
+            if (tid < 128) {
+                const uint32_t v = (uint32_t)r * 2654435761u + tid;
+                asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1,%1,%1,%1};" ::"l"(mine + tid * 16), "r"(v) : "memory");
+            }
+        }
         grid_barrier(ctr, (unsigned)(r + 1) * gridDim.x);
         if (mode == 6) cg::this_cluster().sync();
         if (tid == 0) {
@@ -135,8 +145,9 @@ int main() {
     CK(cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(probe, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     const char* names[] = {"A 8 lanes x 8 KB bulk", "B 1 lane x 8 x 8 KB bulk", "C 1 lane x 64 KB bulk", "D 32 lanes x 2 KB bulk",
-                           "E 16 warps LDG.128+STS", "F 8 x 8 KB bulk, private buffers", "M cluster-8 multicast 8 KB each"};
-    for (int mode = 0; mode < 7; ++mode) {
+                           "E 16 warps LDG.128+STS", "F 8 x 8 KB bulk, private buffers", "M cluster-8 multicast 8 KB each",
+                           "A' 8 x 8 KB bulk, slices rewritten", "E' LDG.128+STS, slices rewritten"};
+    for (int mode = 0; mode < 9; ++mode) {
         CK(cudaMemset(ctr, 0, 4));
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(NCTA);
