@@ -213,10 +213,15 @@ def parity_check(pkg, step_fn, cfg, waves, lens, txt, dev, n_ref=8):
     if ctc_out is not None:
         w = torch.zeros(B, device=dev)
         w[:n] = 1.0 / (txt_len[:n].clamp_min(1).float() * n)
-        ctc, nll = pkg.ops.CTCLossFn.apply(ctc_out.transpose(0, 1), txt_dev, enc_len, txt_len, 0, w)
+        if isinstance(ctc_out, pkg.ops.CTCHeadOutput):     # fused CTC head (the train step's path): logits + row lse
+            ctc, nll = pkg.ops.CTCLossFn.apply(ctc_out.logits.transpose(0, 1), txt_dev, enc_len, txt_len, 0, w, ctc_out.lse)
+            lp_dev = ctc_out.materialize()
+        else:
+            ctc, nll = pkg.ops.CTCLossFn.apply(ctc_out.transpose(0, 1), txt_dev, enc_len, txt_len, 0, w)
+            lp_dev = ctc_out
         total = total + ctc * lam
         g.update(ctc_loss=float(ctc), nll=nll[:n].detach().cpu().double().numpy(),
-                 ctc_output=ctc_out[:n].detach().cpu(), ctc_argmax=model.last_ctc_argmax[:n].cpu())
+                 ctc_output=lp_dev[:n].detach().cpu(), ctc_argmax=model.last_ctc_argmax[:n].cpu())
     if att_out is not None:
         b, t, v = att_out.shape
         tgt = txt_dev[:, :t].clone()
@@ -355,8 +360,8 @@ def micro_bench(pkg, dev, peak):
 
             def step():
                 logits.grad = None
-                lp, _ = pkg.ops.log_softmax(logits, ctc_head=True)
-                crit(lp.transpose(0, 1), txt, Td, tld).backward()
+                head = pkg.ops.ctc_head(logits)                 # fused CTC head: row lse + arg-max, no V-wide output
+                crit(head.transpose(0, 1), txt, Td, tld).backward()
             run(step, ("log_softmax_fwd", "ctc_alpha_beta", "ctc_grad"))
             del logits
         for k in ("log_softmax_fwd", "ctc_alpha_beta", "ctc_grad"):
@@ -373,11 +378,12 @@ def micro_bench(pkg, dev, peak):
         ks = ["log_softmax_fwd_V%d" % V, "ctc_alpha_beta_V%d" % V, "ctc_grad_V%d" % V]
         if all(k in out for k in ks):
             ms = sum(out[k]["ms_per_1000_utt"] for k in ks)
-            by = out[ks[0]]["algorithmic_gbs"] * out[ks[0]]["ms_per_1000_utt"] * 1e6 * 0.5 + \
+            by = out[ks[0]]["algorithmic_gbs"] * out[ks[0]]["ms_per_1000_utt"] * 1e6 + \
                 out[ks[2]]["algorithmic_gbs"] * out[ks[2]]["ms_per_1000_utt"] * 1e6      # 4T'V (logits) + 8T'V
             out["ctc_total_V%d" % V] = {"ms_per_1000_utt": ms, "algorithmic_gbs": by / (ms * 1e-3) / 1e9,
                                         "frac_hbm": by / (ms * 1e-3) / 1e9 / peak,
-                                        "note": "logits -> log-softmax -> alpha/beta -> logit gradient; 12*T'*V bytes"}
+                                        "note": "fused CTC head: logits -> row lse + arg-max -> alpha/beta on logits - lse -> logit gradient; "
+                                                "12*T'*V bytes, no V-wide log-prob tensor"}
     return out
 
 

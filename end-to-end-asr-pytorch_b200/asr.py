@@ -68,7 +68,13 @@ class ASR(nn.Module):
         encode_feature, encode_len = self.encoder(audio_feature, feature_len)
 
         if self.enable_ctc:
-            ctc_output, self.last_ctc_argmax = ops.log_softmax(ops.linear3x(encode_feature, self.ctc_layer), ctc_head=True)
+            logits = ops.linear3x(encode_feature, self.ctc_layer)
+            if getattr(self, "fuse_ctc_head", False) and self.training and logits.is_cuda:
+                # train step: the log-softmax is fused into the CTC kernels (ops.CTCHeadOutput: logits + row lse + ids)
+                ctc_output = ops.ctc_head(logits)
+                self.last_ctc_argmax = ctc_output.ids
+            else:
+                ctc_output, self.last_ctc_argmax = ops.log_softmax(logits, ctc_head=True)
 
         if self.enable_att:
             decode_step = int(decode_step)

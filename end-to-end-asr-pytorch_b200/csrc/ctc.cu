@@ -30,14 +30,44 @@ __global__ void __launch_bounds__(256) log_softmax_fwd_kernel(const float* __res
     const float* xr = x + row * V;
     float m = NEG_INF, s = 0.f;
     int mi = 0x7fffffff;
-    for (int c = lane; c < V; c += 32) {
-        const float v = xr[c];
-        if (v > m) {
-            s = s * expf(m - v) + 1.f;  // m=-inf: s=0 -> 0*exp(-inf)=0
-            m = v;
-            mi = c;
-        } else {
-            s += expf(v - m);
+    if ((V & 3) == 0 && (reinterpret_cast<uintptr_t>(xr) & 15) == 0) {
+        // 128-bit streaming, two independent loads in flight per lane, ONE rescale per 8 values (the running (max, sum)
+        // pair is the only loop-carried dependency); the first index wins ties like torch.argmax
+        const float4* x4 = reinterpret_cast<const float4*>(xr);
+        const int n4 = V >> 2;
+        for (int c = lane; c < n4; c += 64) {
+            const float4 a = x4[c];
+            const bool two = c + 32 < n4;
+            const float4 b = two ? x4[c + 32] : make_float4(NEG_INF, NEG_INF, NEG_INF, NEG_INF);
+            float bm = a.x;
+            int bi = 4 * c;
+            if (a.y > bm) { bm = a.y; bi = 4 * c + 1; }
+            if (a.z > bm) { bm = a.z; bi = 4 * c + 2; }
+            if (a.w > bm) { bm = a.w; bi = 4 * c + 3; }
+            if (b.x > bm) { bm = b.x; bi = 4 * (c + 32); }
+            if (b.y > bm) { bm = b.y; bi = 4 * (c + 32) + 1; }
+            if (b.z > bm) { bm = b.z; bi = 4 * (c + 32) + 2; }
+            if (b.w > bm) { bm = b.w; bi = 4 * (c + 32) + 3; }
+            if (bm > m) {
+                s *= expf(m - bm);          // m = -inf: s = 0 -> 0 * exp(-inf) = 0
+                m = bm;
+                mi = bi;
+            }
+            if (m != NEG_INF) {
+                s += (expf(a.x - m) + expf(a.y - m)) + (expf(a.z - m) + expf(a.w - m));
+                if (two) s += (expf(b.x - m) + expf(b.y - m)) + (expf(b.z - m) + expf(b.w - m));
+            }
+        }
+    } else {
+        for (int c = lane; c < V; c += 32) {
+            const float v = xr[c];
+            if (v > m) {
+                s = s * expf(m - v) + 1.f;  // m=-inf: s=0 -> 0*exp(-inf)=0
+                m = v;
+                mi = c;
+            } else {
+                s += expf(v - m);
+            }
         }
     }
     // warp combine (first index wins ties)
@@ -55,7 +85,9 @@ __global__ void __launch_bounds__(256) log_softmax_fwd_kernel(const float* __res
     const float part = (m == NEG_INF) ? 0.f : s * expf(m - M);
     const float S = warp_sum(part);
     const float L = M + logf(S);
-    if ((V & 3) == 0) {
+    if (y == nullptr) {
+        // statistics only (fused CTC head): the log-probs are never materialised
+    } else if ((V & 3) == 0) {
         const float4* x4 = reinterpret_cast<const float4*>(xr);
         float4* y4 = reinterpret_cast<float4*>(y + row * V);
         for (int c = lane; c < (V >> 2); c += 32) {
@@ -103,6 +135,8 @@ __global__ void __launch_bounds__(256) log_softmax_bwd_kernel(const float* __res
 // ------------------------------------------------------------------------------------------
 struct CtcParams {
     const float* lp;     // log-probs, element (b,t,c) at lp[b*sb + t*st + c]
+    const float* lse;    // [B,T] or null.  Non-null: `lp` holds LOGITS and log-prob(b,t,c) = lp[...] - lse[b*T + t]
+                         // (the log-softmax of the CTC head fused into the loss: its V-wide output is never written)
     long long sb, st;
     const long long* targets;  // [B, L_max]
     const long long* in_len;   // [B]
@@ -188,14 +222,15 @@ __global__ void __launch_bounds__(1024) ctc_alpha_beta_kernel(CtcParams p) {
     // boundary row
     {
         const float* lpt = lpb + (long long)t0 * p.st;
+        const float ls = p.lse ? p.lse[(long long)b * p.T + t0] : 0.f;
         for (int s = threadIdx.x; s < S_max; s += blockDim.x) {
             float a = NEG_INF;
             if (!is_beta) {
-                if (s == 0) a = lpt[p.blank];
-                else if (s == 1 && Sb > 1) a = lpt[lab[1]];
+                if (s == 0) a = lpt[p.blank] - ls;
+                else if (s == 1 && Sb > 1) a = lpt[lab[1]] - ls;
             } else {
-                if (s == Sb - 1) a = lpt[p.blank];
-                else if (s == Sb - 2 && Sb > 1) a = lpt[lab[Sb - 2]];
+                if (s == Sb - 1) a = lpt[p.blank] - ls;
+                else if (s == Sb - 2 && Sb > 1) a = lpt[lab[Sb - 2]] - ls;
             }
             prev[s] = a;
             lat[(long long)t0 * S_max + s] = a;
@@ -204,11 +239,12 @@ __global__ void __launch_bounds__(1024) ctc_alpha_beta_kernel(CtcParams p) {
     for (int step = 1; step < Tb; ++step) {
         const int t = t0 + dt * step;
         const float* lpt = lpb + (long long)t * p.st;
+        const float ls = p.lse ? p.lse[(long long)b * p.T + t] : 0.f;
         __syncthreads();  // prev fully written
         for (int s = threadIdx.x; s < S_max; s += blockDim.x) {
             float v = NEG_INF;
             if (s < Sb) {
-                const float e = lpt[lab[s]];
+                const float e = lpt[lab[s]] - ls;
                 float a0 = prev[s], a1, a2;
                 if (!is_beta) {
                     a1 = (s > 0) ? prev[s - 1] : NEG_INF;
@@ -304,26 +340,29 @@ __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_alpha_beta_warp_kernel(Ctc
     const int t0 = is_beta ? Tb - 1 : 0;
     const int dt = is_beta ? -1 : 1;
     float a[R], e[R];
+    const float* lseb = p.lse ? p.lse + (long long)b * p.T : nullptr;
     {   // boundary row
         const float* lpt = lpb + (long long)t0 * p.st;
+        const float ls = lseb ? lseb[t0] : 0.f;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int s = lane * R + r;
             float v = NEG_INF;
             if (!is_beta) {
-                if (s == 0) v = lpt[p.blank];
-                else if (s == 1 && Sb > 1) v = lpt[lab[r]];
+                if (s == 0) v = lpt[p.blank] - ls;
+                else if (s == 1 && Sb > 1) v = lpt[lab[r]] - ls;
             } else {
-                if (s == Sb - 1) v = lpt[p.blank];
-                else if (s == Sb - 2 && Sb > 1) v = lpt[lab[r]];
+                if (s == Sb - 1) v = lpt[p.blank] - ls;
+                else if (s == Sb - 2 && Sb > 1) v = lpt[lab[r]] - ls;
             }
             a[r] = v;
             if (s < S_max) lat[(long long)t0 * S_max + s] = v;
         }
         if (Tb > 1) {
             const float* lpn = lpb + (long long)(t0 + dt) * p.st;
+            const float lsn = lseb ? lseb[t0 + dt] : 0.f;
 #pragma unroll
-            for (int r = 0; r < R; ++r) e[r] = lpn[lab[r]];
+            for (int r = 0; r < R; ++r) e[r] = lpn[lab[r]] - lsn;
         }
     }
     for (int step = 1; step < Tb; ++step) {
@@ -331,8 +370,9 @@ __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_alpha_beta_warp_kernel(Ctc
         float en[R];
         if (step + 1 < Tb) {
             const float* lpn = lpb + (long long)(t + dt) * p.st;
+            const float lsn = lseb ? lseb[t + dt] : 0.f;
 #pragma unroll
-            for (int r = 0; r < R; ++r) en[r] = lpn[lab[r]];
+            for (int r = 0; r < R; ++r) en[r] = lpn[lab[r]] - lsn;
         }
         // neighbours across the lane boundary
         float n1, n2;
@@ -440,6 +480,7 @@ __global__ void __launch_bounds__(CTC_GRAD_THREADS) ctc_grad_kernel(CtcParams p)
         float* gt = p.grad + (long long)b * p.sb + (long long)t * p.st;
         const float* lpt = p.lp + (long long)b * p.sb + (long long)t * p.st;
         const bool live = t < Tb;
+        const float ls = (p.lse && live) ? p.lse[(long long)b * p.T + t] : 0.f;
         if (vec4) {
             const float4* l4 = reinterpret_cast<const float4*>(lpt);
             float4* g4 = reinterpret_cast<float4*>(gt);
@@ -447,12 +488,13 @@ __global__ void __launch_bounds__(CTC_GRAD_THREADS) ctc_grad_kernel(CtcParams p)
                 float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (live) {
                     const float4 l = l4[c];
-                    o = make_float4(expf(l.x) * scale, expf(l.y) * scale, expf(l.z) * scale, expf(l.w) * scale);
+                    o = make_float4(expf(l.x - ls) * scale, expf(l.y - ls) * scale, expf(l.z - ls) * scale,
+                                    expf(l.w - ls) * scale);
                 }
                 g4[c] = o;
             }
         } else {
-            for (int c = threadIdx.x; c < V; c += blockDim.x) gt[c] = live ? expf(lpt[c]) * scale : 0.f;
+            for (int c = threadIdx.x; c < V; c += blockDim.x) gt[c] = live ? expf(lpt[c] - ls) * scale : 0.f;
         }
     }
     __syncthreads();
@@ -462,6 +504,7 @@ __global__ void __launch_bounds__(CTC_GRAD_THREADS) ctc_grad_kernel(CtcParams p)
         const float* lpt = p.lp + (long long)b * p.sb + (long long)t * p.st;
         const float* al = p.alpha + ((long long)b * p.T + t) * S_max;
         const float* be = p.beta + ((long long)b * p.T + t) * S_max;
+        const float ls = p.lse ? p.lse[(long long)b * p.T + t] : 0.f;
         float mx = NEG_INF;
         for (int s = threadIdx.x; s < Sb; s += blockDim.x) {
             const float v = al[s] + be[s];
@@ -479,14 +522,14 @@ __global__ void __launch_bounds__(CTC_GRAD_THREADS) ctc_grad_kernel(CtcParams p)
         for (int s = 2 * threadIdx.x; s < Sb; s += 2 * blockDim.x) part += e[s];
         const float tot_blank = block_sum(part, s_scratch);
         if (threadIdx.x == 0 && tot_blank > 0.f)
-            gt[p.blank] -= expf(logf(tot_blank) + m + nll - lpt[p.blank]) * scale;
+            gt[p.blank] -= expf(logf(tot_blank) + m + nll - (lpt[p.blank] - ls)) * scale;
         // labels (odd s): the thread owning the last occurrence walks the chain backwards
         for (int s = 2 * threadIdx.x + 1; s < Sb; s += 2 * blockDim.x) {
             if (is_last[s]) {
                 float tot = 0.f;
                 for (int q = s; q >= 0; q = prev_same[q]) tot += e[q];
                 const int l = lab[s];
-                if (l >= 0 && l != p.blank && tot > 0.f) gt[l] -= expf(logf(tot) + m + nll - lpt[l]) * scale;
+                if (l >= 0 && l != p.blank && tot > 0.f) gt[l] -= expf(logf(tot) + m + nll - (lpt[l] - ls)) * scale;
             }
         }
         __syncthreads();
@@ -499,7 +542,7 @@ using namespace b200asr;
 
 extern "C" int b200asr_log_softmax_fwd(const float* logits, float* log_probs, float* lse, long long* argmax,
                                        long long n_rows, int V, b200asr_stream stream) {
-    B200_REQUIRE(logits && log_probs, "log_softmax_fwd: null pointer");
+    B200_REQUIRE(logits && (log_probs || lse), "log_softmax_fwd: null pointer (log_probs may be NULL when lse is given)");
     B200_REQUIRE(n_rows >= 0 && V > 0, "log_softmax_fwd: bad sizes");
     if (n_rows == 0) return B200_OK;
     const int wpb = 8;
@@ -528,7 +571,7 @@ extern "C" size_t b200asr_ctc_workspace_bytes(int B, int T, int L_max) {
     return 2 * (size_t)B * T * S * sizeof(float) + 2 * (size_t)B * S * sizeof(int);
 }
 
-static int ctc_setup(CtcParams& p, const float* log_probs, long long stride_b, long long stride_t,
+static int ctc_setup(CtcParams& p, const float* log_probs, const float* row_lse, long long stride_b, long long stride_t,
                      const long long* targets, const long long* input_lengths, const long long* target_lengths, int B,
                      int T, int V, int L_max, int blank, float* nll, const float* grad_scale, const float* upstream,
                      float* grad, void* workspace, size_t workspace_bytes, const char* who) {
@@ -536,7 +579,7 @@ static int ctc_setup(CtcParams& p, const float* log_probs, long long stride_b, l
     B200_REQUIRE(B > 0 && T > 0 && V > 0 && L_max >= 0, "%s: bad sizes B=%d T=%d V=%d L=%d", who, B, T, V, L_max);
     B200_REQUIRE(blank >= 0 && blank < V, "%s: blank %d outside [0,%d)", who, blank, V);
     B200_REQUIRE(workspace_bytes >= b200asr_ctc_workspace_bytes(B, T, L_max), "%s: workspace too small", who);
-    p.lp = log_probs; p.sb = stride_b; p.st = stride_t; p.targets = targets; p.in_len = input_lengths;
+    p.lp = log_probs; p.lse = row_lse; p.sb = stride_b; p.st = stride_t; p.targets = targets; p.in_len = input_lengths;
     p.tgt_len = target_lengths; p.B = B; p.T = T; p.V = V; p.L_max = L_max; p.S_max = 2 * L_max + 1; p.blank = blank;
     p.nll = nll; p.scale = grad_scale; p.upstream = upstream; p.grad = grad;
     const size_t S = (size_t)p.S_max;
@@ -560,14 +603,14 @@ static int ctc_launch_grad(const CtcParams& p, cudaStream_t stream) {
     return B200_OK;
 }
 
-extern "C" int b200asr_ctc_fwd_bwd(const float* log_probs, long long stride_b, long long stride_t,
-                                   const long long* targets, const long long* input_lengths,
-                                   const long long* target_lengths, int B, int T, int V, int L_max, int blank,
-                                   float* nll, const float* grad_scale, float* grad, void* workspace,
-                                   size_t workspace_bytes, b200asr_stream stream) {
+static int ctc_fwd_bwd_impl(const float* log_probs, const float* row_lse, long long stride_b, long long stride_t,
+                            const long long* targets, const long long* input_lengths,
+                            const long long* target_lengths, int B, int T, int V, int L_max, int blank,
+                            float* nll, const float* grad_scale, float* grad, void* workspace,
+                            size_t workspace_bytes, b200asr_stream stream) {
     CtcParams p;
-    const int rc = ctc_setup(p, log_probs, stride_b, stride_t, targets, input_lengths, target_lengths, B, T, V, L_max,
-                             blank, nll, grad_scale, nullptr, grad, workspace, workspace_bytes, "ctc_fwd_bwd");
+    const int rc = ctc_setup(p, log_probs, row_lse, stride_b, stride_t, targets, input_lengths, target_lengths, B, T, V,
+                             L_max, blank, nll, grad_scale, nullptr, grad, workspace, workspace_bytes, "ctc_fwd_bwd");
     if (rc != B200_OK) return rc;
     const int need = (p.S_max + 31) / 32;      // extended-label positions per lane
     // The warp-synchronous kernel wins while a lane holds few positions (subword targets: S <= 128); for long
@@ -596,16 +639,54 @@ extern "C" int b200asr_ctc_fwd_bwd(const float* log_probs, long long stride_b, l
     return B200_OK;
 }
 
+extern "C" int b200asr_ctc_fwd_bwd(const float* log_probs, long long stride_b, long long stride_t,
+                                   const long long* targets, const long long* input_lengths,
+                                   const long long* target_lengths, int B, int T, int V, int L_max, int blank,
+                                   float* nll, const float* grad_scale, float* grad, void* workspace,
+                                   size_t workspace_bytes, b200asr_stream stream) {
+    return ctc_fwd_bwd_impl(log_probs, nullptr, stride_b, stride_t, targets, input_lengths, target_lengths, B, T, V,
+                            L_max, blank, nll, grad_scale, grad, workspace, workspace_bytes, stream);
+}
+
+extern "C" int b200asr_ctc_fwd_bwd_logits(const float* logits, const float* row_lse, long long stride_b,
+                                          long long stride_t, const long long* targets,
+                                          const long long* input_lengths, const long long* target_lengths, int B,
+                                          int T, int V, int L_max, int blank, float* nll, const float* grad_scale,
+                                          float* grad, void* workspace, size_t workspace_bytes, b200asr_stream stream) {
+    B200_REQUIRE(row_lse, "ctc_fwd_bwd_logits: null row_lse");
+    return ctc_fwd_bwd_impl(logits, row_lse, stride_b, stride_t, targets, input_lengths, target_lengths, B, T, V, L_max,
+                            blank, nll, grad_scale, grad, workspace, workspace_bytes, stream);
+}
+
+static int ctc_grad_impl(const float* log_probs, const float* row_lse, long long stride_b, long long stride_t,
+                         const long long* targets, const long long* input_lengths, const long long* target_lengths,
+                         int B, int T, int V, int L_max, int blank, const float* nll, const float* grad_scale,
+                         const float* upstream, float* grad, void* workspace, size_t workspace_bytes,
+                         b200asr_stream stream) {
+    B200_REQUIRE(grad, "ctc_grad: null gradient pointer");
+    CtcParams p;
+    const int rc = ctc_setup(p, log_probs, row_lse, stride_b, stride_t, targets, input_lengths, target_lengths, B, T, V,
+                             L_max, blank, const_cast<float*>(nll), grad_scale, upstream, grad, workspace,
+                             workspace_bytes, "ctc_grad");
+    if (rc != B200_OK) return rc;
+    return ctc_launch_grad(p, (cudaStream_t)stream);
+}
+
 extern "C" int b200asr_ctc_grad(const float* log_probs, long long stride_b, long long stride_t,
                                 const long long* targets, const long long* input_lengths,
                                 const long long* target_lengths, int B, int T, int V, int L_max, int blank,
                                 const float* nll, const float* grad_scale, const float* upstream, float* grad,
                                 void* workspace, size_t workspace_bytes, b200asr_stream stream) {
-    B200_REQUIRE(grad, "ctc_grad: null gradient pointer");
-    CtcParams p;
-    const int rc = ctc_setup(p, log_probs, stride_b, stride_t, targets, input_lengths, target_lengths, B, T, V, L_max,
-                             blank, const_cast<float*>(nll), grad_scale, upstream, grad, workspace, workspace_bytes,
-                             "ctc_grad");
-    if (rc != B200_OK) return rc;
-    return ctc_launch_grad(p, (cudaStream_t)stream);
+    return ctc_grad_impl(log_probs, nullptr, stride_b, stride_t, targets, input_lengths, target_lengths, B, T, V, L_max,
+                         blank, nll, grad_scale, upstream, grad, workspace, workspace_bytes, stream);
+}
+
+extern "C" int b200asr_ctc_grad_logits(const float* logits, const float* row_lse, long long stride_b,
+                                       long long stride_t, const long long* targets, const long long* input_lengths,
+                                       const long long* target_lengths, int B, int T, int V, int L_max, int blank,
+                                       const float* nll, const float* grad_scale, const float* upstream, float* grad,
+                                       void* workspace, size_t workspace_bytes, b200asr_stream stream) {
+    B200_REQUIRE(row_lse, "ctc_grad_logits: null row_lse");
+    return ctc_grad_impl(logits, row_lse, stride_b, stride_t, targets, input_lengths, target_lengths, B, T, V, L_max,
+                         blank, nll, grad_scale, upstream, grad, workspace, workspace_bytes, stream);
 }

@@ -22,9 +22,14 @@
 // TMEM allocation, 2..9 = splitters, which also own the second accumulation level: the TMEM chain is cut every 4 K
 // blocks, the partial tile is drained (tcgen05.ld 32x32b) into 128 fp32 registers per thread and summed there, while
 // the tensor core fills the other of two TMEM buffers; the epilogue (+ bias [+ C], 128-bit stores) runs from those
-// registers.  Shared memory: three TMA stages of raw tiles (A 16 + B 32 KB) and ONE buffer of residual tiles: the
-// issuer runs the hi.hi products of K block i+1 (raw tiles only) while the splitters refill the residual buffer that the
-// cross products of K block i have just released, so the loads have two K blocks of slack.
+// registers.  Two shared-memory stages of 96 KB (A 16 + B 32 raw, the same again for the residuals).
+//
+// What bounds it (measured, profiles/r02_ncu_lstm_gemm.txt + tools/time_gemm.py): shared-memory bandwidth.  Per 32-wide
+// K block the tensor core reads 12 x (4 + 8) KB of operands, TMA writes 48 KB and the splitters read and write 48 KB
+// each = 288 KB ~ 2250 cycles at 128 B/clk against 1536 cycles of MMA time: 225 TFLOP/s fp32-equivalent (675 TF/s of
+// TF32 issue, ~60 % of the pipe; ncu: tensor pipe 45-50 % active at M = 8192) - on par with the three cuBLAS TF32 GEMMs
+// + split passes it replaces (tools/time_gemm.py).  Tried and rejected: three raw stages with a single residual
+// buffer (the splitter pass, ~1300 cycles, then serialises with the cross products: 187 TFLOP/s).
 //
 // Shared-memory images.  K-major operand, R rows: R consecutive 128-byte rows (32 k each), 128-byte swizzle; one MMA
 // (8 k) advances the descriptor start by 32 bytes.  MN-major operand, R columns: R/32 boxes of [32 k][32 columns] =
@@ -40,12 +45,10 @@ namespace b200asr {
 namespace {
 
 constexpr int G_BM = 128, G_BN = 256, G_BK = 32;
-constexpr int G_STAGES = 3;                  // raw (TMA) stages; the residual tiles have ONE buffer (see the issuer)
+constexpr int G_STAGES = 2;
 constexpr int G_A_BYTES = G_BM * G_BK * 4;      // 16 KB
 constexpr int G_B_BYTES = G_BN * G_BK * 4;      // 32 KB
-constexpr int G_STAGE_BYTES = G_A_BYTES + G_B_BYTES;          // 48 KB raw tiles per stage
-constexpr int G_LO_OFFSET = G_STAGES * G_STAGE_BYTES;         // the residual tiles [A lo | B lo] follow the raw stages
-constexpr int G_SMEM_TILES = G_LO_OFFSET + G_STAGE_BYTES;     // 192 KB
+constexpr int G_STAGE_BYTES = 2 * (G_A_BYTES + G_B_BYTES);
 constexpr int G_SPLIT_WARPS = 8;
 constexpr int G_THREADS = 32 * (2 + G_SPLIT_WARPS);
 constexpr int G_BOX = 32 * G_BK * 4;            // one MN-major box: 32 columns x 32 k
@@ -101,12 +104,11 @@ template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(G_THREADS, 1)
 gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmArgs g) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    // raw stage s: [A raw | B raw]; then one [A lo | B lo]
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + G_SMEM_TILES);               // [G_STAGES] TMA landed
-    uint64_t* empty = full + G_STAGES;                                               // [G_STAGES] MMAs of the stage retired
-    uint64_t* split = empty + G_STAGES;                                              // residual tiles written
-    uint64_t* lo_free = split + 1;                                                   // their MMAs retired
-    uint64_t* acc_full = lo_free + 1;                                                // [2] a chunk's MMAs retired
+    // stage s: [A raw | B raw | A lo | B lo]
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + G_STAGES * G_STAGE_BYTES);   // TMA landed
+    uint64_t* split = full + G_STAGES;                                               // residual tiles written
+    uint64_t* empty = split + G_STAGES;                                              // MMAs of the stage retired
+    uint64_t* acc_full = empty + G_STAGES;                                           // [2] a chunk's MMAs retired
     uint64_t* acc_free = acc_full + 2;                                               // [2] the chunk has been drained
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 2);
 
@@ -127,10 +129,9 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     if (tid == 0) {
         for (int s = 0; s < G_STAGES; ++s) {
             mbar_init(&full[s], 1);
+            mbar_init(&split[s], G_SPLIT_WARPS);
             mbar_init(&empty[s], 1);
         }
-        mbar_init(split, G_SPLIT_WARPS);
-        mbar_init(lo_free, 1);
         for (int j = 0; j < 2; ++j) {
             mbar_init(&acc_full[j], 1);
             mbar_init(&acc_free[j], G_SPLIT_WARPS);
@@ -177,32 +178,22 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                     mbar_wait(&acc_free[buf], (uint32_t)(((c >> 1) - 1) & 1));
                     umma::fence_after_sync();
                 }
+                mbar_wait(&split[s], (uint32_t)((i / G_STAGES) & 1));
+                umma::fence_after_sync();
                 const uint32_t d = tmem + 256u * buf;
                 const uint32_t a = smem_u32(smem + s * G_STAGE_BYTES), b = a + G_A_BYTES;
-                const uint32_t alo = smem_u32(smem + G_LO_OFFSET), blo = alo + G_A_BYTES;
-                // the hi.hi products only need the raw tiles: issue them as soon as the TMA has landed, so that the
-                // splitters' pass over the stage overlaps a third of its tensor-core work
-                mbar_wait(&full[s], (uint32_t)((i / G_STAGES) & 1));
-                umma::fence_after_sync();
-#pragma unroll
-                for (int k4 = 0; k4 < G_BK / 8; ++k4) {
-                    const uint64_t da = A_MN ? desc_mn_sw128(a + k4 * 1024) : umma::desc_k_sw128(a + k4 * 32);
-                    const uint64_t db = B_MN ? desc_mn_sw128(b + k4 * 1024) : umma::desc_k_sw128(b + k4 * 32);
-                    umma::mma_ss<umma::FMT_TF32>(d, da, db, idesc, (j | k4) != 0);
-                }
-                mbar_wait(split, (uint32_t)(i & 1));
-                umma::fence_after_sync();
+                const uint32_t alo = b + G_B_BYTES, blo = alo + G_A_BYTES;
 #pragma unroll
                 for (int k4 = 0; k4 < G_BK / 8; ++k4) {
                     const uint64_t da = A_MN ? desc_mn_sw128(a + k4 * 1024) : umma::desc_k_sw128(a + k4 * 32);
                     const uint64_t db = B_MN ? desc_mn_sw128(b + k4 * 1024) : umma::desc_k_sw128(b + k4 * 32);
                     const uint64_t dal = A_MN ? desc_mn_sw128(alo + k4 * 1024) : umma::desc_k_sw128(alo + k4 * 32);
                     const uint64_t dbl = B_MN ? desc_mn_sw128(blo + k4 * 1024) : umma::desc_k_sw128(blo + k4 * 32);
+                    umma::mma_ss<umma::FMT_TF32>(d, da, db, idesc, (j | k4) != 0);
                     umma::mma_ss<umma::FMT_TF32>(d, dal, db, idesc, 1);
                     umma::mma_ss<umma::FMT_TF32>(d, da, dbl, idesc, 1);
                 }
                 umma::commit(&empty[s]);
-                umma::commit(lo_free);
                 if (j == G_CH - 1 || i == nkb - 1) umma::commit(&acc_full[buf]);
             }
         }
@@ -240,9 +231,8 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         for (int i = 0; i < nkb; ++i) {
             const int s = i % G_STAGES;
             mbar_wait(&full[s], (uint32_t)((i / G_STAGES) & 1));
-            if (i > 0) mbar_wait(lo_free, (uint32_t)((i - 1) & 1));     // the cross products of K block i-1 have retired
             const float4* src = reinterpret_cast<const float4*>(smem + s * G_STAGE_BYTES);
-            float4* dst = reinterpret_cast<float4*>(smem + G_LO_OFFSET);
+            float4* dst = reinterpret_cast<float4*>(smem + s * G_STAGE_BYTES + G_A_BYTES + G_B_BYTES);
 #pragma unroll 4
             for (int j = st_tid; j < a_vec; j += 32 * G_SPLIT_WARPS) {
                 const float4 v = src[j];
@@ -255,9 +245,9 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            if (lane == 0) g_arrive(split);
-            // chunk i/G_CH - 1 ended with K block i-1, whose MMAs retired before lo_free let this iteration start
-            if (i >= G_CH && (i % G_CH) == 0) drain(next_drain++);
+            if (lane == 0) g_arrive(&split[s]);
+            // chunk i/G_CH - 1 retired at the latest when K block i-2 left the 2-stage ring: drain it now
+            if (i >= G_CH && (i % G_CH) == 1) drain(next_drain++);
         }
         while (next_drain < nchunks) drain(next_drain++);
         // ---------------------------------------------------------------- epilogue: registers -> C
@@ -383,7 +373,7 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, GemmArgs g, void* ws, s
     g.kb_per_split = (g.KB + nsplit - 1) / nsplit;
     nsplit = (g.KB + g.kb_per_split - 1) / g.kb_per_split;       // no empty slices
     g.partial = reinterpret_cast<float*>(ws);
-    const size_t smem = (size_t)G_SMEM_TILES + 256;
+    const size_t smem = (size_t)G_STAGES * G_STAGE_BYTES + 256;
     auto fn = gemm3x_kernel<A_MN, B_MN>;
     B200_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((g.N + G_BN - 1) / G_BN, (g.M + G_BM - 1) / G_BM, nsplit);

@@ -322,9 +322,7 @@ __global__ void __launch_bounds__(32 * (UBP + 2 + UL_MAX_CTRL), 1) bilstm_fwd_um
                     umma::fence_after_sync();
                     if (a == 0) UL_TRACE(1);
                     if (a == NA - 1) UL_TRACE(6);
-                    if (a == 1) UL_TRACE(12);
-                    if (a == 3) UL_TRACE(13);
-                    if (a == 5) UL_TRACE(14);
+                    if (a == NA / 2) UL_TRACE(14);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const uint64_t da = umma::desc_k_sw128(a_base + a * UL_ATOM_A + j * 32);

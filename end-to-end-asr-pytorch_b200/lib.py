@@ -36,6 +36,10 @@ SIGNATURES = {
                                     _P, _P, c_size_t, _P]),
     "b200asr_ctc_grad": (c_int, [_P, c_longlong, c_longlong, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P,
                                  _P, _P, c_size_t, _P]),
+    "b200asr_ctc_fwd_bwd_logits": (c_int, [_P, _P, c_longlong, c_longlong, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P,
+                                           _P, _P, _P, c_size_t, _P]),
+    "b200asr_ctc_grad_logits": (c_int, [_P, _P, c_longlong, c_longlong, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P,
+                                        _P, _P, _P, _P, c_size_t, _P]),
     "b200asr_ctc_prefix_score": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P]),
     "b200asr_bilstm_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "b200asr_bilstm_plan": (c_int, [c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),

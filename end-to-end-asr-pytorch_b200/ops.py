@@ -417,6 +417,56 @@ def log_softmax(logits, ctc_head=False):
     return LogSoftmaxFn.apply(logits, ctc_head)
 
 
+class CTCHeadOutput:
+    """`ctc_output` of ASR.forward when the CTC head is fused into the loss (train step): the logits [B, T, V], their
+    per-row log-sum-exp [B, T] and the arg-max ids [B, T] instead of the V-wide log-prob tensor, which the train step
+    never reads except through CTCLoss (bin/train_asr.py:123-124) and arg-max (cal_er, util.py:113-127).  Quacks
+    like the tensor for exactly those uses; `materialize()` gives the log-probs [B, T, V] (detached) on demand."""
+
+    def __init__(self, logits, lse, ids, time_major=False):
+        self.logits, self.lse, self.ids, self.time_major = logits, lse, ids, time_major
+
+    @property
+    def shape(self):
+        s = self.logits.shape
+        return torch.Size((s[1], s[0], s[2])) if self.time_major else s
+
+    @property
+    def device(self):
+        return self.logits.device
+
+    def transpose(self, a, b):
+        if {a % 3, b % 3} != {0, 1}:
+            raise L.B200AsrError("CTCHeadOutput only swaps batch and time")
+        return CTCHeadOutput(self.logits, self.lse, self.ids, not self.time_major)
+
+    def argmax(self, dim=-1):
+        if dim not in (-1, 2):
+            raise L.B200AsrError("CTCHeadOutput.argmax is over the classes")
+        return self.ids.transpose(0, 1) if self.time_major else self.ids
+
+    def detach(self):
+        return CTCHeadOutput(self.logits.detach(), self.lse, self.ids, self.time_major)
+
+    def materialize(self):
+        lp = self.logits.detach() - self.lse.unsqueeze(-1)
+        return lp.transpose(0, 1) if self.time_major else lp
+
+
+def ctc_head(logits):
+    """logits [B, T, V] -> CTCHeadOutput: one pass over the logits for the row statistics (lse + arg-max), nothing
+    V-wide written."""
+    lib = L.load()
+    x = _f32c(logits)
+    B, T, V = x.shape
+    lse = torch.empty((B, T), device=x.device, dtype=torch.float32)
+    am = torch.empty((B, T), device=x.device, dtype=torch.int64)
+    with L.timed("log_softmax_fwd", 4 * B * T * V):
+        L.check(lib.b200asr_log_softmax_fwd(L.ptr(x), None, L.ptr(lse), L.ptr(am), B * T, V, L.stream()),
+                "log_softmax_fwd(stats)")
+    return CTCHeadOutput(x, lse, am)
+
+
 class CTCLossFn(Function):
     """sum_b weight_b * nll_b.  Forward = the alpha/beta lattice kernels (nll); backward = ONE gradient kernel that
     already multiplies by weight_b and by the upstream scalar, so no scaling pass over [T,B,V] follows.
@@ -426,9 +476,13 @@ class CTCLossFn(Function):
     """
 
     @staticmethod
-    def forward(ctx, log_probs, targets, input_lengths, target_lengths, blank, weights):
+    def forward(ctx, log_probs, targets, input_lengths, target_lengths, blank, weights, row_lse=None):
+        """row_lse [B, T] given: `log_probs` holds the LOGITS of the CTC head and the log-softmax is fused into the
+        lattice / gradient kernels (b200asr_ctc_*_logits); the returned gradient is then the logit gradient."""
         lib = L.load()
         if log_probs.dtype != torch.float32 or log_probs.stride(2) != 1:
+            if row_lse is not None:
+                raise L.B200AsrError("fused CTC head: logits must be fp32 with unit class stride")
             log_probs = log_probs.float().contiguous()
         T, B, V = log_probs.shape
         dev = log_probs.device
@@ -442,11 +496,21 @@ class CTCLossFn(Function):
         nll = torch.empty(B, device=dev, dtype=torch.float32)
         ws_bytes = lib.b200asr_ctc_workspace_bytes(B, T, Lmax)
         ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+        if row_lse is not None:
+            row_lse = _f32c(row_lse)
+            assert tuple(row_lse.shape) == (B, T)
         with L.timed("ctc_alpha_beta", 4 * B):
-            L.check(lib.b200asr_ctc_fwd_bwd(L.ptr(log_probs), log_probs.stride(1), log_probs.stride(0),
-                                            L.ptr(targets), L.ptr(il), L.ptr(tl), B, T, V, Lmax, blank, L.ptr(nll),
-                                            L.ptr(w), None, L.ptr(ws), ws_bytes, L.stream()), "ctc_fwd_bwd")
+            if row_lse is None:
+                L.check(lib.b200asr_ctc_fwd_bwd(L.ptr(log_probs), log_probs.stride(1), log_probs.stride(0),
+                                                L.ptr(targets), L.ptr(il), L.ptr(tl), B, T, V, Lmax, blank, L.ptr(nll),
+                                                L.ptr(w), None, L.ptr(ws), ws_bytes, L.stream()), "ctc_fwd_bwd")
+            else:
+                L.check(lib.b200asr_ctc_fwd_bwd_logits(L.ptr(log_probs), L.ptr(row_lse), log_probs.stride(1),
+                                                       log_probs.stride(0), L.ptr(targets), L.ptr(il), L.ptr(tl), B, T,
+                                                       V, Lmax, blank, L.ptr(nll), L.ptr(w), None, L.ptr(ws), ws_bytes,
+                                                       L.stream()), "ctc_fwd_bwd_logits")
         ctx.save_for_backward(log_probs, targets, il, tl, w, nll, ws)
+        ctx.row_lse = row_lse
         ctx.blank = blank
         ctx.mark_non_differentiable(nll)
         loss = (nll * w).sum()
@@ -462,11 +526,17 @@ class CTCLossFn(Function):
         up = _f32c(gloss.reshape(1))
         # algorithmic bytes: read the log-probs and write the gradient once each
         with L.timed("ctc_grad", 8 * T * V * B):
-            L.check(lib.b200asr_ctc_grad(L.ptr(log_probs), log_probs.stride(1), log_probs.stride(0), L.ptr(targets),
-                                         L.ptr(il), L.ptr(tl), B, T, V, targets.shape[1], ctx.blank, L.ptr(nll),
-                                         L.ptr(w), L.ptr(up), L.ptr(grad), L.ptr(ws), ws.numel(), L.stream()),
-                    "ctc_grad")
-        return grad, None, None, None, None, None
+            if ctx.row_lse is None:
+                L.check(lib.b200asr_ctc_grad(L.ptr(log_probs), log_probs.stride(1), log_probs.stride(0),
+                                             L.ptr(targets), L.ptr(il), L.ptr(tl), B, T, V, targets.shape[1], ctx.blank,
+                                             L.ptr(nll), L.ptr(w), L.ptr(up), L.ptr(grad), L.ptr(ws), ws.numel(),
+                                             L.stream()), "ctc_grad")
+            else:
+                L.check(lib.b200asr_ctc_grad_logits(L.ptr(log_probs), L.ptr(ctx.row_lse), log_probs.stride(1),
+                                                    log_probs.stride(0), L.ptr(targets), L.ptr(il), L.ptr(tl), B, T, V,
+                                                    targets.shape[1], ctx.blank, L.ptr(nll), L.ptr(w), L.ptr(up),
+                                                    L.ptr(grad), L.ptr(ws), ws.numel(), L.stream()), "ctc_grad_logits")
+        return grad, None, None, None, None, None, None
 
 
 class CTCLoss(torch.nn.Module):
@@ -483,6 +553,12 @@ class CTCLoss(torch.nn.Module):
         self.global_batch = None
 
     def forward(self, log_probs, targets, input_lengths, target_lengths):
+        row_lse = None
+        if isinstance(log_probs, CTCHeadOutput):       # fused head: logits + row lse instead of V-wide log-probs
+            if not log_probs.time_major:
+                raise L.B200AsrError("CTCLoss expects [T, B, V] (pass ctc_output.transpose(0, 1))")
+            row_lse = log_probs.lse
+            log_probs = log_probs.logits.transpose(0, 1)
         B = log_probs.shape[1]
         dev = log_probs.device
         tl = torch.as_tensor(target_lengths, dtype=torch.int64).to(dev)
@@ -493,7 +569,7 @@ class CTCLoss(torch.nn.Module):
             w = torch.ones(B, device=dev, dtype=torch.float32)
         else:
             raise NotImplementedError("reduction=%s" % self.reduction)
-        loss, nll = CTCLossFn.apply(log_probs, targets, input_lengths, tl, self.blank, w)
+        loss, nll = CTCLossFn.apply(log_probs, targets, input_lengths, tl, self.blank, w, row_lse)
         self.last_nll = nll
         return loss
 

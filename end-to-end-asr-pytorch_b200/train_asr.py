@@ -2,6 +2,8 @@
 Solver(config, paras, mode).load_data() / .set_model() / .exec(), same loss assembly, validation and checkpoints.
 Differences that make it B200-native: waveforms go to the GPU and the fused front end runs there (fetch_data);
 CTC / CE / attention / LSTM are the sm_100a kernels; one process per GPU with a single NCCL grad all-reduce."""
+import os
+
 import torch
 
 from . import ops
@@ -43,6 +45,8 @@ class Solver(BaseSolver):
         init_adadelta = self.config["hparas"]["optimizer"] == "Adadelta"
         self.model = ASR(self.feat_dim, self.vocab_size, init_adadelta, **self.config["model"]).to(self.device)
         self.verbose(self.model.create_msg())
+        # in model.train() mode ctc_output is only consumed by CTCLoss and arg-max (exec() below): fuse the CTC head
+        self.model.fuse_ctc_head = os.environ.get("B200ASR_FUSE_CTC", "1") == "1"
         self.seq_loss = lambda logits, target: ops.cross_entropy(logits, target, ignore_index=0)
         self.ctc_loss = ops.CTCLoss(blank=0, zero_infinity=False)
         self.emb_fuse, self.emb_reg = False, False

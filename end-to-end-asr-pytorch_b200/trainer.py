@@ -1,6 +1,8 @@
 """The train step (the hot path) as one object: waveforms -> fused front end -> ASR.forward -> CTC (+CE) ->
 backward -> [grad all-reduce] -> fused norm/clip/update.  Used by the Solver mirror (train_asr.py) and bench.py.
 Mirrors bin/train_asr.py:95-137 + src/solver.py:76-91 of the reference."""
+import os
+
 import torch
 import torch.nn.functional as F
 
@@ -21,6 +23,8 @@ class TrainStep:
         init_adadelta = config["hparas"]["optimizer"] == "Adadelta"
         self.model = ASR(self.feat_dim, vocab_size, init_adadelta, **config["model"]).to(self.device)
         self.model.train()
+        # the train step reads ctc_output only through CTCLoss and arg-max: fuse the log-softmax into the CTC kernels
+        self.model.fuse_ctc_head = os.environ.get("B200ASR_FUSE_CTC", "1") == "1"
         self.ctc_loss = ops.CTCLoss(blank=0, zero_infinity=False)
         self.optimizer = Optimizer([{"params": self.model.parameters()}], **config["hparas"])
         self.dp.attach(self.optimizer, self.model)

@@ -69,7 +69,7 @@ B200ASR_API int b200asr_delta_cmvn_fwd(const float* fbank, const int* n_frames, 
 
 /* ---- K9: log-softmax over the vocabulary (src/asr.py:96) -------------------------------------------------
  * log_probs may alias logits.  lse [n_rows] and argmax [n_rows] (int64; util.py:117-118 / test_asr.py:116-118)
- * are optional (NULL).                                                                                      */
+ * are optional (NULL); log_probs may be NULL when lse is given (statistics only, see b200asr_ctc_fwd_bwd_logits). */
 B200ASR_API int b200asr_log_softmax_fwd(const float* logits, float* log_probs, float* lse, long long* argmax,
                             long long n_rows, int V, b200asr_stream stream);
 B200ASR_API int b200asr_log_softmax_bwd(const float* log_probs, const float* grad_out, float* grad_in, long long n_rows,
@@ -95,6 +95,22 @@ B200ASR_API int b200asr_ctc_grad(const float* log_probs, long long stride_b, lon
                      const long long* input_lengths, const long long* target_lengths, int B, int T, int V,
                      int L_max, int blank, const float* nll, const float* grad_scale, const float* upstream,
                      float* grad, void* workspace, size_t workspace_bytes, b200asr_stream stream);
+
+/* The CTC head fused into the loss (src/asr.py:96 + bin/train_asr.py:123-124 in one pass structure): the same two
+ * calls on LOGITS plus the per-row log-sum-exp  row_lse[b * T + t]  (b200asr_log_softmax_fwd with log_probs = NULL
+ * writes only lse + argmax).  log-prob(b,t,c) = logits[...] - row_lse[b*T + t] is formed on the fly, the V-wide log-prob
+ * tensor is never written or re-read, and `grad` IS the logit gradient (exp(x - lse) - occupancy has zero class sum,
+ * SURVEY.md F9):  12*T*V bytes per utterance (read logits twice, write the gradient once) instead of 28*T*V.      */
+B200ASR_API int b200asr_ctc_fwd_bwd_logits(const float* logits, const float* row_lse, long long stride_b, long long stride_t,
+                               const long long* targets, const long long* input_lengths,
+                               const long long* target_lengths, int B, int T, int V, int L_max, int blank, float* nll,
+                               const float* grad_scale, float* grad, void* workspace, size_t workspace_bytes,
+                               b200asr_stream stream);
+B200ASR_API int b200asr_ctc_grad_logits(const float* logits, const float* row_lse, long long stride_b, long long stride_t,
+                            const long long* targets, const long long* input_lengths, const long long* target_lengths,
+                            int B, int T, int V, int L_max, int blank, const float* nll, const float* grad_scale,
+                            const float* upstream, float* grad, void* workspace, size_t workspace_bytes,
+                            b200asr_stream stream);
 
 /* ---- CTC prefix scoring (joint CTC/attention beam search) ---------------------------------
  * replaces CTCPrefixScore.cheap_compute (src/ctc.py:81-116), called from src/decode.py:129-131 once per hypothesis

@@ -177,6 +177,47 @@ def test_ctc_random_vs_aten_cpu(pkg, B, T, V, Lmax, head):
     assert torch.equal(lp.argmax(-1).cpu(), lpr.argmax(-1))
 
 
+@pytest.mark.parametrize("B,T,V,Lmax", [(4, 50, 31, 20), (3, 37, 500, 9), (6, 149, 5000, 40), (2, 300, 31, 141), (5, 64, 30, 1)])
+def test_ctc_fused_head_vs_aten_cpu(pkg, B, T, V, Lmax):
+    """The train step's CTC path: ops.ctc_head (row lse + arg-max, no V-wide log-prob tensor) -> CTCLoss on logits - lse
+    -> the gradient kernel writes the LOGIT gradient.  Same loss / per-utterance nll / logit gradient / ids as
+    log_softmax + F.ctc_loss on the CPU, and bit-identical nll to the unfused kernels."""
+    gen = torch.Generator().manual_seed(B * 1000 + T + 7)
+    logits = torch.randn(B, T, V, generator=gen)
+    tl = torch.randint(1, max(Lmax, 2), (B,), generator=gen)
+    tl[0] = max(Lmax - 1, 1)
+    il = torch.randint(T // 2 + Lmax, T + 1, (B,), generator=gen).clamp(max=T)
+    il[0] = T
+    txt = torch.zeros(B, max(Lmax, 2), dtype=torch.long)
+    for b in range(B):
+        txt[b, :tl[b]] = torch.randint(1, V, (int(tl[b]),), generator=gen)
+        if tl[b] > 2:
+            txt[b, 1] = txt[b, 0]
+    x = logits.to(DEV).requires_grad_(True)
+    head = pkg.ops.ctc_head(x)
+    assert isinstance(head, pkg.ops.CTCHeadOutput) and tuple(head.shape) == (B, T, V)
+    crit = pkg.CTCLoss(blank=0)
+    loss = crit(head.transpose(0, 1), txt.to(DEV), il.to(DEV), tl.to(DEV)) * 0.3                # upstream scale
+    nll_fused = crit.last_nll.clone()
+    loss.backward()
+    xr = logits.clone().requires_grad_(True)
+    lpr = F.log_softmax(xr, -1)
+    ref = F.ctc_loss(lpr.transpose(0, 1), txt, il, tl, blank=0, reduction="mean", zero_infinity=False) * 0.3
+    ref.backward()
+    assert abs(loss.item() - ref.item()) < 1e-4 * abs(ref.item())
+    assert scaled_err(x.grad.cpu().numpy(), xr.grad.numpy()) < (1e-4 if V < 1000 else 1e-3)
+    assert torch.equal(head.argmax(-1).cpu(), lpr.argmax(-1))                                   # greedy ids bit exact
+    assert rel_err(head.materialize().cpu().numpy(), lpr.detach().numpy()) < 1e-5
+    # unfused kernels on materialised log-probs: same lattice arithmetic up to the rounding of x - lse
+    x2 = logits.to(DEV).requires_grad_(True)
+    lp, _ = pkg.ops.log_softmax(x2, ctc_head=True)
+    crit(lp.transpose(0, 1), txt.to(DEV), il.to(DEV), tl.to(DEV))
+    assert rel_err(nll_fused.cpu().numpy(), crit.last_nll.cpu().numpy()) < 1e-6
+    # padded frames get a zero gradient, rows beyond the batch's lengths are never touched by NaNs
+    for b in range(B):
+        assert float(x.grad[b, int(il[b]):].abs().max()) == 0.0 if int(il[b]) < T else True
+
+
 # ------------------------------------------------------------------------------------------- LSTM
 def _torch_lstm(I, H, bidir, seed):
     torch.manual_seed(seed)

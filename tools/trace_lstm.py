@@ -35,7 +35,7 @@ for slot, name in [(8, "publisher: all epilogue warps arrived"), (9, "publisher:
     print("  t%-2d - t5   %7.0f   %s" % (slot, (t[lo:hi, slot] - t[lo:hi, 5]).mean(), name))
 for slot, name in [(15, "control lane NA-1: last atom producers done")]:
     print("  t%-2d - t5   %7.0f   %s" % (slot, (t[lo:hi, slot] - t[lo:hi, 5]).mean(), name))
-for slot, name in [(1, "MMA lane: atom 0 landed"), (12, "MMA lane: passed atom 1"), (13, "MMA lane: passed atom 3"),
-                   (14, "MMA lane: passed atom 5"), (6, "MMA lane: last atom landed"), (2, "MMA lane: commit issued"),
+for slot, name in [(1, "MMA lane: passed atom 0"), (14, "MMA lane: passed atom NA/2"), (6, "MMA lane: passed last atom"),
+                   (2, "MMA lane: commit issued"),
                    (3, "epilogue: accumulator complete"), (0, "next step start")]:
     print("  t%-2d[s+1] - t5[s] %7.0f   %s" % (slot, (t[lo + 1:hi + 1, slot] - t[lo:hi, 5]).mean(), name))
