@@ -48,6 +48,8 @@ struct AttnParams {
     float* dvalue;        // [B, T, E]
     float* dprev;         // [B, T]
     float* wpart;         // [B*CS, P], P = D*K + K*W + D + 1   (d w_proj | d w_conv | d w_e | d b_e)
+    int accumulate;       // != 0: d(key) and wpart are ADDED to (the decode loop's per-batch accumulators); dvalue may
+                          // then be null (d(value) = sum over steps of attn (x) dctx is formed once after the loop)
 };
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
@@ -236,7 +238,7 @@ __global__ void __launch_bounds__(1024) locattn_bwd_kernel(AttnParams p) {
                     part += dc.x * v.x + dc.y * v.y + dc.z * v.z + dc.w * v.w;
                     dv = make_float4(a * dc.x, a * dc.y, a * dc.z, a * dc.w);
                 }
-                *reinterpret_cast<float4*>(dvr + e) = dv;
+                if (p.dvalue) *reinterpret_cast<float4*>(dvr + e) = dv;
             }
             part = warp_sum(part);
             if (lane == 0) {
@@ -291,7 +293,8 @@ __global__ void __launch_bounds__(1024) locattn_bwd_kernel(AttnParams p) {
                     dloc = dpre * (1.f - loc * loc);
                     for (int k = 0; k < K; ++k) dpw_acc[k] = fmaf(dloc, s_conv[k * ATT_TT + tl], dpw_acc[k]);
                 }
-                p.dkey[((size_t)b * T + t) * D + d_own] = dpre;
+                if (!p.accumulate) p.dkey[((size_t)b * T + t) * D + d_own] = dpre;
+                else if (tl < tv) p.dkey[((size_t)b * T + t) * D + d_own] += dpre;
                 s_dloc[tl * D + d_own] = dloc;
             }
         }
@@ -325,7 +328,7 @@ __global__ void __launch_bounds__(1024) locattn_bwd_kernel(AttnParams p) {
         const float* pp = s_prev + t0s + j;
         float acc = 0.f;
         for (int tl = 0; tl < tv_all; ++tl) acc = fmaf(dc[tl], pp[tl], acc);
-        wp[D * K + idx] = acc;
+        wp[D * K + idx] = p.accumulate ? wp[D * K + idx] + acc : acc;
     }
     // dprev[t'] = sum_k sum_j dconv[k][t' - j + R] * w[k][j]   (dconv zero outside [0, len))
     for (int tl = warp; tl < t1s - t0s; tl += nw) {
@@ -340,12 +343,57 @@ __global__ void __launch_bounds__(1024) locattn_bwd_kernel(AttnParams p) {
     }
     // E. per-CTA partial weight gradients and d(q)
     if (d_own < D) {
-        for (int k = 0; k < K; ++k) wp[d_own * K + k] = dpw_acc[k];
-        wp[D * K + K * W + d_own] = dew_acc;
+        if (p.accumulate) {
+            for (int k = 0; k < K; ++k) wp[d_own * K + k] += dpw_acc[k];
+            wp[D * K + K * W + d_own] += dew_acc;
+        } else {
+            for (int k = 0; k < K; ++k) wp[d_own * K + k] = dpw_acc[k];
+            wp[D * K + K * W + d_own] = dew_acc;
+        }
         p.dq_part[((size_t)b * CS + rank) * D + d_own] = dq_acc;
     }
-    if (threadIdx.x == 0) wp[D * K + K * W + D] = deb_acc;
+    if (threadIdx.x == 0) wp[D * K + K * W + D] = p.accumulate ? wp[D * K + K * W + D] + deb_acc : deb_acc;
     cluster.sync();
+}
+
+// d(value)[b,t,:] = sum over the L decode steps of attn[b,l,t] * dctx[b,l,:]  - formed ONCE after the loop instead of
+// writing (and having autograd re-add) a [B,T,E] tensor per step.  grid (ceil(T/8), B), 256 threads.
+constexpr int DV_TT = 8;
+__global__ void __launch_bounds__(256) attn_dvalue_kernel(const float* __restrict__ attn, const float* __restrict__ dctx,
+                                                          float* __restrict__ dvalue, int B, int L, int T, int E,
+                                                          int accumulate) {
+    extern __shared__ float s_a[];                 // [L][DV_TT]
+    const int b = blockIdx.y, t0 = blockIdx.x * DV_TT;
+    for (int i = threadIdx.x; i < L * DV_TT; i += blockDim.x) {
+        const int l = i / DV_TT, tt = i - l * DV_TT;
+        s_a[i] = (t0 + tt < T) ? attn[((size_t)b * L + l) * T + t0 + tt] : 0.f;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x * 4; e < E; e += blockDim.x * 4) {
+        float4 acc[DV_TT];
+#pragma unroll
+        for (int tt = 0; tt < DV_TT; ++tt) acc[tt] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int l = 0; l < L; ++l) {
+            const float4 d = *reinterpret_cast<const float4*>(dctx + ((size_t)b * L + l) * E + e);
+#pragma unroll
+            for (int tt = 0; tt < DV_TT; ++tt) {
+                const float a = s_a[l * DV_TT + tt];
+                acc[tt].x = fmaf(a, d.x, acc[tt].x); acc[tt].y = fmaf(a, d.y, acc[tt].y);
+                acc[tt].z = fmaf(a, d.z, acc[tt].z); acc[tt].w = fmaf(a, d.w, acc[tt].w);
+            }
+        }
+#pragma unroll
+        for (int tt = 0; tt < DV_TT; ++tt) {
+            if (t0 + tt < T) {
+                float4* o = reinterpret_cast<float4*>(dvalue + ((size_t)b * T + t0 + tt) * E + e);
+                if (accumulate) {
+                    const float4 old = *o;
+                    acc[tt].x += old.x; acc[tt].y += old.y; acc[tt].z += old.z; acc[tt].w += old.w;
+                }
+                *o = acc[tt];
+            }
+        }
+    }
 }
 
 static int pick_cluster(int T, int E) {
@@ -404,13 +452,14 @@ extern "C" int b200asr_locattn_fwd(const float* q, const float* key, const float
     return launch_attn((const void*)locattn_fwd_kernel, p, threads, smem, (cudaStream_t)stream);
 }
 
-extern "C" int b200asr_locattn_bwd(const float* q, const float* key, const float* value, const float* prev_att,
-                                   const long long* enc_len, const float* w_conv, const float* w_proj,
-                                   const float* w_energy, float temperature, const float* attn, const float* dctx,
-                                   const float* dattn, int B, int T, int D, int E, int K, int R, float* dq_part,
-                                   float* dkey, float* dvalue, float* dprev, float* wpart, b200asr_stream stream) {
+static int locattn_bwd_impl(const float* q, const float* key, const float* value, const float* prev_att,
+                            const long long* enc_len, const float* w_conv, const float* w_proj,
+                            const float* w_energy, float temperature, const float* attn, const float* dctx,
+                            const float* dattn, int B, int T, int D, int E, int K, int R, float* dq_part,
+                            float* dkey, float* dvalue, float* dprev, float* wpart, int accumulate,
+                            b200asr_stream stream) {
     B200_REQUIRE(q && key && value && prev_att && enc_len && w_conv && w_proj && w_energy && attn && dctx && dq_part &&
-                     dkey && dvalue && dprev && wpart,
+                     dkey && (dvalue || accumulate) && dprev && wpart,
                  "locattn_bwd: null pointer");
     B200_REQUIRE(B > 0 && T > 0 && D > 0 && E > 0 && K > 0 && R >= 0, "locattn_bwd: bad sizes");
     B200_REQUIRE(E % 4 == 0, "locattn_bwd: value dim %d must be a multiple of 4", E);
@@ -420,7 +469,7 @@ extern "C" int b200asr_locattn_bwd(const float* q, const float* key, const float
     p.q = q; p.key = key; p.value = value; p.prev = prev_att; p.len = enc_len; p.w_conv = w_conv; p.w_proj = w_proj;
     p.w_e = w_energy; p.temperature = temperature; p.B = B; p.T = T; p.D = D; p.E = E; p.K = K; p.R = R;
     p.CS = pick_cluster(T, E); p.attn_in = attn; p.dctx = dctx; p.dattn = dattn; p.dq_part = dq_part; p.dkey = dkey;
-    p.dvalue = dvalue; p.dprev = dprev; p.wpart = wpart;
+    p.dvalue = dvalue; p.dprev = dprev; p.wpart = wpart; p.accumulate = accumulate;
     int threads = (D + 31) / 32 * 32;
     if (threads < 128) threads = 128;
     const int W = 2 * R + 1;
@@ -428,4 +477,34 @@ extern "C" int b200asr_locattn_bwd(const float* q, const float* key, const float
                                          (size_t)p.CS * T + (size_t)K * ATT_TT + (size_t)ATT_TT * D +
                                          (size_t)K * (T + 2 * R));
     return launch_attn((const void*)locattn_bwd_kernel, p, threads, smem, (cudaStream_t)stream);
+}
+
+extern "C" int b200asr_locattn_bwd(const float* q, const float* key, const float* value, const float* prev_att,
+                                   const long long* enc_len, const float* w_conv, const float* w_proj,
+                                   const float* w_energy, float temperature, const float* attn, const float* dctx,
+                                   const float* dattn, int B, int T, int D, int E, int K, int R, float* dq_part,
+                                   float* dkey, float* dvalue, float* dprev, float* wpart, b200asr_stream stream) {
+    return locattn_bwd_impl(q, key, value, prev_att, enc_len, w_conv, w_proj, w_energy, temperature, attn, dctx, dattn, B,
+                            T, D, E, K, R, dq_part, dkey, dvalue, dprev, wpart, 0, stream);
+}
+
+extern "C" int b200asr_locattn_bwd_acc(const float* q, const float* key, const float* value, const float* prev_att,
+                                       const long long* enc_len, const float* w_conv, const float* w_proj,
+                                       const float* w_energy, float temperature, const float* attn, const float* dctx,
+                                       const float* dattn, int B, int T, int D, int E, int K, int R, float* dq_part,
+                                       float* dkey_acc, float* dprev, float* wpart_acc, b200asr_stream stream) {
+    return locattn_bwd_impl(q, key, value, prev_att, enc_len, w_conv, w_proj, w_energy, temperature, attn, dctx, dattn, B,
+                            T, D, E, K, R, dq_part, dkey_acc, nullptr, dprev, wpart_acc, 1, stream);
+}
+
+extern "C" int b200asr_attn_dvalue(const float* attn_steps, const float* dctx_steps, int B, int L, int T, int E,
+                                   float* dvalue, int accumulate, b200asr_stream stream) {
+    B200_REQUIRE(attn_steps && dctx_steps && dvalue, "attn_dvalue: null pointer");
+    B200_REQUIRE(B > 0 && L > 0 && T > 0 && E > 0 && E % 4 == 0, "attn_dvalue: bad sizes B=%d L=%d T=%d E=%d", B, L, T, E);
+    const size_t smem = (size_t)L * DV_TT * sizeof(float);
+    B200_REQUIRE(smem <= 48 * 1024, "attn_dvalue: %d decode steps do not fit", L);
+    dim3 grid((T + DV_TT - 1) / DV_TT, B);
+    attn_dvalue_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(attn_steps, dctx_steps, dvalue, B, L, T, E, accumulate);
+    B200_LAUNCH_CHECK("attn_dvalue_kernel");
+    return B200_OK;
 }

@@ -236,6 +236,52 @@ __global__ void __launch_bounds__(1024) ctc_alpha_beta_kernel(CtcParams p) {
             lat[(long long)t0 * S_max + s] = a;
         }
     }
+    if (S_max <= (int)blockDim.x) {
+        // one lattice position per thread (every target shorter than 512 labels): the emission gathers run PD frames
+        // ahead in a register ring, off the T-long dependency chain
+        constexpr int PD = 4;
+        const int s = threadIdx.x;
+        const bool act = s < Sb;
+        const int l = act ? lab[s] : 0;
+        const int sk = (s < S_max) ? skip[s] : 0;
+        const float* lseb = p.lse ? p.lse + (long long)b * p.T : nullptr;
+        float eq[PD];
+#pragma unroll
+        for (int d = 0; d < PD; ++d) {
+            const int st = 1 + d;
+            eq[d] = 0.f;
+            if (st < Tb && act) eq[d] = lpb[(long long)(t0 + dt * st) * p.st + l] - (lseb ? lseb[t0 + dt * st] : 0.f);
+        }
+        for (int base = 1; base < Tb; base += PD) {
+#pragma unroll
+            for (int d = 0; d < PD; ++d) {
+                const int step = base + d;
+                if (step >= Tb) break;                       // block-uniform
+                const int t = t0 + dt * step;
+                const float e = eq[d];
+                if (step + PD < Tb && act)
+                    eq[d] = lpb[(long long)(t + dt * PD) * p.st + l] - (lseb ? lseb[t + dt * PD] : 0.f);
+                __syncthreads();  // prev fully written
+                if (s < S_max) {
+                    float v = NEG_INF;
+                    if (act) {
+                        float a0 = prev[s], a1, a2;
+                        if (!is_beta) {
+                            a1 = (s > 0) ? prev[s - 1] : NEG_INF;
+                            a2 = sk ? prev[s - 2] : NEG_INF;
+                        } else {
+                            a1 = (s + 1 < Sb) ? prev[s + 1] : NEG_INF;
+                            a2 = sk ? prev[s + 2] : NEG_INF;
+                        }
+                        v = lse3(a0, a1, a2) + e;
+                    }
+                    cur[s] = v;
+                    lat[(long long)t * S_max + s] = v;
+                }
+                float* tmp = prev; prev = cur; cur = tmp;
+            }
+        }
+    } else
     for (int step = 1; step < Tb; ++step) {
         const int t = t0 + dt * step;
         const float* lpt = lpb + (long long)t * p.st;
@@ -339,7 +385,11 @@ __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_alpha_beta_warp_kernel(Ctc
     }
     const int t0 = is_beta ? Tb - 1 : 0;
     const int dt = is_beta ? -1 : 1;
-    float a[R], e[R];
+    // The emission gathers x[t, label] are independent of the recursion: they are kept PD frames ahead in a register
+    // ring, so the T-long chain never waits for the ~1000-cycle gather latency (measured: the one-frame look-ahead of
+    // round 1 left the kernel latency-bound at ~1300 cycles per frame).
+    constexpr int PD = 4;
+    float a[R], eq[PD][R];
     const float* lseb = p.lse ? p.lse + (long long)b * p.T : nullptr;
     {   // boundary row
         const float* lpt = lpb + (long long)t0 * p.st;
@@ -358,57 +408,67 @@ __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_alpha_beta_warp_kernel(Ctc
             a[r] = v;
             if (s < S_max) lat[(long long)t0 * S_max + s] = v;
         }
-        if (Tb > 1) {
-            const float* lpn = lpb + (long long)(t0 + dt) * p.st;
-            const float lsn = lseb ? lseb[t0 + dt] : 0.f;
 #pragma unroll
-            for (int r = 0; r < R; ++r) e[r] = lpn[lab[r]] - lsn;
+        for (int d = 0; d < PD; ++d) {
+            const int st = 1 + d;
+            if (st < Tb) {
+                const float* lpn = lpb + (long long)(t0 + dt * st) * p.st;
+                const float lsn = lseb ? lseb[t0 + dt * st] : 0.f;
+#pragma unroll
+                for (int r = 0; r < R; ++r) eq[d][r] = lpn[lab[r]] - lsn;
+            }
         }
     }
-    for (int step = 1; step < Tb; ++step) {
-        const int t = t0 + dt * step;
-        float en[R];
-        if (step + 1 < Tb) {
-            const float* lpn = lpb + (long long)(t + dt) * p.st;
-            const float lsn = lseb ? lseb[t + dt] : 0.f;
+    for (int base = 1; base < Tb; base += PD) {
 #pragma unroll
-            for (int r = 0; r < R; ++r) en[r] = lpn[lab[r]] - lsn;
-        }
-        // neighbours across the lane boundary
-        float n1, n2;
-        if (!is_beta) {
-            n1 = __shfl_up_sync(0xffffffffu, a[R - 1], 1);
-            n2 = __shfl_up_sync(0xffffffffu, a[R >= 2 ? R - 2 : 0], 1);
-            if (R == 1) n2 = __shfl_up_sync(0xffffffffu, a[0], 2);
-            if (lane == 0) { n1 = NEG_INF; n2 = NEG_INF; }
-            if (R == 1 && lane == 1) n2 = NEG_INF;
-        } else {
-            n1 = __shfl_down_sync(0xffffffffu, a[0], 1);
-            n2 = __shfl_down_sync(0xffffffffu, a[R >= 2 ? 1 : 0], 1);
-            if (R == 1) n2 = __shfl_down_sync(0xffffffffu, a[0], 2);
-            if (lane == 31) { n1 = NEG_INF; n2 = NEG_INF; }
-            if (R == 1 && lane == 30) n2 = NEG_INF;
-        }
-        float nw[R];
+        for (int d = 0; d < PD; ++d) {
+            const int step = base + d;
+            if (step >= Tb) break;                       // warp-uniform
+            const int t = t0 + dt * step;
+            float e[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            float a1, a2;
-            if (!is_beta) {
-                a1 = (r >= 1) ? a[r >= 1 ? r - 1 : 0] : n1;
-                a2 = (r >= 2) ? a[r >= 2 ? r - 2 : 0] : (r == 1 ? n1 : n2);
-            } else {
-                a1 = (r + 1 < R) ? a[r + 1 < R ? r + 1 : 0] : n1;
-                a2 = (r + 2 < R) ? a[r + 2 < R ? r + 2 : 0] : (r + 1 < R ? n1 : n2);
+            for (int r = 0; r < R; ++r) e[r] = eq[d][r];
+            if (step + PD < Tb) {                        // refill this ring slot for frame step + PD
+                const float* lpn = lpb + (long long)(t + dt * PD) * p.st;
+                const float lsn = lseb ? lseb[t + dt * PD] : 0.f;
+#pragma unroll
+                for (int r = 0; r < R; ++r) eq[d][r] = lpn[lab[r]] - lsn;
             }
-            if (!skip[r]) a2 = NEG_INF;
-            nw[r] = in_range[r] ? lse3(a[r], a1, a2) + e[r] : NEG_INF;
-        }
+            // neighbours across the lane boundary
+            float n1, n2;
+            if (!is_beta) {
+                n1 = __shfl_up_sync(0xffffffffu, a[R - 1], 1);
+                n2 = __shfl_up_sync(0xffffffffu, a[R >= 2 ? R - 2 : 0], 1);
+                if (R == 1) n2 = __shfl_up_sync(0xffffffffu, a[0], 2);
+                if (lane == 0) { n1 = NEG_INF; n2 = NEG_INF; }
+                if (R == 1 && lane == 1) n2 = NEG_INF;
+            } else {
+                n1 = __shfl_down_sync(0xffffffffu, a[0], 1);
+                n2 = __shfl_down_sync(0xffffffffu, a[R >= 2 ? 1 : 0], 1);
+                if (R == 1) n2 = __shfl_down_sync(0xffffffffu, a[0], 2);
+                if (lane == 31) { n1 = NEG_INF; n2 = NEG_INF; }
+                if (R == 1 && lane == 30) n2 = NEG_INF;
+            }
+            float nw[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            a[r] = nw[r];
-            e[r] = en[r];
-            const int s = lane * R + r;
-            if (s < S_max) lat[(long long)t * S_max + s] = nw[r];
+            for (int r = 0; r < R; ++r) {
+                float a1, a2;
+                if (!is_beta) {
+                    a1 = (r >= 1) ? a[r >= 1 ? r - 1 : 0] : n1;
+                    a2 = (r >= 2) ? a[r >= 2 ? r - 2 : 0] : (r == 1 ? n1 : n2);
+                } else {
+                    a1 = (r + 1 < R) ? a[r + 1 < R ? r + 1 : 0] : n1;
+                    a2 = (r + 2 < R) ? a[r + 2 < R ? r + 2 : 0] : (r + 1 < R ? n1 : n2);
+                }
+                if (!skip[r]) a2 = NEG_INF;
+                nw[r] = in_range[r] ? lse3(a[r], a1, a2) + e[r] : NEG_INF;
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                a[r] = nw[r];
+                const int s = lane * R + r;
+                if (s < S_max) lat[(long long)t * S_max + s] = nw[r];
+            }
         }
     }
     if (!is_beta) {

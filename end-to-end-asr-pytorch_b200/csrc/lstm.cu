@@ -1497,7 +1497,7 @@ static int bilstm_run(bool bwd, float* gates, const float* w_hh, float* cstate, 
                              (g_lstm_flags & 8) ? nullptr : g_trace, g_lstm_flags >> 4, stream);
     // flag bit 5 (mode 512) toggles the backward between the tcgen05 kernel and the mma.sync generation
     if (bwd && g_lstm_mode == 0 && (((g_lstm_flags & 32) != 0) != (LSTM_UMMA_BWD_DEFAULT != 0)) &&
-        lstm_umma_bwd_supported(B, H, ndir))
+        lstm_umma_bwd_supported(B, H, ndir, g_lstm_flags >> 4))
         return lstm_umma_bwd(gates, w_hh, cstate, out_or_dout, B, T, H, ndir, workspace, workspace_bytes,
                              (g_lstm_flags & 8) ? g_trace : nullptr, g_lstm_flags >> 4, stream);
     unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);

@@ -512,13 +512,17 @@ __global__ void __launch_bounds__(32 * (ULB_EPI_WARPS + 2 + ULB_CTRL), 1) bilstm
     constexpr int KS = (4 * UB) / 16;               // MMAs (k-steps of 16) per product and n-block
     extern __shared__ __align__(1024) uint8_t smem[];
     const int H = p.H, T = p.T, nub = p.nub;
-    const int NB = H / 256;                         // n-blocks of 256 accumulator columns
+    // n-blocks of (up to) 256 accumulator columns; they alternate over TWO 256-column TMEM buffers, so H = 640 (cfg D:
+    // 256 + 256 + 128) fits the 512 columns: block 2 re-uses buffer 0 once block 0 of the same step has been drained.
+    // Barrier phases count the USES of a buffer: use(j, step) = step * uses_per_step[j & 1] + j / 2.
+    const int NB = (H + 255) / 256;
+    const int ups0 = (NB + 1) / 2, ups1 = NB / 2;
     uint8_t* sWhi = smem;
     uint8_t* sWlo = smem + (size_t)H * 128;
     uint8_t* sA1 = sWlo + (size_t)H * 128;
     uint8_t* sA2 = sA1 + 8192;
     float* inbox = reinterpret_cast<float*>(sA2 + 8192);                       // [nub][32][UB]
-    const size_t inbox_bytes = (size_t)nub * UL_BC * UB * sizeof(float);
+    const size_t inbox_bytes = POLL ? 0 : (size_t)nub * UL_BC * UB * sizeof(float);   // POLL sums straight from L2
     float* rscale = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(inbox) + inbox_bytes);   // [32]
     uint64_t* in_full = reinterpret_cast<uint64_t*>(rscale + 32);
     uint64_t* a_ready = in_full + 1;
@@ -588,7 +592,10 @@ __global__ void __launch_bounds__(32 * (ULB_EPI_WARPS + 2 + ULB_CTRL), 1) bilstm
             const uint32_t chunk = (uint32_t)(inbox_bytes / ULB_CTRL);
             for (int step = 0; step + 1 < T; ++step) {
                 // my epilogue warps summed the inbox of `step` before they released the A tile of `step`
-                mbar_wait(&mma_done[NB - 1], (uint32_t)(step & 1));
+                {
+                    const int jl = NB - 1, ul = step * ((jl & 1) ? ups1 : ups0) + (jl >> 1);
+                    mbar_wait(&mma_done[jl & 1], (uint32_t)(ul & 1));
+                }
                 ul_spin_until(ctr, (unsigned)(step + 1) * (unsigned)nub, p.err_flag, (p.flags & 1) != 0);
                 if (c == 0) UL_TRACE(10);
                 const uint8_t* src = reinterpret_cast<const uint8_t*>(xb + (size_t)(step & 1) * xelems +
@@ -601,7 +608,6 @@ __global__ void __launch_bounds__(32 * (ULB_EPI_WARPS + 2 + ULB_CTRL), 1) bilstm
     } else if (warp == ULB_EPI_WARPS) {
         // ------------------------------------------------------------------ MMA lane
         if (lane == 0) {
-            constexpr uint32_t idesc = umma::instr_desc(umma::FMT_F16, 64, 256);
             const uint32_t a1 = smem_u32(sA1), a2 = smem_u32(sA2), whi = smem_u32(sWhi), wlo = smem_u32(sWlo);
             mbar_wait(wload, 0);
             for (int step = 0; step + 1 < T; ++step) {
@@ -609,16 +615,19 @@ __global__ void __launch_bounds__(32 * (ULB_EPI_WARPS + 2 + ULB_CTRL), 1) bilstm
                 umma::fence_after_sync();
                 UL_TRACE(1);
                 for (int j = 0; j < NB; ++j) {
-                    if (step > 0) mbar_wait(&d_free[j], (uint32_t)((step - 1) & 1));
+                    const int buf = j & 1, use = step * (buf ? ups1 : ups0) + (j >> 1);
+                    if (use > 0) mbar_wait(&d_free[buf], (uint32_t)((use - 1) & 1));   // previous use has been drained
                     umma::fence_after_sync();
+                    const int ncols = min(256, H - 256 * j);
+                    const uint32_t idesc = umma::instr_desc(umma::FMT_F16, 64, ncols);
 #pragma unroll
                     for (int kk = 0; kk < KS; ++kk) {
-                        umma::mma_ss<umma::FMT_F16>(tmem + 256 * j, umma::desc_k_sw128(a1 + kk * 32),
+                        umma::mma_ss<umma::FMT_F16>(tmem + 256 * buf, umma::desc_k_sw128(a1 + kk * 32),
                                                     umma::desc_k_sw128(whi + j * 32768 + kk * 32), idesc, kk > 0);
-                        umma::mma_ss<umma::FMT_F16>(tmem + 256 * j, umma::desc_k_sw128(a2 + kk * 32),
+                        umma::mma_ss<umma::FMT_F16>(tmem + 256 * buf, umma::desc_k_sw128(a2 + kk * 32),
                                                     umma::desc_k_sw128(wlo + j * 32768 + kk * 32), idesc, 1);
                     }
-                    umma::commit(&mma_done[j]);
+                    umma::commit(&mma_done[buf]);
                 }
                 UL_TRACE(2);
             }
@@ -665,13 +674,15 @@ __global__ void __launch_bounds__(32 * (ULB_EPI_WARPS + 2 + ULB_CTRL), 1) bilstm
                     for (int sb = 0; sb < nub; sb += 32) {
                         // cheap spin on one word, then the block of 32 sources (they finish within a few hundred cycles)
                         float v[32];
+                        const int nhere = min(32, nub - sb);          // nub = 40 at H = 640: a tail block of 8 sources
                         v[0] = ld_relaxed_f32(ib + (size_t)sb * UL_BC * UB);
                         while ((__float_as_uint(v[0]) & 1u) != tag) {
                             ul_watchdog(t0, p.err_flag);
                             v[0] = ld_relaxed_f32(ib + (size_t)sb * UL_BC * UB);
                         }
 #pragma unroll
-                        for (int j = 1; j < 32; ++j) v[j] = ld_relaxed_f32(ib + (size_t)(sb + j) * UL_BC * UB);
+                        for (int j = 1; j < 32; ++j)
+                            v[j] = (j < nhere) ? ld_relaxed_f32(ib + (size_t)(sb + j) * UL_BC * UB) : __uint_as_float(tag);
                         uint32_t pending = 0;
 #pragma unroll
                         for (int j = 1; j < 32; ++j) pending |= ((__float_as_uint(v[j]) & 1u) != tag) ? (1u << j) : 0u;
@@ -686,7 +697,9 @@ __global__ void __launch_bounds__(32 * (ULB_EPI_WARPS + 2 + ULB_CTRL), 1) bilstm
                         }
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
-                            s0 += v[j]; s1 += v[j + 1]; s2 += v[j + 2]; s3 += v[j + 3];
+                            if (j < nhere) {                          // nub is a multiple of 4 (ulb_plan)
+                                s0 += v[j]; s1 += v[j + 1]; s2 += v[j + 2]; s3 += v[j + 3];
+                            }
                         }
                     }
                     dh += (s0 + s1) + (s2 + s3);
@@ -753,16 +766,23 @@ __global__ void __launch_bounds__(32 * (ULB_EPI_WARPS + 2 + ULB_CTRL), 1) bilstm
                 // ---- drain the accumulator into the destinations' inboxes, n-block by n-block
                 float* outbase = xb + (size_t)(step & 1) * xelems;
                 for (int j = 0; j < NB; ++j) {
-                    mbar_wait(&mma_done[j], (uint32_t)(step & 1));
+                    const int buf = j & 1, use = step * (buf ? ups1 : ups0) + (j >> 1);
+                    const bool mine = 256 * j + 64 * jq < H;          // the last block of H = 640 is only 128 wide
+                    if (!mine) {                                      // nothing of this block is mine: just release it
+                        __syncwarp();
+                        if (lane == 0) ul_arrive(&d_free[buf]);
+                        continue;
+                    }
+                    mbar_wait(&mma_done[buf], (uint32_t)(use & 1));
                     umma::fence_after_sync();
                     if (trc && j == 0) UL_TRACE(6);
                     uint32_t v0[16], v1[16];
-                    umma::ld_16x256b_x4(t_lane + 256 * j + 64 * jq, v0);
-                    umma::ld_16x256b_x4(t_lane + 256 * j + 64 * jq + 32, v1);
+                    umma::ld_16x256b_x4(t_lane + 256 * buf + 64 * jq, v0);
+                    umma::ld_16x256b_x4(t_lane + 256 * buf + 64 * jq + 32, v1);
                     umma::wait_ld();
                     umma::fence_before_sync();
                     __syncwarp();
-                    if (lane == 0) ul_arrive(&d_free[j]);
+                    if (lane == 0) ul_arrive(&d_free[buf]);
                     const float rs = rscale[drow];
                     const float k = 1.f / 2048.f;
 #pragma unroll
@@ -866,8 +886,9 @@ struct UlbPlan {
     size_t smem, pack_bytes, xbuf_bytes;
 };
 
-int ulb_plan(int B, int H, int ndir, UlbPlan* out) {
-    if (H != 256 && H != 512) return -1;          // accumulator = H TMEM columns in n-blocks of 256
+int ulb_plan(int B, int H, int ndir, bool poll, UlbPlan* out) {
+    // accumulator = H columns in n-blocks of 256 over two TMEM buffers: 256 | 512 | 640 | 768 (a last block of 128 or 256)
+    if (H % 128 != 0 || H < 256 || H > 768) return -1;
     const int sms = sm_count();
     const size_t cap = (size_t)max_optin_smem();
     for (int n = 1; n <= B; ++n) {
@@ -878,9 +899,11 @@ int ulb_plan(int B, int H, int ndir, UlbPlan* out) {
             const int nub = H / UB;
             const int ctas = ndir * nbg * nub;
             if (ctas > sms) continue;
+            if (nub % 4) continue;
             const size_t inbox = (size_t)nub * UL_BC * UB * 4;
-            const size_t smem = (size_t)2 * H * 128 + 16384 + inbox + 128 + 128;
-            if (smem > cap || (inbox / ULB_CTRL) % 16) continue;
+            // the polling exchange keeps no inbox in shared memory (which is what lets H = 640 fit)
+            const size_t smem = (size_t)2 * H * 128 + 16384 + (poll ? 0 : inbox) + 128 + 128;
+            if (smem > cap || (inbox / ULB_CTRL) % 16 || (2 * H * 128) % 32768) continue;
             out->UB = UB; out->nub = nub; out->nbg = nbg; out->ctas = ctas; out->Bsub = Bs;
             out->nsplit = (B + Bs - 1) / Bs; out->smem = smem;
             out->pack_bytes = (size_t)ndir * nub * 2 * H * 128;
@@ -922,15 +945,19 @@ int ul_launch_bwd(const UlbPlan& pl, UlParams p, const float* w_hh, cudaStream_t
 
 }  // namespace
 
-bool lstm_umma_bwd_supported(int B, int H, int ndir) {
+static bool ulb_poll(int flags) { return ((flags & 8) != 0) != (UL_POLL_BWD_DEFAULT != 0); }
+
+bool lstm_umma_bwd_supported(int B, int H, int ndir, int flags) {
     UlbPlan pl;
-    return ulb_plan(B, H, ndir, &pl) == 0;
+    return ulb_plan(B, H, ndir, ulb_poll(flags), &pl) == 0;
 }
 
 int lstm_umma_bwd(float* gates, const float* w_hh, const float* cstate, const float* dout, int B, int T, int H, int ndir,
                   void* workspace, size_t workspace_bytes, long long* trace, int flags, cudaStream_t stream) {
     UlbPlan pl;
-    B200_REQUIRE(ulb_plan(B, H, ndir, &pl) == 0, "bilstm(umma bwd): unsupported shape B=%d H=%d ndir=%d", B, H, ndir);
+    // flag bit 3 (debug mode 2048) selects the OTHER exchange protocol than the default one
+    const bool poll = ulb_poll(flags);
+    B200_REQUIRE(ulb_plan(B, H, ndir, poll, &pl) == 0, "bilstm(umma bwd): unsupported shape B=%d H=%d ndir=%d", B, H, ndir);
     B200_REQUIRE(workspace_bytes >= lstm_umma_workspace_bytes(B, H, ndir), "bilstm(umma bwd): workspace too small");
     uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
     UlParams p;
@@ -943,8 +970,6 @@ int lstm_umma_bwd(float* gates, const float* w_hh, const float* cstate, const fl
     p.flags = flags;
     p.B = B; p.T = T; p.H = H; p.ndir = ndir; p.UB = pl.UB; p.nub = pl.nub; p.nbg = pl.nbg; p.NA = 0; p.NC = ULB_CTRL;
     p.b0 = 0; p.Bend = B;
-    // flag bit 3 (debug mode 2048) selects the OTHER exchange protocol than the default one
-    const bool poll = ((flags & 8) != 0) != (UL_POLL_BWD_DEFAULT != 0);
     if (pl.UB == 16) return poll ? ul_launch_bwd<16, true>(pl, p, w_hh, stream) : ul_launch_bwd<16, false>(pl, p, w_hh, stream);
     return poll ? ul_launch_bwd<8, true>(pl, p, w_hh, stream) : ul_launch_bwd<8, false>(pl, p, w_hh, stream);
 }
@@ -959,7 +984,11 @@ size_t lstm_umma_workspace_bytes(int B, int H, int ndir) {
     UlbPlan pb;
     size_t f = 0, b = 0;
     if (ul_plan(B, H, ndir, &pl) == 0) f = ul_align(pl.pack_bytes) + ul_align(pl.xbuf_bytes) + UL_COUNTER_BYTES;
-    if (ulb_plan(B, H, ndir, &pb) == 0) b = ul_align(pb.pack_bytes) + ul_align(pb.xbuf_bytes) + UL_COUNTER_BYTES;
+    for (int poll = 0; poll < 2; ++poll)
+        if (ulb_plan(B, H, ndir, poll != 0, &pb) == 0) {
+            const size_t bb = ul_align(pb.pack_bytes) + ul_align(pb.xbuf_bytes) + UL_COUNTER_BYTES;
+            b = bb > b ? bb : b;
+        }
     return f > b ? f : b;
 }
 

@@ -6,7 +6,7 @@
 namespace b200asr {
 
 bool lstm_umma_fwd_supported(int B, int H, int ndir);
-bool lstm_umma_bwd_supported(int B, int H, int ndir);
+bool lstm_umma_bwd_supported(int B, int H, int ndir, int flags);
 int lstm_umma_bwd(float* gates, const float* w_hh, const float* cstate, const float* dout, int B, int T, int H, int ndir,
                   void* workspace, size_t workspace_bytes, long long* trace, int flags, cudaStream_t stream);
 size_t lstm_umma_workspace_bytes(int B, int H, int ndir);

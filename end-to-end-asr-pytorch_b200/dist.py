@@ -122,7 +122,9 @@ class DataParallel:
                 by_param[i] = b
 
         def launch(b):
-            if b["work"] is None:
+            # after close() (communicator torn down) the hooks degrade to the single-process behaviour: rank 0 may keep
+            # stepping on its own shard, e.g. bench.py's parity block after the timed regions
+            if b["work"] is None and self.enabled and dist.is_initialized():
                 b["work"] = dist.all_reduce(buf.grad[b["lo"]:b["hi"]], op=dist.ReduceOp.SUM, async_op=True)
 
         def make_hook(i):
@@ -147,7 +149,8 @@ class DataParallel:
             for b in self._buckets:
                 launch(b)
             for b in self._buckets:
-                b["work"].wait()
+                if b["work"] is not None:
+                    b["work"].wait()
                 b["work"], b["seen"] = None, 0
             return flat
 

@@ -57,6 +57,9 @@ SIGNATURES = {
                                     c_int, _P, _P, _P]),
     "b200asr_locattn_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_float, _P, _P, _P, c_int, c_int, c_int, c_int,
                                     c_int, c_int, _P, _P, _P, _P, _P, _P]),
+    "b200asr_locattn_bwd_acc": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_float, _P, _P, _P, c_int, c_int, c_int, c_int,
+                                        c_int, c_int, _P, _P, _P, _P, _P]),
+    "b200asr_attn_dvalue": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, c_int, _P]),
     "b200asr_ce_fwd_bwd": (c_int, [_P, _P, c_longlong, c_longlong, c_int, _P, _P, _P, _P]),
     "b200asr_gemm3x_supported": (c_int, [c_int, c_int, c_int]),
     "b200asr_gemm3x_tn": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),

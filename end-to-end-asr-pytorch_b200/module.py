@@ -192,10 +192,12 @@ class LocationAwareAttention(BaseAttention):
         self.loc_proj = nn.Linear(kernel_num, dim, bias=False)
         self.gen_energy = nn.Linear(dim, 1)
         self.dim = dim
+        self._mem = None
 
     def reset_mem(self):
         super().reset_mem()
         self.prev_att = None
+        self._mem = None
 
     def set_mem(self, prev_att):
         self.prev_att = prev_att
@@ -212,9 +214,13 @@ class LocationAwareAttention(BaseAttention):
         if self.prev_att is None:
             self.prev_att = self.init_prev_att(bs, ts, k.device)
         if self.num_head == 1 and hasattr(ops, "loc_attention_step") and k.is_cuda:
-            output, attn = ops.loc_attention_step(q, k, v, self.prev_att.view(bs, ts), self.k_len,
-                                                  self.loc_conv.weight, self.loc_proj.weight,
-                                                  self.gen_energy.weight, self.gen_energy.bias, self.temperature)
+            if getattr(self, "_mem", None) is None:
+                # first step of a batch: ONE gradient-accumulator node for key / value / the location weights
+                self._mem = ops.attention_memory(k, v, self.loc_conv.weight, self.loc_proj.weight,
+                                                 self.gen_energy.weight, self.gen_energy.bias)
+            mem, mk, mv, cw, pw, ew, eb, token = self._mem
+            output, attn = ops.loc_attention_mem_step(mem, token, q, mk, mv, self.prev_att.view(bs, ts), self.k_len,
+                                                      cw, pw, ew, eb, self.temperature)
             attn = attn.view(bs, 1, ts)
         else:
             loc = torch.tanh(self.loc_proj(self.loc_conv(self.prev_att).transpose(1, 2)))

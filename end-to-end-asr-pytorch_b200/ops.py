@@ -713,6 +713,136 @@ def loc_attention_step(q, key, value, prev_att, enc_len, conv_w, proj_w, e_w, e_
 
 
 # ----------------------------------------------------------------------------------------------------------
+# The decode loop calls the attention L times on the SAME key / value / weights (src/asr.py:112-151).  Left to autograd,
+# every step's backward writes a [B,T,D] and a [B,T,E] gradient that the engine then re-adds L-1 times (cfg C: 46 x
+# (78 + 11) MB written and ~3x that re-read and re-written by ATen adds).  Instead the per-batch gradients live in ONE
+# accumulator node:  AttnMemFn  hands key / value / the four small weights to the steps (plus a 1-element token whose
+# only job is to make the engine run AttnMemFn.backward after the LAST step);  LocAttnMemStepFn.backward  adds d(key) and
+# the weight-gradient partials in place (b200asr_locattn_bwd_acc) and records (attn_l, dctx_l);  AttnMemFn.backward
+# forms d(value) = sum_l attn_l (x) dctx_l once (b200asr_attn_dvalue) and reduces the weight partials once.
+class AttnMem:
+    def __init__(self):
+        self.dkey = None
+        self.wpart = None
+        self.attn, self.dctx = [], []
+        self.meta = None
+
+
+class AttnMemFn(Function):
+    @staticmethod
+    def forward(ctx, mem, key, value, conv_w, proj_w, e_w, e_b):
+        ctx.set_materialize_grads(False)        # undefined output gradients arrive as None, not as [B,T,E] zeros
+        ctx.mem = mem
+        ctx.shapes = (key.shape, value.shape, conv_w.shape, proj_w.shape, e_w.shape, e_b.shape)
+        token = torch.zeros(1, device=key.device, dtype=torch.float32)
+        return (key.view_as(key), value.view_as(value), conv_w.view_as(conv_w), proj_w.view_as(proj_w),
+                e_w.view_as(e_w), e_b.view_as(e_b), token)
+
+    @staticmethod
+    def backward(ctx, gkey, gvalue, gcw, gpw, gew, geb, _gtoken):
+        lib = L.load()
+        mem = ctx.mem
+        s_key, s_value, s_conv, s_proj, s_ew, s_eb = ctx.shapes
+        B, T, D = s_key
+        E = s_value[2]
+        dev = _gtoken.device
+        dkey = mem.dkey if mem.dkey is not None else torch.zeros(s_key, device=dev)
+        if gkey is not None:
+            dkey = dkey + gkey
+        if mem.attn:
+            attn_all = torch.stack(mem.attn, 1).contiguous()          # [B, L, T]
+            dctx_all = torch.stack(mem.dctx, 1).contiguous()          # [B, L, E]
+            Lsteps = attn_all.shape[1]
+            acc = gvalue is not None
+            dvalue = _f32c(gvalue).clone() if acc else torch.empty(s_value, device=dev, dtype=torch.float32)
+            with L.timed("attn_dvalue", 4 * B * (T * E + Lsteps * (T + E))):
+                L.check(lib.b200asr_attn_dvalue(L.ptr(attn_all), L.ptr(dctx_all), B, Lsteps, T, E, L.ptr(dvalue),
+                                                int(acc), L.stream()), "attn_dvalue")
+        else:
+            dvalue = gvalue
+        d_conv = d_proj = d_ew = d_eb = None
+        if mem.wpart is not None:
+            K, _, W = s_conv
+            wsum = mem.wpart.sum(0)
+            d_proj = wsum[:D * K].view(s_proj)
+            d_conv = wsum[D * K:D * K + K * W].view(s_conv)
+            d_ew = wsum[D * K + K * W:D * K + K * W + D].view(s_ew)
+            d_eb = wsum[D * K + K * W + D:].view(s_eb)
+        add = lambda a, b: a if b is None else (b if a is None else a + b)
+        mem.dkey = mem.wpart = None
+        mem.attn, mem.dctx = [], []
+        return None, dkey, dvalue, add(d_conv, gcw), add(d_proj, gpw), add(d_ew, gew), add(d_eb, geb)
+
+
+def attention_memory(key, value, conv_w, proj_w, e_w, e_b):
+    """-> (mem, key, value, conv_w, proj_w, e_w, e_b, token) for loc_attention_mem_step."""
+    mem = AttnMem()
+    return (mem,) + tuple(AttnMemFn.apply(mem, _f32c(key), _f32c(value), conv_w, proj_w, e_w, e_b))
+
+
+class LocAttnMemStepFn(Function):
+    """One decode step on an attention memory: forward = the same single-launch kernel as LocAttnStepFn; backward =
+    b200asr_locattn_bwd_acc (d(key) / weight partials added into the memory, no d(value) write)."""
+
+    @staticmethod
+    def forward(ctx, mem, token, q, key, value, prev_att, enc_len, conv_w, proj_w, e_w, e_b, temperature):
+        ctx.set_materialize_grads(False)
+        lib = L.load()
+        q, prev_att = _f32c(q), _f32c(prev_att)
+        B, T, D = key.shape
+        E = value.shape[2]
+        K, _, W = conv_w.shape
+        R = (W - 1) // 2
+        dev = key.device
+        enc_len = enc_len.to(device=dev, dtype=torch.int64).contiguous()
+        cw, pw = _f32c(conv_w.detach()), _f32c(proj_w.detach())
+        ew, eb = _f32c(e_w.detach()).view(-1), _f32c(e_b.detach()).view(-1)
+        attn = torch.empty((B, T), device=dev, dtype=torch.float32)
+        cvec = torch.empty((B, E), device=dev, dtype=torch.float32)
+        with L.timed("locattn_fwd", 4 * B * T * (D + E)):
+            L.check(lib.b200asr_locattn_fwd(L.ptr(q), L.ptr(key), L.ptr(value), L.ptr(prev_att), L.ptr(enc_len),
+                                            L.ptr(cw), L.ptr(pw), L.ptr(ew), L.ptr(eb), float(temperature), B, T, D, E,
+                                            K, R, L.ptr(attn), L.ptr(cvec), L.stream()), "locattn_fwd")
+        ctx.save_for_backward(q, key, value, prev_att, enc_len, cw, pw, ew, attn)
+        ctx.mem = mem
+        ctx.dims = (B, T, D, E, K, R)
+        ctx.temperature = float(temperature)
+        return cvec, attn
+
+    @staticmethod
+    def backward(ctx, dctx, dattn):
+        lib = L.load()
+        q, key, value, prev_att, enc_len, cw, pw, ew, attn = ctx.saved_tensors
+        B, T, D, E, K, R = ctx.dims
+        mem = ctx.mem
+        dev = key.device
+        CS = lib.b200asr_locattn_cluster_size(T, E)
+        P = lib.b200asr_locattn_wpart_floats(D, K, R)
+        if mem.dkey is None:
+            mem.dkey = torch.zeros((B, T, D), device=dev, dtype=torch.float32)
+            mem.wpart = torch.zeros((B * CS, P), device=dev, dtype=torch.float32)
+        dctx = _f32c(dctx) if dctx is not None else torch.zeros((B, E), device=dev)
+        dattn = _f32c(dattn) if dattn is not None else None
+        dq_part = torch.empty((B, CS, D), device=dev, dtype=torch.float32)
+        dprev = torch.empty((B, T), device=dev, dtype=torch.float32)
+        with L.timed("locattn_bwd", 4 * B * T * (2 * D + E)):
+            L.check(lib.b200asr_locattn_bwd_acc(L.ptr(q), L.ptr(key), L.ptr(value), L.ptr(prev_att), L.ptr(enc_len),
+                                                L.ptr(cw), L.ptr(pw), L.ptr(ew), ctx.temperature, L.ptr(attn),
+                                                L.ptr(dctx), L.ptr(dattn), B, T, D, E, K, R, L.ptr(dq_part),
+                                                L.ptr(mem.dkey), L.ptr(dprev), L.ptr(mem.wpart), L.stream()),
+                    "locattn_bwd_acc")
+        mem.attn.append(attn)
+        mem.dctx.append(dctx)
+        token_grad = torch.zeros(1, device=dev, dtype=torch.float32)
+        return None, token_grad, dq_part.sum(1), None, None, dprev, None, None, None, None, None, None
+
+
+def loc_attention_mem_step(mem, token, q, key, value, prev_att, enc_len, conv_w, proj_w, e_w, e_b, temperature):
+    """-> (context [B,E], attn [B,T]); key ... e_b and token come from attention_memory()."""
+    return LocAttnMemStepFn.apply(mem, token, q, key, value, prev_att, enc_len, conv_w, proj_w, e_w, e_b, temperature)
+
+
+# ----------------------------------------------------------------------------------------------------------
 class Linear3xFn(Function):
     """y = x W^T + b for the large dense layers of the step (CTC head, key projection, vocabulary projection) on
     the tensor cores with the same error-compensated 3xTF32 scheme as the LSTM input projection (fp32-class)."""

@@ -177,6 +177,18 @@ B200ASR_API int b200asr_locattn_bwd(const float* q, const float* key, const floa
                                     const float* w_energy, float temperature, const float* attn, const float* dctx,
                                     const float* dattn, int B, int T, int D, int E, int K, int R, float* dq_part,
                                     float* dkey, float* dvalue, float* dprev, float* wpart, b200asr_stream stream);
+/* The decode loop's form of the backward (src/asr.py:112-151 calls the attention L times on the SAME key / value):
+ * d(key) and the weight-gradient partials are ADDED into per-batch accumulators (zeroed by the caller before the first
+ * step) and d(value) is not produced here at all: d(value)[b,t,:] = sum_l attn_l[b,t] * dctx_l[b,:] is formed once after
+ * the loop by b200asr_attn_dvalue from the stacked per-step alignments [B,L,T] and context gradients [B,L,E] - instead
+ * of a [B,T,E] write per step that autograd then has to re-add L-1 times.                                             */
+B200ASR_API int b200asr_locattn_bwd_acc(const float* q, const float* key, const float* value, const float* prev_att,
+                                        const long long* enc_len, const float* w_conv, const float* w_proj,
+                                        const float* w_energy, float temperature, const float* attn, const float* dctx,
+                                        const float* dattn, int B, int T, int D, int E, int K, int R, float* dq_part,
+                                        float* dkey_acc, float* dprev, float* wpart_acc, b200asr_stream stream);
+B200ASR_API int b200asr_attn_dvalue(const float* attn_steps, const float* dctx_steps, int B, int L, int T, int E,
+                                    float* dvalue, int accumulate, b200asr_stream stream);
 
 /* ---- K15: cross-entropy (log-softmax + NLL, ignore_index) forward + logit gradient ----------------------
  * replaces torch.nn.CrossEntropyLoss(ignore_index=0) at bin/train_asr.py:47,127-131.  row_loss [n_rows] =

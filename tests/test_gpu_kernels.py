@@ -205,7 +205,8 @@ def test_ctc_fused_head_vs_aten_cpu(pkg, B, T, V, Lmax):
     ref = F.ctc_loss(lpr.transpose(0, 1), txt, il, tl, blank=0, reduction="mean", zero_infinity=False) * 0.3
     ref.backward()
     assert abs(loss.item() - ref.item()) < 1e-4 * abs(ref.item())
-    assert scaled_err(x.grad.cpu().numpy(), xr.grad.numpy()) < (1e-4 if V < 1000 else 1e-3)
+    # (T = 300 with 140 labels: ATen's own fp32 lattice carries ~1e-4 of noise there, see the unfused test above)
+    assert scaled_err(x.grad.cpu().numpy(), xr.grad.numpy()) < (2e-4 if V < 1000 else 1e-3)
     assert torch.equal(head.argmax(-1).cpu(), lpr.argmax(-1))                                   # greedy ids bit exact
     assert rel_err(head.materialize().cpu().numpy(), lpr.detach().numpy()) < 1e-5
     # unfused kernels on materialised log-probs: same lattice arithmetic up to the rounding of x - lse
@@ -419,6 +420,47 @@ def test_loc_attention_step_fwd_bwd(pkg, B, T, D, E, K, R, lens):
             assert float(x.grad.abs().max()) < 1e-5 and float(r.grad.abs().max()) < 1e-12
         else:
             assert scaled_err(x.grad.cpu().numpy(), r.grad.numpy()) < 2e-5, n
+
+
+@pytest.mark.parametrize("B,T,D,E,K,R,lens,L", [
+    (3, 12, 16, 64, 4, 5, [12, 9, 5], 3),
+    (4, 40, 300, 256, 10, 100, [40, 33, 17, 8], 5),
+    (2, 149, 300, 2048, 10, 100, [149, 120], 4),          # cfg-C shape
+])
+def test_loc_attention_memory_decode_loop(pkg, B, T, D, E, K, R, lens, L):
+    """The decode loop's form: L chained steps (the alignment of step l feeds step l+1) on ONE attention memory -
+    d(key) / weight partials accumulated in place, d(value) formed once after the loop - against the fp64 torch loop."""
+    g = torch.Generator().manual_seed(B * 100 + T + L)
+    mk = lambda *s, sc=1.0: (torch.randn(*s, generator=g) * sc)
+    qs, key, value = mk(L, B, D), mk(B, T, D), mk(B, T, E)
+    lens = torch.tensor(lens)
+    prev = (torch.arange(T)[None] < lens[:, None]).float()
+    prev = prev / prev.sum(1, keepdim=True)
+    cw, pw, ew, eb = mk(K, 1, 2 * R + 1, sc=0.3), mk(D, K, sc=0.5), mk(1, D, sc=0.3), mk(1)
+    gc, ga = mk(L, B, E), mk(L, B, T)
+    extra_gv = mk(B, T, E)                                 # value also feeds something else (the CTC head in the model)
+    names = ["q", "key", "value", "cw", "pw", "ew", "eb"]
+    ref_in = [t.double().requires_grad_(True) for t in (qs, key, value, cw, pw, ew, eb)]
+    p_ref, tot = prev.double(), 0
+    for l in range(L):
+        c, a = _loc_attention_torch(ref_in[0][l], ref_in[1], ref_in[2], p_ref, lens, *ref_in[3:], 0.5)
+        tot = tot + (c * gc[l].double()).sum() + (a * ga[l].double()).sum()
+        p_ref = a
+    (tot + (ref_in[2] * extra_gv.double()).sum()).backward()
+    dev_in = [t.to(DEV).requires_grad_(True) for t in (qs, key, value, cw, pw, ew, eb)]
+    mem, mkey, mval, mcw, mpw, mew, meb, token = pkg.ops.attention_memory(*dev_in[1:])
+    p_dev, tot = prev.to(DEV), 0
+    for l in range(L):
+        c, a = pkg.ops.loc_attention_mem_step(mem, token, dev_in[0][l], mkey, mval, p_dev, lens.to(DEV), mcw, mpw, mew, meb, 0.5)
+        tot = tot + (c * gc[l].to(DEV)).sum() + (a * ga[l].to(DEV)).sum()
+        p_dev = a
+    (tot + (dev_in[2] * extra_gv.to(DEV)).sum()).backward()
+    for n, x, r in zip(names, dev_in, ref_in):
+        if n == "eb":
+            assert float(x.grad.abs().max()) < 1e-4 and float(r.grad.abs().max()) < 1e-10
+        else:
+            assert scaled_err(x.grad.cpu().numpy(), r.grad.numpy()) < 5e-5, n
+    assert mem.dkey is None and not mem.attn                # the memory released its accumulators
 
 
 def test_gemm_tf32x3_is_fp32_class(pkg):
