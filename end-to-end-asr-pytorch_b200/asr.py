@@ -140,12 +140,14 @@ class Decoder(nn.Module):
         if module != "LSTM":
             raise NotImplementedError("only an LSTM decoder is on the accelerated path")
         self.hidden_state = None
+        self._dw = None
         self.enable_cell = True
         self.layers = nn.LSTM(input_dim, dim, num_layers=layer, dropout=dropout, batch_first=True)
         self.char_trans = nn.Linear(dim, vocab_size)
         self.final_dropout = nn.Dropout(dropout)
 
     def init_state(self, bs):
+        self._dw = None          # per-batch handles of the own-GEMM step path (ops.decoder_weights)
         device = next(self.parameters()).device
         self.hidden_state = (torch.zeros((self.layer, bs, self.dim), device=device),
                              torch.zeros((self.layer, bs, self.dim), device=device))
@@ -168,12 +170,22 @@ class Decoder(nn.Module):
         h_all, c_all = self.hidden_state
         hs, cs = [], []
         inp = x
+        own = x.is_cuda and all(ops.decoder_gemm_supported(getattr(self.layers, "weight_ih_l%d" % l).shape[1], self.dim)
+                                for l in range(self.layer))
+        if own and getattr(self, "_dw", None) is None:
+            # first step of a batch: [W_ih | W_hh] per layer + ONE weight-gradient accumulator node each
+            self._dw = [ops.decoder_weights(*(getattr(self.layers, "%s_l%d" % (n, l))
+                                              for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")))
+                        for l in range(self.layer)]
         for l in range(self.layer):
             w_ih = getattr(self.layers, "weight_ih_l%d" % l)
             w_hh = getattr(self.layers, "weight_hh_l%d" % l)
             b_ih = getattr(self.layers, "bias_ih_l%d" % l)
             b_hh = getattr(self.layers, "bias_hh_l%d" % l)
-            pre = F.linear(inp, w_ih, b_ih) + F.linear(h_all[l], w_hh, b_hh)
+            if own:
+                pre = ops.decoder_step(self._dw[l], inp, h_all[l])
+            else:
+                pre = F.linear(inp, w_ih, b_ih) + F.linear(h_all[l], w_hh, b_hh)
             h, c = ops.lstm_cell(pre, c_all[l])
             hs.append(h)
             cs.append(c)

@@ -113,12 +113,19 @@ __global__ void __launch_bounds__(1024) locattn_fwd_kernel(AttnParams p) {
         float e = NEG_INF;
         if (t < len) {
             const float* kr = p.key + ((size_t)b * T + t) * D;
+            float kv[16];                                   // the frame's key row (D <= 512), all loads in flight at once
+#pragma unroll
+            for (int i = 0; i < 16; ++i) kv[i] = (lane + 32 * i < D) ? kr[lane + 32 * i] : 0.f;
             float part = 0.f;
-            for (int d = lane; d < D; d += 32) {
-                float pre = 0.f;
-                for (int k = 0; k < K; ++k) pre = fmaf(s_pw[d * K + k], s_conv[k * TS + tl], pre);
-                const float loc = tanhf(pre);
-                part = fmaf(s_ew[d], tanhf(kr[d] + s_q[d] + loc), part);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int d = lane + 32 * i;
+                if (d < D) {
+                    float pre = 0.f;
+                    for (int k = 0; k < K; ++k) pre = fmaf(s_pw[d * K + k], s_conv[k * TS + tl], pre);
+                    const float loc = tanhf(pre);
+                    part = fmaf(s_ew[d], tanhf(kv[i] + s_q[d] + loc), part);
+                }
             }
             e = (warp_sum(part) + be) / p.temperature;
         }
@@ -162,6 +169,7 @@ __global__ void __launch_bounds__(1024) locattn_fwd_kernel(AttnParams p) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         if (act) {
             const float* vb = p.value + (size_t)b * T * E + (size_t)rank * ES + col * 4;
+#pragma unroll 4
             for (int t = grp; t < len; t += ngroups) {
                 const float a = s_energy[t];
                 const float4 v = *reinterpret_cast<const float4*>(vb + (size_t)t * E);
@@ -184,7 +192,8 @@ __global__ void __launch_bounds__(1024) locattn_fwd_kernel(AttnParams p) {
 }
 
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) locattn_bwd_kernel(AttnParams p) {
+// one thread per attention dim (D <= 384), two CTAs per SM: the 256 CTAs of a 64-utterance batch stay ONE wave
+__global__ void __launch_bounds__(384, 2) locattn_bwd_kernel(AttnParams p) {
     extern __shared__ __align__(16) float sm[];
     __shared__ float s_scratch[32];
     cg::cluster_group cluster = cg::this_cluster();
@@ -224,21 +233,44 @@ __global__ void __launch_bounds__(1024) locattn_bwd_kernel(AttnParams p) {
     // A. d(attn) partial over my feature slice + d(value) = attn (x) dctx
     const int ES = E / CS;
     {
+        // the slice of d(ctx) is the same for every frame: registers; the value row of the NEXT frame of this warp is
+        // loaded while the current one is reduced (one row per iteration left the loop bound by the load latency)
+        constexpr int MAXV = 4;                              // ES <= 512 (checked by the host wrapper)
         const float* dcb = p.dctx + (size_t)b * E + (size_t)rank * ES;
+        float4 dcr[MAXV], cur[MAXV], nxt[MAXV];
+#pragma unroll
+        for (int k = 0; k < MAXV; ++k) {
+            const int e = lane * 4 + 128 * k;
+            dcr[k] = (e < ES) ? *reinterpret_cast<const float4*>(dcb + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+            cur[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (warp < T && warp < len && e < ES)
+                cur[k] = *reinterpret_cast<const float4*>(p.value + ((size_t)b * T + warp) * E + (size_t)rank * ES + e);
+        }
         for (int t = warp; t < T; t += nw) {
             const float a = s_attn[t];
-            const float* vr = p.value + ((size_t)b * T + t) * E + (size_t)rank * ES;
             float* dvr = p.dvalue + ((size_t)b * T + t) * E + (size_t)rank * ES;
+            const int tn = t + nw;
+#pragma unroll
+            for (int k = 0; k < MAXV; ++k) {
+                const int e = lane * 4 + 128 * k;
+                nxt[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (tn < T && tn < len && e < ES)
+                    nxt[k] = *reinterpret_cast<const float4*>(p.value + ((size_t)b * T + tn) * E + (size_t)rank * ES + e);
+            }
             float part = 0.f;
-            for (int e = lane * 4; e < ES; e += 128) {
-                const float4 dc = *reinterpret_cast<const float4*>(dcb + e);
-                float4 dv = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (t < len) {
-                    const float4 v = *reinterpret_cast<const float4*>(vr + e);
-                    part += dc.x * v.x + dc.y * v.y + dc.z * v.z + dc.w * v.w;
-                    dv = make_float4(a * dc.x, a * dc.y, a * dc.z, a * dc.w);
+#pragma unroll
+            for (int k = 0; k < MAXV; ++k) {
+                const int e = lane * 4 + 128 * k;
+                if (e < ES) {
+                    const float4 dc = dcr[k], v = cur[k];
+                    if (t < len) part += dc.x * v.x + dc.y * v.y + dc.z * v.z + dc.w * v.w;
+                    if (p.dvalue) {
+                        float4 dv = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (t < len) dv = make_float4(a * dc.x, a * dc.y, a * dc.z, a * dc.w);
+                        *reinterpret_cast<float4*>(dvr + e) = dv;
+                    }
                 }
-                if (p.dvalue) *reinterpret_cast<float4*>(dvr + e) = dv;
+                cur[k] = nxt[k];
             }
             part = warp_sum(part);
             if (lane == 0) {
@@ -274,18 +306,31 @@ __global__ void __launch_bounds__(1024) locattn_bwd_kernel(AttnParams p) {
     for (int tb = t0s; tb < t1s; tb += ATT_TT) {
         const int tv = min(min(t1s, len) - tb, ATT_TT);   // valid (unmasked) frames of this tile
         const int tn = min(t1s - tb, ATT_TT);              // frames of this tile
+        // the first half of the tile's key column of this thread, issued before the location convolution so that the
+        // loads overlap it (the second half is fetched while the first is consumed)
+        constexpr int KH = ATT_TT / 2;
+        float kreg[KH], kreg2[KH];
+#pragma unroll
+        for (int tl = 0; tl < KH; ++tl)
+            kreg[tl] = (d_own < D && tl < tv) ? p.key[((size_t)b * T + tb + tl) * D + d_own] : 0.f;
         if (tv > 0) conv_slice(s_prev, s_w, s_conv, K, W, tb, tv, ATT_TT);
         __syncthreads();
         if (d_own < D) {
             const float qd = s_q[d_own], ew = s_ew[d_own];
-            for (int tl = 0; tl < tn; ++tl) {
+#pragma unroll
+            for (int tl = 0; tl < KH; ++tl)
+                kreg2[tl] = (KH + tl < tv) ? p.key[((size_t)b * T + tb + KH + tl) * D + d_own] : 0.f;
+#pragma unroll
+            for (int tl = 0; tl < ATT_TT; ++tl) {
+                if (tl >= tn) break;
+                const float kval = tl < KH ? kreg[tl < KH ? tl : 0] : kreg2[tl >= KH ? tl - KH : 0];
                 const int t = tb + tl;
                 float dpre = 0.f, dloc = 0.f;
                 if (tl < tv) {
                     float pre = 0.f;
                     for (int k = 0; k < K; ++k) pre = fmaf(s_pw[d_own * K + k], s_conv[k * ATT_TT + tl], pre);
                     const float loc = tanhf(pre);
-                    const float s = tanhf(p.key[((size_t)b * T + t) * D + d_own] + qd + loc);
+                    const float s = tanhf(kval + qd + loc);
                     const float de = s_de[t];
                     dpre = de * ew * (1.f - s * s);
                     dew_acc = fmaf(de, s, dew_acc);
@@ -445,7 +490,8 @@ extern "C" int b200asr_locattn_fwd(const float* q, const float* key, const float
     p.q = q; p.key = key; p.value = value; p.prev = prev_att; p.len = enc_len; p.w_conv = w_conv; p.w_proj = w_proj;
     p.w_e = w_energy; p.b_e = b_energy; p.temperature = temperature; p.B = B; p.T = T; p.D = D; p.E = E; p.K = K;
     p.R = R; p.CS = pick_cluster(T, E); p.attn = attn; p.ctx = ctx;
-    const int threads = 256;
+    B200_REQUIRE(D <= 512, "locattn_fwd: attention dim %d > 512", D);
+    const int threads = 512;
     const int W = 2 * R + 1, TS = (T + p.CS - 1) / p.CS;
     const size_t smem = sizeof(float) * ((size_t)T + 2 * R + (size_t)K * W + (size_t)D * K + 2 * D + T + (size_t)K * TS +
                                          (size_t)threads * 4 + 4);
@@ -464,7 +510,8 @@ static int locattn_bwd_impl(const float* q, const float* key, const float* value
     B200_REQUIRE(B > 0 && T > 0 && D > 0 && E > 0 && K > 0 && R >= 0, "locattn_bwd: bad sizes");
     B200_REQUIRE(E % 4 == 0, "locattn_bwd: value dim %d must be a multiple of 4", E);
     B200_REQUIRE(K <= 16, "locattn_bwd: at most 16 location kernels (got %d)", K);
-    B200_REQUIRE(D <= 1024, "locattn_bwd: attention dim %d > 1024", D);
+    B200_REQUIRE(D <= 384, "locattn_bwd: attention dim %d > 384", D);
+    B200_REQUIRE(E / pick_cluster(T, E) <= 512, "locattn_bwd: value dim %d too large for %d-CTA clusters", E, pick_cluster(T, E));
     AttnParams p = {};
     p.q = q; p.key = key; p.value = value; p.prev = prev_att; p.len = enc_len; p.w_conv = w_conv; p.w_proj = w_proj;
     p.w_e = w_energy; p.temperature = temperature; p.B = B; p.T = T; p.D = D; p.E = E; p.K = K; p.R = R;

@@ -415,8 +415,8 @@ extern "C" int b200asr_gemm3x_tn(const float* A, const float* B, const float* bi
     return b200asr_gemm3x_tn_ld(A, K, B, bias, C, M, N, K, ldc, accumulate, stream);
 }
 
-extern "C" int b200asr_gemm3x_tn_ld(const float* A, int lda, const float* B, const float* bias, float* C, int M, int N,
-                                    int K, int ldc, int accumulate, b200asr_stream stream) {
+static int gemm3x_tn_impl(const float* A, int lda, const float* B, const float* bias, float* C, int M, int N, int K,
+                          int ldc, int accumulate, void* ws, size_t ws_bytes, b200asr_stream stream) {
     B200_REQUIRE(A && B && C, "gemm3x_tn: null pointer");
     B200_REQUIRE(lda > 0 && (lda % 4) == 0, "gemm3x_tn: lda %d must be a positive multiple of 4", lda);
     B200_REQUIRE(b200asr_gemm3x_supported(M, N, K), "gemm3x_tn: unsupported sizes M=%d N=%d K=%d (K %% 4 must be 0)", M,
@@ -431,11 +431,22 @@ extern "C" int b200asr_gemm3x_tn_ld(const float* A, int lda, const float* B, con
     GemmArgs g = {};
     g.bias = bias; g.C = C; g.M = M; g.N = N; g.ldc = ldc; g.accumulate = accumulate;
     g.KB = (K + G_BK - 1) / G_BK; g.kbt = g.KB;
-    return launch<false, false>(ma, mb, g, nullptr, 0, (cudaStream_t)stream);
+    return launch<false, false>(ma, mb, g, ws, ws_bytes, (cudaStream_t)stream);
 }
 
-extern "C" int b200asr_gemm3x_nn(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int M,
-                                 int N, int K, int ldc, int accumulate, b200asr_stream stream) {
+extern "C" int b200asr_gemm3x_tn_ld(const float* A, int lda, const float* B, const float* bias, float* C, int M, int N,
+                                    int K, int ldc, int accumulate, b200asr_stream stream) {
+    return gemm3x_tn_impl(A, lda, B, bias, C, M, N, K, ldc, accumulate, nullptr, 0, stream);
+}
+
+extern "C" int b200asr_gemm3x_tn_ws(const float* A, int lda, const float* B, const float* bias, float* C, int M, int N,
+                                    int K, int ldc, int accumulate, void* workspace, size_t workspace_bytes,
+                                    b200asr_stream stream) {
+    return gemm3x_tn_impl(A, lda, B, bias, C, M, N, K, ldc, accumulate, workspace, workspace_bytes, stream);
+}
+
+static int gemm3x_nn_impl(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int M, int N,
+                          int K, int ldc, int accumulate, void* ws, size_t ws_bytes, b200asr_stream stream) {
     B200_REQUIRE(A && B && C, "gemm3x_nn: null pointer");
     B200_REQUIRE(M > 0 && N > 0 && K > 0, "gemm3x_nn: bad sizes M=%d N=%d K=%d", M, N, K);
     B200_REQUIRE(lda >= K && (lda % 4) == 0 && ldb >= N && (ldb % 4) == 0 && ldc >= N,
@@ -449,7 +460,18 @@ extern "C" int b200asr_gemm3x_nn(const float* A, int lda, const float* B, int ld
     GemmArgs g = {};
     g.bias = bias; g.C = C; g.M = M; g.N = N; g.ldc = ldc; g.accumulate = accumulate;
     g.KB = (K + G_BK - 1) / G_BK; g.kbt = g.KB;
-    return launch<false, true>(ma, mb, g, nullptr, 0, (cudaStream_t)stream);
+    return launch<false, true>(ma, mb, g, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int b200asr_gemm3x_nn(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int M,
+                                 int N, int K, int ldc, int accumulate, b200asr_stream stream) {
+    return gemm3x_nn_impl(A, lda, B, ldb, bias, C, M, N, K, ldc, accumulate, nullptr, 0, stream);
+}
+
+extern "C" int b200asr_gemm3x_nn_ws(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int M,
+                                    int N, int K, int ldc, int accumulate, void* workspace, size_t workspace_bytes,
+                                    b200asr_stream stream) {
+    return gemm3x_nn_impl(A, lda, B, ldb, bias, C, M, N, K, ldc, accumulate, workspace, workspace_bytes, stream);
 }
 
 extern "C" int b200asr_gemm3x_nt(const float* A, long long lda, long long a_bstride, int a_shift, const float* B,

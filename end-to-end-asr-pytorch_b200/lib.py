@@ -66,6 +66,8 @@ SIGNATURES = {
     "b200asr_gemm3x_tn_ld": (c_int, [_P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "b200asr_gemm3x_nn": (c_int, [_P, c_int, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "b200asr_gemm3x_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "b200asr_gemm3x_tn_ws": (c_int, [_P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
+    "b200asr_gemm3x_nn_ws": (c_int, [_P, c_int, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
     "b200asr_gemm3x_nt": (c_int, [_P, c_longlong, c_longlong, c_int, _P, c_longlong, c_longlong, c_int, _P, c_int, c_int,
                                   c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
     "b200asr_split_tf32": (c_int, [_P, _P, _P, c_longlong, _P]),

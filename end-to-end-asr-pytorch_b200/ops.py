@@ -62,8 +62,14 @@ def gemm_tn(a, w, bias=None, out=None, accumulate=False):
     b = _f32c(bias) if bias is not None else None
     # algorithmic bytes: both operands and the result once; flops 2*M*N*K (x3 tensor-core products)
     with L.timed("gemm3x_tn", 4 * (M * K + N * K + M * N * (2 if accumulate else 1))):
-        L.check(lib.b200asr_gemm3x_tn(L.ptr(a), L.ptr(w), L.ptr(b), L.ptr(out), M, N, K, out.stride(0),
-                                      int(bool(accumulate)), L.stream()), "gemm3x_tn")
+        if M <= 256:          # skinny (the decoder's per-step products): split-K over all SMs
+            ws_bytes = lib.b200asr_gemm3x_workspace_bytes(M, N)
+            ws = torch.empty(max(ws_bytes, 16), device=a.device, dtype=torch.uint8)
+            L.check(lib.b200asr_gemm3x_tn_ws(L.ptr(a), K, L.ptr(w), L.ptr(b), L.ptr(out), M, N, K, out.stride(0),
+                                             int(bool(accumulate)), L.ptr(ws), ws_bytes, L.stream()), "gemm3x_tn_ws")
+        else:
+            L.check(lib.b200asr_gemm3x_tn(L.ptr(a), L.ptr(w), L.ptr(b), L.ptr(out), M, N, K, out.stride(0),
+                                          int(bool(accumulate)), L.stream()), "gemm3x_tn")
     return out
 
 
@@ -95,8 +101,14 @@ def gemm_nn(a, w, out=None, accumulate=False):
         accumulate = False
     assert out.stride(1) == 1 and out.shape == (M, N)
     with L.timed("gemm3x_nn", 4 * (M * K + N * K + M * N * (2 if accumulate else 1))):
-        L.check(lib.b200asr_gemm3x_nn(L.ptr(a), K, L.ptr(w), N, None, L.ptr(out), M, N, K, out.stride(0),
-                                      int(bool(accumulate)), L.stream()), "gemm3x_nn")
+        if M <= 256:
+            ws_bytes = lib.b200asr_gemm3x_workspace_bytes(M, N)
+            ws = torch.empty(max(ws_bytes, 16), device=a.device, dtype=torch.uint8)
+            L.check(lib.b200asr_gemm3x_nn_ws(L.ptr(a), K, L.ptr(w), N, None, L.ptr(out), M, N, K, out.stride(0),
+                                             int(bool(accumulate)), L.ptr(ws), ws_bytes, L.stream()), "gemm3x_nn_ws")
+        else:
+            L.check(lib.b200asr_gemm3x_nn(L.ptr(a), K, L.ptr(w), N, None, L.ptr(out), M, N, K, out.stride(0),
+                                          int(bool(accumulate)), L.stream()), "gemm3x_nn")
     return out
 
 
@@ -610,6 +622,82 @@ class LSTMCellFn(Function):
 
 def lstm_cell(pre, c_prev):
     return LSTMCellFn.apply(pre, c_prev)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Decoder LSTM step (src/asr.py:214-221): the two per-step projections  x . W_ih^T + h . W_hh^T + b  are ONE skinny
+# tensor-core GEMM on [x | h] . [W_ih | W_hh]^T (split-K, csrc/gemm.cu), the backward's input gradient is one more, and
+# the weight gradients of all L steps are ONE  dPre^T . [x | h]  contraction over the L*B stacked rows at the end of the
+# loop (same accumulator-node idea as the attention memory above) instead of 2 L library SGEMMs + 2 L accumulations.
+class DecMem:
+    def __init__(self):
+        self.dpre, self.x = [], []
+
+
+class DecWeightsFn(Function):
+    @staticmethod
+    def forward(ctx, mem, w_ih, w_hh, b_ih, b_hh):
+        ctx.set_materialize_grads(False)
+        ctx.mem = mem
+        ctx.I = w_ih.shape[1]
+        token = torch.zeros(1, device=w_ih.device, dtype=torch.float32)
+        return torch.cat([w_ih, w_hh], 1).contiguous(), (b_ih + b_hh).contiguous(), token
+
+    @staticmethod
+    def backward(ctx, gW, gb, _gtoken):
+        mem, I = ctx.mem, ctx.I
+        dW = gW
+        db = gb
+        if mem.dpre:
+            dpre_all = torch.cat(mem.dpre, 0)
+            x_all = torch.cat(mem.x, 0)
+            d = gemm_nt(dpre_all, x_all, dpre_all.shape[1], x_all.shape[1], dpre_all.shape[0])
+            dW = d if gW is None else d + gW
+            s = dpre_all.sum(0)
+            db = s if gb is None else s + gb
+            mem.dpre, mem.x = [], []
+        if dW is None:
+            return None, None, None, None, None
+        return None, dW[:, :I], dW[:, I:], db, db
+
+
+class DecStepFn(Function):
+    @staticmethod
+    def forward(ctx, mem, token, x, h, wcat, bias):
+        ctx.set_materialize_grads(False)
+        xcat = torch.cat([x, h], 1).contiguous()
+        pre = gemm_tn(xcat, wcat, bias=bias)
+        ctx.save_for_backward(xcat, wcat)
+        ctx.mem = mem
+        ctx.I = x.shape[1]
+        return pre
+
+    @staticmethod
+    def backward(ctx, dpre):
+        xcat, wcat = ctx.saved_tensors
+        if dpre is None:
+            return None, None, None, None, None, None
+        dpre = _f32c(dpre)
+        dx = gemm_nn(dpre, wcat)
+        ctx.mem.dpre.append(dpre)
+        ctx.mem.x.append(xcat)
+        return None, torch.zeros(1, device=dpre.device), dx[:, :ctx.I], dx[:, ctx.I:], None, None
+
+
+def decoder_weights(w_ih, w_hh, b_ih, b_hh):
+    """-> (mem, wcat [4H, I+H], bias [4H], token) for decoder_step(); once per batch and decoder layer."""
+    mem = DecMem()
+    return (mem,) + tuple(DecWeightsFn.apply(mem, w_ih, w_hh, b_ih, b_hh))
+
+
+def decoder_step(dw, x, h):
+    """pre-activations [B, 4H] of one decoder LSTM step from decoder_weights()' handle."""
+    mem, wcat, bias, token = dw
+    return DecStepFn.apply(mem, token, x, h, wcat, bias)
+
+
+def decoder_gemm_supported(I, H):
+    return GEMM_MODE == "umma" and (I + H) % 4 == 0 and (4 * H) % 4 == 0
 
 
 # ----------------------------------------------------------------------------------------------------------

@@ -78,6 +78,7 @@ class TrainStep:
         if model.enable_att:     # drop the step's cached keys / alignments / decoder state (they pin the autograd graph)
             model.attention.reset_mem()
             model.decoder.hidden_state = None
+            model.decoder._dw = None
         grad_norm = self.optimizer.step()
         self.step_id += 1
         det = lambda t: t.detach() if t is not None else None     # keep no reference to the autograd graph

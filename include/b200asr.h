@@ -165,7 +165,7 @@ B200ASR_API int b200asr_lstm_cell_bwd(const float* gates, const float* c_prev, c
  * backward: dctx [B,E], dattn [B,T] or NULL -> dq_part [B,CS,D] (sum over CS = dq), dkey [B,T,D], dvalue [B,T,E],
  * dprev [B,T], wpart [B*CS, P] with P = D*K + K*(2R+1) + D + 1 laid out (d w_proj | d w_conv | d w_energy | d b_energy);
  * the caller sums wpart over its first axis.  CS = b200asr_locattn_cluster_size(T, E) CTAs cooperate per utterance
- * through distributed shared memory.  K <= 16, E % 4 == 0, D <= 1024.                                              */
+ * through distributed shared memory.  K <= 16, E % 4 == 0, D <= 512 (D <= 384, E / CS <= 512 backward).                                              */
 B200ASR_API int b200asr_locattn_cluster_size(int T, int E);
 B200ASR_API size_t b200asr_locattn_wpart_floats(int D, int K, int R);
 B200ASR_API int b200asr_locattn_fwd(const float* q, const float* key, const float* value, const float* prev_att,
@@ -238,6 +238,14 @@ B200ASR_API int b200asr_gemm3x_nn(const float* A, int lda, const float* B, int l
  * Small M x N with a long contraction is cut into split-K slices over all SMs (partials in `workspace`, summed in a
  * fixed order by a second launch); workspace may be NULL (no split).                                              */
 B200ASR_API size_t b200asr_gemm3x_workspace_bytes(int M, int N);
+/* the tn / nn forms with a split-K workspace (b200asr_gemm3x_workspace_bytes(M, N)): skinny products - the decoder's
+ * per-step  [B, in] . W^T  with B = 64 rows (src/asr.py:214-221) - are cut along K over all SMs, partial tiles summed in
+ * a fixed order by a second launch (bias / accumulate applied there).                                              */
+B200ASR_API int b200asr_gemm3x_tn_ws(const float* A, int lda, const float* B, const float* bias, float* C, int M, int N, int K,
+                         int ldc, int accumulate, void* workspace, size_t workspace_bytes, b200asr_stream stream);
+B200ASR_API int b200asr_gemm3x_nn_ws(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int M,
+                         int N, int K, int ldc, int accumulate, void* workspace, size_t workspace_bytes,
+                         b200asr_stream stream);
 B200ASR_API int b200asr_gemm3x_nt(const float* A, long long lda, long long a_bstride, int a_shift, const float* B,
                       long long ldb, long long b_bstride, int b_shift, float* C, int M, int N, int T, int batches,
                       int ldc, int accumulate, int permute_rows, void* workspace, size_t workspace_bytes,

@@ -463,6 +463,35 @@ def test_loc_attention_memory_decode_loop(pkg, B, T, D, E, K, R, lens, L):
     assert mem.dkey is None and not mem.attn                # the memory released its accumulators
 
 
+@pytest.mark.parametrize("B,I,H,L", [(3, 96, 32, 4), (64, 2560, 512, 3), (32, 1792, 512, 2)])
+def test_decoder_step_gemm_loop(pkg, B, I, H, L):
+    """The speller's LSTM step on the own GEMM (one skinny split-K product on [x | h] . [W_ih | W_hh]^T per step, the
+    weight gradients of all steps as ONE contraction at the end of the loop) against fp64 F.linear + autograd."""
+    torch.manual_seed(B + I)
+    w_ih, w_hh = torch.randn(4 * H, I) * 0.05, torch.randn(4 * H, H) * 0.05
+    b_ih, b_hh = torch.randn(4 * H) * 0.1, torch.randn(4 * H) * 0.1
+    xs, gs = torch.randn(L, B, I), torch.randn(L, B, 4 * H)
+    h0 = torch.randn(B, H) * 0.5
+    ref_in = [t.double().requires_grad_(True) for t in (w_ih, w_hh, b_ih, b_hh, xs, h0)]
+    h, tot = ref_in[5], 0
+    for l in range(L):
+        pre = F.linear(ref_in[4][l], ref_in[0], ref_in[2]) + F.linear(h, ref_in[1], ref_in[3])
+        tot = tot + (pre * gs[l].double()).sum()
+        h = torch.tanh(pre[:, :H])                          # feed a function of the step back, like the cell does
+    tot.backward()
+    dev_in = [t.to(DEV).requires_grad_(True) for t in (w_ih, w_hh, b_ih, b_hh, xs, h0)]
+    dw = pkg.ops.decoder_weights(*dev_in[:4])
+    h, tot = dev_in[5], 0
+    for l in range(L):
+        pre = pkg.ops.decoder_step(dw, dev_in[4][l], h)
+        tot = tot + (pre * gs[l].to(DEV)).sum()
+        h = torch.tanh(pre[:, :H])
+    tot.backward()
+    for n, x, r in zip(["w_ih", "w_hh", "b_ih", "b_hh", "xs", "h0"], dev_in, ref_in):
+        assert scaled_err(x.grad.cpu().numpy(), r.grad.numpy()) < 1e-5, n
+    assert not dw[0].dpre                                   # the accumulator released its step records
+
+
 def test_gemm_tf32x3_is_fp32_class(pkg):
     """The error-compensated tensor-core GEMM must be as accurate as an fp32 SGEMM (vs an fp64 product)."""
     torch.manual_seed(0)
