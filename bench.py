@@ -310,7 +310,9 @@ def parity_check(pkg, step_fn, cfg, waves, lens, txt, dev, n_ref=8):
 
 def micro_bench(pkg, dev, peak):
     """BASELINE.json configs[4]: mel-fbank (+delta+CMVN) and the CTC kernels on 1000 synthetic utterances of 2-30 s
-    (batches of 100, zero padded to the batch maximum), L2 flushed (256 MB write) before every timed launch, CUDA
+    (front end: batches of 100; CTC: batches of 250 = 500 lattice warps per launch, enough to occupy the 148 SMs of the
+    T'-long latency chain - the train step's batch of 64 is reported by the `kernels` table instead; zero padded to the
+    batch maximum), L2 flushed (256 MB write) before every timed launch, CUDA
     events per C-ABI launch.  Algorithmic bytes per SURVEY.md 8(d): fbank 4N + 160m, delta+CMVN 4m(40+120), CTC
     2*4*T'*V (+4*T'*V logits read for the log-softmax that feeds it).  Returns {kernel: {ms, GB/s, frac of HBM peak}}."""
     cfg = pkg.synthetic.load_config("cfgB")
@@ -346,14 +348,15 @@ def micro_bench(pkg, dev, peak):
         del wave
     out = {}
     for V, Lr in ((31, (20, 130)), (5000, (6, 45))):
-        for i in range(0, 1000, 100):
-            l = lens[i:i + 100]
+        CB = 250
+        for i in range(0, 1000, CB):
+            l = lens[i:i + CB]
             Tp = ((l - 400) // 160 + 1) // 4
             Tm = int(Tp.max())
-            logits = torch.randn(100, Tm, V, device=dev, requires_grad=True)
-            tl = torch.minimum(torch.randint(Lr[0], Lr[1], (100,), generator=g), (Tp // 3).clamp(min=1))
-            txt = torch.zeros(100, int(tl.max()), dtype=torch.long)
-            for b in range(100):
+            logits = torch.randn(CB, Tm, V, device=dev, requires_grad=True)
+            tl = torch.minimum(torch.randint(Lr[0], Lr[1], (CB,), generator=g), (Tp // 3).clamp(min=1))
+            txt = torch.zeros(CB, int(tl.max()), dtype=torch.long)
+            for b in range(CB):
                 txt[b, :tl[b]] = torch.randint(1, V, (int(tl[b]),), generator=g)
             txt, Td, tld = txt.to(dev), Tp.to(dev), tl.to(dev)
             crit = pkg.CTCLoss(blank=0)

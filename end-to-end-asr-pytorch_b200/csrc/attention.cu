@@ -192,8 +192,11 @@ __global__ void __launch_bounds__(1024) locattn_fwd_kernel(AttnParams p) {
 }
 
 // ------------------------------------------------------------------------------------------
-// one thread per attention dim (D <= 384), two CTAs per SM: the 256 CTAs of a 64-utterance batch stay ONE wave
-__global__ void __launch_bounds__(384, 2) locattn_bwd_kernel(AttnParams p) {
+// one thread per attention dim.  MINB = 2 (D <= 384, E / CS <= 512): two CTAs per SM, so that the 256 CTAs of a
+// 64-utterance batch stay ONE wave (measured cfg C: 8.3 vs 10.8 ms per 46 steps); MINB = 1 (D <= 512, E / CS <= 1024):
+// more registers for the value-row prefetch when all CTAs are co-resident anyway (cfg D, 32 utterances: 9.5 vs 11.2 ms).
+template <int MINB>
+__global__ void __launch_bounds__(MINB == 2 ? 384 : 512, MINB) locattn_bwd_kernel(AttnParams p) {
     extern __shared__ __align__(16) float sm[];
     __shared__ float s_scratch[32];
     cg::cluster_group cluster = cg::this_cluster();
@@ -235,7 +238,7 @@ __global__ void __launch_bounds__(384, 2) locattn_bwd_kernel(AttnParams p) {
     {
         // the slice of d(ctx) is the same for every frame: registers; the value row of the NEXT frame of this warp is
         // loaded while the current one is reduced (one row per iteration left the loop bound by the load latency)
-        constexpr int MAXV = 4;                              // ES <= 512 (checked by the host wrapper)
+        constexpr int MAXV = MINB == 2 ? 4 : 8;              // ES <= 128 * MAXV (checked by the host wrapper)
         const float* dcb = p.dctx + (size_t)b * E + (size_t)rank * ES;
         float4 dcr[MAXV], cur[MAXV], nxt[MAXV];
 #pragma unroll
@@ -306,10 +309,10 @@ __global__ void __launch_bounds__(384, 2) locattn_bwd_kernel(AttnParams p) {
     for (int tb = t0s; tb < t1s; tb += ATT_TT) {
         const int tv = min(min(t1s, len) - tb, ATT_TT);   // valid (unmasked) frames of this tile
         const int tn = min(t1s - tb, ATT_TT);              // frames of this tile
-        // the first half of the tile's key column of this thread, issued before the location convolution so that the
-        // loads overlap it (the second half is fetched while the first is consumed)
-        constexpr int KH = ATT_TT / 2;
-        float kreg[KH], kreg2[KH];
+        // the tile's key column of this thread, issued before the location convolution so that the loads overlap it
+        // (MINB = 2, fewer registers: only the first half; the second half is fetched while the first is consumed)
+        constexpr int KH = MINB == 2 ? ATT_TT / 2 : ATT_TT;
+        float kreg[KH], kreg2[ATT_TT / 2];
 #pragma unroll
         for (int tl = 0; tl < KH; ++tl)
             kreg[tl] = (d_own < D && tl < tv) ? p.key[((size_t)b * T + tb + tl) * D + d_own] : 0.f;
@@ -317,13 +320,15 @@ __global__ void __launch_bounds__(384, 2) locattn_bwd_kernel(AttnParams p) {
         __syncthreads();
         if (d_own < D) {
             const float qd = s_q[d_own], ew = s_ew[d_own];
+            if (MINB == 2) {
 #pragma unroll
-            for (int tl = 0; tl < KH; ++tl)
-                kreg2[tl] = (KH + tl < tv) ? p.key[((size_t)b * T + tb + KH + tl) * D + d_own] : 0.f;
+                for (int tl = 0; tl < ATT_TT / 2; ++tl)
+                    kreg2[tl] = (ATT_TT / 2 + tl < tv) ? p.key[((size_t)b * T + tb + ATT_TT / 2 + tl) * D + d_own] : 0.f;
+            }
 #pragma unroll
             for (int tl = 0; tl < ATT_TT; ++tl) {
                 if (tl >= tn) break;
-                const float kval = tl < KH ? kreg[tl < KH ? tl : 0] : kreg2[tl >= KH ? tl - KH : 0];
+                const float kval = tl < KH ? kreg[tl < KH ? tl : 0] : kreg2[tl >= ATT_TT / 2 ? tl - ATT_TT / 2 : 0];
                 const int t = tb + tl;
                 float dpre = 0.f, dloc = 0.f;
                 if (tl < tv) {
@@ -510,8 +515,8 @@ static int locattn_bwd_impl(const float* q, const float* key, const float* value
     B200_REQUIRE(B > 0 && T > 0 && D > 0 && E > 0 && K > 0 && R >= 0, "locattn_bwd: bad sizes");
     B200_REQUIRE(E % 4 == 0, "locattn_bwd: value dim %d must be a multiple of 4", E);
     B200_REQUIRE(K <= 16, "locattn_bwd: at most 16 location kernels (got %d)", K);
-    B200_REQUIRE(D <= 384, "locattn_bwd: attention dim %d > 384", D);
-    B200_REQUIRE(E / pick_cluster(T, E) <= 512, "locattn_bwd: value dim %d too large for %d-CTA clusters", E, pick_cluster(T, E));
+    B200_REQUIRE(D <= 512, "locattn_bwd: attention dim %d > 512", D);
+    B200_REQUIRE(E / pick_cluster(T, E) <= 1024, "locattn_bwd: value dim %d too large for %d-CTA clusters", E, pick_cluster(T, E));
     AttnParams p = {};
     p.q = q; p.key = key; p.value = value; p.prev = prev_att; p.len = enc_len; p.w_conv = w_conv; p.w_proj = w_proj;
     p.w_e = w_energy; p.temperature = temperature; p.B = B; p.T = T; p.D = D; p.E = E; p.K = K; p.R = R;
@@ -523,7 +528,9 @@ static int locattn_bwd_impl(const float* q, const float* key, const float* value
     const size_t smem = sizeof(float) * ((size_t)T + 2 * R + (size_t)K * W + (size_t)D * K + 2 * D + 2 * (size_t)T +
                                          (size_t)p.CS * T + (size_t)K * ATT_TT + (size_t)ATT_TT * D +
                                          (size_t)K * (T + 2 * R));
-    return launch_attn((const void*)locattn_bwd_kernel, p, threads, smem, (cudaStream_t)stream);
+    const bool two_per_sm = (long long)B * p.CS > sm_count() && D <= 384 && E / p.CS <= 512;
+    return launch_attn(two_per_sm ? (const void*)locattn_bwd_kernel<2> : (const void*)locattn_bwd_kernel<1>, p, threads,
+                       smem, (cudaStream_t)stream);
 }
 
 extern "C" int b200asr_locattn_bwd(const float* q, const float* key, const float* value, const float* prev_att,

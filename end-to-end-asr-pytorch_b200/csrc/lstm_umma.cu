@@ -185,6 +185,7 @@ __global__ void __launch_bounds__(32 * (UBP + 2 + UL_MAX_CTRL), 1) bilstm_fwd_um
     uint64_t* wload = d_free + 2;
     uint64_t* pub = d_free + 3;                  // the epilogue warps have stored h_step
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_free + 4);
+    uint64_t* landed = d_free + 5;               // [UL_MAX_ATOMS] polling exchange: a bulk copy of the atom has landed
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int NC = p.NC;
@@ -194,7 +195,10 @@ __global__ void __launch_bounds__(32 * (UBP + 2 + UL_MAX_CTRL), 1) bilstm_fwd_um
     const int dir = blk;
 
     if (tid == 0) {
-        for (int a = 0; a < UL_MAX_ATOMS; ++a) mbar_init(&full[a], 1);
+        for (int a = 0; a < UL_MAX_ATOMS; ++a) {
+            mbar_init(&full[a], 1);
+            mbar_init(&landed[a], 1);
+        }
         mbar_init(d_free, UBP);
         mbar_init(pub, UBP);
         mbar_init(mma_done, 1);
@@ -221,42 +225,45 @@ __global__ void __launch_bounds__(32 * (UBP + 2 + UL_MAX_CTRL), 1) bilstm_fwd_um
                     bulk_g2s(sB + (size_t)a * N * 128, wsrc + (size_t)a * N * 128, N * 128, wload);
             }
         } else {
-            // loader warp c-1 owns K atoms c-1, c-1+NC, ...: lane l moves the 16-byte chunks j*32 + l (j = 0..15) of
-            // an atom from the exchange buffer into the same position of the shared-memory A image
+            // loader warp c-1 owns K atoms c-1, c-1+NC, ...  Per atom and step: (1) lanes 0..7 spin on the LAST row of the
+            // atom in the exchange buffer (8 chunks = a slice of every producer) until no poison is left - the data
+            // itself is the flag, nobody fences; (2) lane 0 pulls the atom with ONE bulk copy; (3) the warp checks the
+            // landed image for poison (a slower producer warp's rows may lag the sentinel row) and re-pulls if needed;
+            // (4) the atom is released to the MMA lane.
+            uint32_t nland[2] = {0u, 0u};                 // bulk copies completed per owned atom (barrier phase)
             for (int step = 0; step + 1 < T; ++step) {
                 // my own MMAs of `step` (which read the atoms about to be overwritten) are done
                 if (step > 0) mbar_wait(mma_done, (uint32_t)((step - 1) & 1));
                 const uint8_t* img = xb + (size_t)(step % UL_NBUF) * img_bytes;
-                for (int a = c - 1; a < NA; a += NC) {
-                    const uint8_t* src = img + (size_t)a * UL_ATOM_A + (size_t)lane * 16;
-                    uint8_t* dst = sA + (size_t)a * UL_ATOM_A + (size_t)lane * 16;
+                int own = 0;
+                for (int a = c - 1; a < NA; a += NC, ++own) {
+                    const uint8_t* src = img + (size_t)a * UL_ATOM_A;
+                    uint8_t* dst = sA + (size_t)a * UL_ATOM_A;
                     const long long t0 = clock64();
-                    // sentinel: the last 32 chunks (rows 60..63, written by the last epilogue quadrant) - cheap spin
-                    uint4 v15 = ld_relaxed_v4(src + 15 * 512);
-                    while (__any_sync(0xffffffffu, has_poison16(v15))) {
-                        ul_watchdog(t0, p.err_flag);
-                        v15 = ld_relaxed_v4(src + 15 * 512);
-                    }
-                    if (a == 0 && lane == 0) UL_TRACE(10);
-                    uint4 v[15];
-#pragma unroll
-                    for (int j = 0; j < 15; ++j) v[j] = ld_relaxed_v4(src + j * 512);
-                    unsigned pending = 0;
-#pragma unroll
-                    for (int j = 0; j < 15; ++j) pending |= has_poison16(v[j]) ? (1u << j) : 0u;
-                    while (__any_sync(0xffffffffu, pending != 0u)) {
-                        ul_watchdog(t0, p.err_flag);
-#pragma unroll
-                        for (int j = 0; j < 15; ++j)
-                            if (pending & (1u << j)) {
-                                v[j] = ld_relaxed_v4(src + j * 512);
-                                if (!has_poison16(v[j])) pending &= ~(1u << j);
+                    bool bad = true;
+                    while (bad) {
+                        if (lane < 8) {
+                            uint4 v = ld_relaxed_v4(src + 63 * 128 + lane * 16);
+                            while (has_poison16(v)) {
+                                ul_watchdog(t0, p.err_flag);
+                                v = ld_relaxed_v4(src + 63 * 128 + lane * 16);
                             }
-                    }
+                        }
+                        __syncwarp();
+                        if (a == 0 && lane == 0) UL_TRACE(10);
+                        if (lane == 0) {
+                            mbar_expect_tx(&landed[a], UL_ATOM_A);
+                            bulk_g2s(dst, src, UL_ATOM_A, &landed[a]);
+                        }
+                        mbar_wait(&landed[a], nland[own & 1] & 1u);
+                        ++nland[own & 1];
+                        bool p16 = false;
 #pragma unroll
-                    for (int j = 0; j < 15; ++j) *reinterpret_cast<uint4*>(dst + j * 512) = v[j];
-                    *reinterpret_cast<uint4*>(dst + 15 * 512) = v15;
-                    fence_proxy_async_smem();
+                        for (int j = 0; j < 16; ++j)
+                            p16 |= has_poison16(*reinterpret_cast<const uint4*>(dst + (size_t)(j * 32 + lane) * 16));
+                        bad = __any_sync(0xffffffffu, p16);
+                        if (bad) ul_watchdog(t0, p.err_flag);
+                    }
                     __syncwarp();
                     if (lane == 0) ul_arrive(&full[a]);
                     if (a == 0 && lane == 0) UL_TRACE(11);
@@ -837,7 +844,7 @@ int ul_plan(int B, int H, int ndir, UlPlan* out) {
             const int nub = H / UB;
             const int ctas = ndir * nbg * nub;
             if (ctas > sms) continue;
-            const size_t smem = (size_t)NA * UL_ATOM_A + (size_t)NA * 8 * UBp * 128 + 256;
+            const size_t smem = (size_t)NA * UL_ATOM_A + (size_t)NA * 8 * UBp * 128 + 512;
             if (smem > cap) continue;
             if ((size_t)ndir * nbg * UL_MAX_ATOMS * 4 > UL_COUNTER_BYTES - 64) continue;
             out->UB = UB; out->UBp = UBp; out->nub = nub; out->nbg = nbg; out->ctas = ctas; out->NA = NA;
