@@ -13,6 +13,9 @@ FLAGS = [
 ]
 
 
+FLAGS += os.environ.get("B200ASR_NVCC_EXTRA", "").split()      # e.g. -DB200ASR_GEMM_HH_FIRST=1 for an A/B build
+
+
 def sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 

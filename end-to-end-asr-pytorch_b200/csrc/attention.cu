@@ -309,26 +309,20 @@ __global__ void __launch_bounds__(MINB == 2 ? 384 : 512, MINB) locattn_bwd_kerne
     for (int tb = t0s; tb < t1s; tb += ATT_TT) {
         const int tv = min(min(t1s, len) - tb, ATT_TT);   // valid (unmasked) frames of this tile
         const int tn = min(t1s - tb, ATT_TT);              // frames of this tile
-        // the tile's key column of this thread, issued before the location convolution so that the loads overlap it
-        // (MINB = 2, fewer registers: only the first half; the second half is fetched while the first is consumed)
-        constexpr int KH = MINB == 2 ? ATT_TT / 2 : ATT_TT;
-        float kreg[KH], kreg2[ATT_TT / 2];
+        // the tile's key column of this thread, issued before the location convolution so that the 32 loads overlap it
+        // (a local array on purpose: fully unrolling the 32-frame body to keep it in registers measured slower)
+        float kreg[ATT_TT];
 #pragma unroll
-        for (int tl = 0; tl < KH; ++tl)
+        for (int tl = 0; tl < ATT_TT; ++tl)
             kreg[tl] = (d_own < D && tl < tv) ? p.key[((size_t)b * T + tb + tl) * D + d_own] : 0.f;
         if (tv > 0) conv_slice(s_prev, s_w, s_conv, K, W, tb, tv, ATT_TT);
         __syncthreads();
         if (d_own < D) {
             const float qd = s_q[d_own], ew = s_ew[d_own];
-            if (MINB == 2) {
-#pragma unroll
-                for (int tl = 0; tl < ATT_TT / 2; ++tl)
-                    kreg2[tl] = (ATT_TT / 2 + tl < tv) ? p.key[((size_t)b * T + tb + ATT_TT / 2 + tl) * D + d_own] : 0.f;
-            }
-#pragma unroll
+#pragma unroll 4
             for (int tl = 0; tl < ATT_TT; ++tl) {
                 if (tl >= tn) break;
-                const float kval = tl < KH ? kreg[tl < KH ? tl : 0] : kreg2[tl >= ATT_TT / 2 ? tl - ATT_TT / 2 : 0];
+                const float kval = kreg[tl];
                 const int t = tb + tl;
                 float dpre = 0.f, dloc = 0.f;
                 if (tl < tv) {
