@@ -104,9 +104,13 @@ __device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t smem_addr) {
     return d;
 }
 
-template <bool A_MN, bool B_MN>
+// B_PRE: the residual tile of B comes from a pre-computed residual matrix (same shape / layout as B: the weights, split
+// once per step by b200asr_tf32_residual) through its own tensor map, so the splitters only pass over the A tile and the
+// issuer can run  A.B  and  A.B_lo  (8 of the 12 MMAs of a K block) as soon as the TMA has landed.
+template <bool A_MN, bool B_MN, bool B_PRE>
 __global__ void __launch_bounds__(G_THREADS, 1)
-gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmArgs g) {
+gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+              const __grid_constant__ CUtensorMap map_blo, const GemmArgs g) {
     extern __shared__ __align__(1024) uint8_t smem[];
     // stage s: [A raw | B raw | A lo | B lo]
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + G_STAGES * G_STAGE_BYTES);   // TMA landed
@@ -155,7 +159,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                 const int s = i % G_STAGES;
                 if (i >= G_STAGES) mbar_wait(&empty[s], (uint32_t)(((i / G_STAGES) - 1) & 1));
                 uint8_t* st = smem + s * G_STAGE_BYTES;
-                mbar_expect_tx(&full[s], a_bytes + b_bytes);
+                mbar_expect_tx(&full[s], a_bytes + (B_PRE ? 2 * b_bytes : b_bytes));
                 const int bt = kb / g.kbt, t0 = (kb - bt * g.kbt) * G_BK;
                 if (A_MN) {
                     for (int j = 0; j < a_boxes; ++j)
@@ -168,6 +172,15 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                         tma_load_3d(st + G_A_BYTES + j * G_BOX, &map_b, n0 + 32 * j, t0 + g.b_shift, bt, &full[s]);
                 } else {
                     tma_load_2d(st + G_A_BYTES, &map_b, kb * G_BK, n0, &full[s]);
+                }
+                if (B_PRE) {                                   // residual of B -> the "B lo" slot of the stage
+                    uint8_t* lo = st + G_A_BYTES + G_B_BYTES + G_A_BYTES;
+                    if (B_MN) {
+                        for (int j = 0; j < b_boxes; ++j)
+                            tma_load_3d(lo + j * G_BOX, &map_blo, n0 + 32 * j, t0 + g.b_shift, bt, &full[s]);
+                    } else {
+                        tma_load_2d(lo, &map_blo, kb * G_BK, n0, &full[s]);
+                    }
                 }
             }
         }
@@ -185,9 +198,9 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                 const uint32_t d = tmem + 256u * buf;
                 const uint32_t a = smem_u32(smem + s * G_STAGE_BYTES), b = a + G_A_BYTES;
                 const uint32_t alo = b + G_B_BYTES, blo = alo + G_A_BYTES;
-                if (HH_FIRST) {
-                    // the hi.hi products need the raw tiles only: issue them when the TMA has landed, so that the
-                    // splitters' pass over the stage overlaps a third of its tensor-core work
+                if (HH_FIRST || B_PRE) {
+                    // the hi.hi products need the raw tiles only (and A.B_lo too when B's residual came by TMA): issue
+                    // them when the TMA has landed, so that the splitters' pass overlaps tensor-core work
                     mbar_wait(&full[s], (uint32_t)((i / G_STAGES) & 1));
                     umma::fence_after_sync();
 #pragma unroll
@@ -195,6 +208,10 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                         const uint64_t da = A_MN ? desc_mn_sw128(a + k4 * 1024) : umma::desc_k_sw128(a + k4 * 32);
                         const uint64_t db = B_MN ? desc_mn_sw128(b + k4 * 1024) : umma::desc_k_sw128(b + k4 * 32);
                         umma::mma_ss<umma::FMT_TF32>(d, da, db, idesc, (j | k4) != 0);
+                        if (B_PRE) {
+                            const uint64_t dbl = B_MN ? desc_mn_sw128(blo + k4 * 1024) : umma::desc_k_sw128(blo + k4 * 32);
+                            umma::mma_ss<umma::FMT_TF32>(d, da, dbl, idesc, 1);
+                        }
                     }
                 }
                 mbar_wait(&split[s], (uint32_t)((i / G_STAGES) & 1));
@@ -205,9 +222,9 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                     const uint64_t db = B_MN ? desc_mn_sw128(b + k4 * 1024) : umma::desc_k_sw128(b + k4 * 32);
                     const uint64_t dal = A_MN ? desc_mn_sw128(alo + k4 * 1024) : umma::desc_k_sw128(alo + k4 * 32);
                     const uint64_t dbl = B_MN ? desc_mn_sw128(blo + k4 * 1024) : umma::desc_k_sw128(blo + k4 * 32);
-                    if (!HH_FIRST) umma::mma_ss<umma::FMT_TF32>(d, da, db, idesc, (j | k4) != 0);
+                    if (!HH_FIRST && !B_PRE) umma::mma_ss<umma::FMT_TF32>(d, da, db, idesc, (j | k4) != 0);
                     umma::mma_ss<umma::FMT_TF32>(d, dal, db, idesc, 1);
-                    umma::mma_ss<umma::FMT_TF32>(d, da, dbl, idesc, 1);
+                    if (!B_PRE) umma::mma_ss<umma::FMT_TF32>(d, da, dbl, idesc, 1);
                 }
                 umma::commit(&empty[s]);
                 if (j == G_CH - 1 || i == nkb - 1) umma::commit(&acc_full[buf]);
@@ -243,7 +260,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             if (lane == 0) g_arrive(&acc_free[buf]);
         };
         // only the bytes that were loaded: A tile (or its valid boxes) and B tile (or its valid boxes)
-        const int a_vec = (int)(a_bytes / 16), b_vec = (int)(b_bytes / 16);
+        const int a_vec = (int)(a_bytes / 16), b_vec = B_PRE ? 0 : (int)(b_bytes / 16);
         for (int i = 0; i < nkb; ++i) {
             const int s = i % G_STAGES;
             mbar_wait(&full[s], (uint32_t)((i / G_STAGES) & 1));
@@ -325,6 +342,18 @@ __global__ void gemm3x_reduce_kernel(const float* __restrict__ partial, int nspl
     }
 }
 
+// lo = x - trunc_tf32(x): the residual the tensor core does not see when it reads the raw fp32 bit pattern
+__global__ void tf32_residual_kernel(const float* __restrict__ x, float* __restrict__ lo, long long n) {
+    const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i4 + 3 < n && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(lo)) & 15) == 0) {
+        const float4 v = *reinterpret_cast<const float4*>(x + i4);
+        *reinterpret_cast<float4*>(lo + i4) =
+            make_float4(tf32_residual(v.x), tf32_residual(v.y), tf32_residual(v.z), tf32_residual(v.w));
+    } else {
+        for (long long i = i4; i < n && i < i4 + 4; ++i) lo[i] = tf32_residual(x[i]);
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -382,18 +411,19 @@ int pick_split(int M, int N, int KB) {
     return s < 1 ? 1 : s;
 }
 
-template <bool A_MN, bool B_MN>
-int launch(const CUtensorMap& ma, const CUtensorMap& mb, GemmArgs g, void* ws, size_t ws_bytes, cudaStream_t stream) {
+template <bool A_MN, bool B_MN, bool B_PRE = false>
+int launch(const CUtensorMap& ma, const CUtensorMap& mb, GemmArgs g, void* ws, size_t ws_bytes, cudaStream_t stream,
+           const CUtensorMap* mblo = nullptr) {
     int nsplit = pick_split(g.M, g.N, g.KB);
     if (nsplit > 1 && (ws == nullptr || ws_bytes < (size_t)nsplit * g.M * g.N * sizeof(float))) nsplit = 1;
     g.kb_per_split = (g.KB + nsplit - 1) / nsplit;
     nsplit = (g.KB + g.kb_per_split - 1) / g.kb_per_split;       // no empty slices
     g.partial = reinterpret_cast<float*>(ws);
     const size_t smem = (size_t)G_STAGES * G_STAGE_BYTES + 256;
-    auto fn = gemm3x_kernel<A_MN, B_MN>;
+    auto fn = gemm3x_kernel<A_MN, B_MN, B_PRE>;
     B200_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((g.N + G_BN - 1) / G_BN, (g.M + G_BM - 1) / G_BM, nsplit);
-    fn<<<grid, G_THREADS, smem, stream>>>(ma, mb, g);
+    fn<<<grid, G_THREADS, smem, stream>>>(ma, mb, mblo ? *mblo : mb, g);
     B200_LAUNCH_CHECK("gemm3x_kernel");
     if (nsplit > 1) {
         const long long total = (long long)g.M * g.N;
@@ -432,7 +462,8 @@ extern "C" int b200asr_gemm3x_tn(const float* A, const float* B, const float* bi
 }
 
 static int gemm3x_tn_impl(const float* A, int lda, const float* B, const float* bias, float* C, int M, int N, int K,
-                          int ldc, int accumulate, void* ws, size_t ws_bytes, b200asr_stream stream) {
+                          int ldc, int accumulate, void* ws, size_t ws_bytes, b200asr_stream stream,
+                          const float* B_lo = nullptr) {
     B200_REQUIRE(A && B && C, "gemm3x_tn: null pointer");
     B200_REQUIRE(lda > 0 && (lda % 4) == 0, "gemm3x_tn: lda %d must be a positive multiple of 4", lda);
     B200_REQUIRE(b200asr_gemm3x_supported(M, N, K), "gemm3x_tn: unsupported sizes M=%d N=%d K=%d (K %% 4 must be 0)", M,
@@ -447,6 +478,13 @@ static int gemm3x_tn_impl(const float* A, int lda, const float* B, const float* 
     GemmArgs g = {};
     g.bias = bias; g.C = C; g.M = M; g.N = N; g.ldc = ldc; g.accumulate = accumulate;
     g.KB = (K + G_BK - 1) / G_BK; g.kbt = g.KB;
+    if (B_lo) {
+        B200_REQUIRE(aligned16(B_lo), "gemm3x_tn: operands must be 16-byte aligned");
+        CUtensorMap mlo;
+        rc = make_map_k(&mlo, B_lo, N, K, K, G_BN);
+        if (rc != B200_OK) return rc;
+        return launch<false, false, true>(ma, mb, g, ws, ws_bytes, (cudaStream_t)stream, &mlo);
+    }
     return launch<false, false>(ma, mb, g, ws, ws_bytes, (cudaStream_t)stream);
 }
 
@@ -462,7 +500,8 @@ extern "C" int b200asr_gemm3x_tn_ws(const float* A, int lda, const float* B, con
 }
 
 static int gemm3x_nn_impl(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int M, int N,
-                          int K, int ldc, int accumulate, void* ws, size_t ws_bytes, b200asr_stream stream) {
+                          int K, int ldc, int accumulate, void* ws, size_t ws_bytes, b200asr_stream stream,
+                          const float* B_lo = nullptr) {
     B200_REQUIRE(A && B && C, "gemm3x_nn: null pointer");
     B200_REQUIRE(M > 0 && N > 0 && K > 0, "gemm3x_nn: bad sizes M=%d N=%d K=%d", M, N, K);
     B200_REQUIRE(lda >= K && (lda % 4) == 0 && ldb >= N && (ldb % 4) == 0 && ldc >= N,
@@ -476,6 +515,13 @@ static int gemm3x_nn_impl(const float* A, int lda, const float* B, int ldb, cons
     GemmArgs g = {};
     g.bias = bias; g.C = C; g.M = M; g.N = N; g.ldc = ldc; g.accumulate = accumulate;
     g.KB = (K + G_BK - 1) / G_BK; g.kbt = g.KB;
+    if (B_lo) {
+        B200_REQUIRE(aligned16(B_lo), "gemm3x_nn: operands must be 16-byte aligned");
+        CUtensorMap mlo;
+        rc = make_map_mn(&mlo, B_lo, N, K, 1, ldb, 0);
+        if (rc != B200_OK) return rc;
+        return launch<false, true, true>(ma, mb, g, ws, ws_bytes, (cudaStream_t)stream, &mlo);
+    }
     return launch<false, true>(ma, mb, g, ws, ws_bytes, (cudaStream_t)stream);
 }
 
@@ -514,4 +560,27 @@ extern "C" int b200asr_gemm3x_nt(const float* A, long long lda, long long a_bstr
     g.kbt = (T + G_BK - 1) / G_BK; g.KB = g.kbt * batches;
     g.a_shift = a_shift; g.b_shift = b_shift;
     return launch<true, true>(ma, mb, g, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int b200asr_tf32_residual(const float* x, float* lo, long long n, b200asr_stream stream) {
+    B200_REQUIRE(x && lo && n >= 0, "tf32_residual: bad arguments");
+    if (n == 0) return B200_OK;
+    const long long threads = (n + 3) / 4;
+    tf32_residual_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, lo, n);
+    B200_LAUNCH_CHECK("tf32_residual_kernel");
+    return B200_OK;
+}
+
+extern "C" int b200asr_gemm3x_tn_pre(const float* A, int lda, const float* B, const float* B_lo, const float* bias,
+                                     float* C, int M, int N, int K, int ldc, int accumulate, void* workspace,
+                                     size_t workspace_bytes, b200asr_stream stream) {
+    B200_REQUIRE(B_lo, "gemm3x_tn_pre: null residual");
+    return gemm3x_tn_impl(A, lda, B, bias, C, M, N, K, ldc, accumulate, workspace, workspace_bytes, stream, B_lo);
+}
+
+extern "C" int b200asr_gemm3x_nn_pre(const float* A, int lda, const float* B, const float* B_lo, int ldb, const float* bias,
+                                     float* C, int M, int N, int K, int ldc, int accumulate, void* workspace,
+                                     size_t workspace_bytes, b200asr_stream stream) {
+    B200_REQUIRE(B_lo, "gemm3x_nn_pre: null residual");
+    return gemm3x_nn_impl(A, lda, B, ldb, bias, C, M, N, K, ldc, accumulate, workspace, workspace_bytes, stream, B_lo);
 }

@@ -49,8 +49,20 @@ def gate_perm(H, device):
 GEMM_MODE = os.environ.get("B200ASR_GEMM", "umma")
 
 
-def gemm_tn(a, w, bias=None, out=None, accumulate=False):
-    """out[M,N] (= or +=) a[M,K] @ w[N,K]^T (+ bias[N]) on the tensor cores at fp32-class accuracy (csrc/gemm.cu)."""
+def tf32_residual(w):
+    """w - trunc_tf32(w): the part of a weight matrix the tensor core does not see in the raw fp32 bit pattern.  Computed
+    once per step and weight (instead of once per tile by every CTA) for the `_pre` GEMM forms."""
+    lib = L.load()
+    w = _f32c(w)
+    lo = torch.empty_like(w)
+    with L.timed("tf32_residual", 8 * w.numel()):
+        L.check(lib.b200asr_tf32_residual(L.ptr(w), L.ptr(lo), w.numel(), L.stream()), "tf32_residual")
+    return lo
+
+
+def gemm_tn(a, w, bias=None, out=None, accumulate=False, w_lo=None):
+    """out[M,N] (= or +=) a[M,K] @ w[N,K]^T (+ bias[N]) on the tensor cores at fp32-class accuracy (csrc/gemm.cu).
+    w_lo = tf32_residual(w) selects the pre-split form."""
     lib = L.load()
     a, w = _f32c(a), _f32c(w)
     M, K = a.shape
@@ -62,7 +74,13 @@ def gemm_tn(a, w, bias=None, out=None, accumulate=False):
     b = _f32c(bias) if bias is not None else None
     # algorithmic bytes: both operands and the result once; flops 2*M*N*K (x3 tensor-core products)
     with L.timed("gemm3x_tn", 4 * (M * K + N * K + M * N * (2 if accumulate else 1))):
-        if M <= 256:          # skinny (the decoder's per-step products): split-K over all SMs
+        if w_lo is not None:
+            ws_bytes = lib.b200asr_gemm3x_workspace_bytes(M, N) if M <= 256 else 0
+            ws = torch.empty(max(ws_bytes, 16), device=a.device, dtype=torch.uint8)
+            L.check(lib.b200asr_gemm3x_tn_pre(L.ptr(a), K, L.ptr(w), L.ptr(w_lo), L.ptr(b), L.ptr(out), M, N, K,
+                                              out.stride(0), int(bool(accumulate)), L.ptr(ws), ws_bytes, L.stream()),
+                    "gemm3x_tn_pre")
+        elif M <= 256:          # skinny (the decoder's per-step products): split-K over all SMs
             ws_bytes = lib.b200asr_gemm3x_workspace_bytes(M, N)
             ws = torch.empty(max(ws_bytes, 16), device=a.device, dtype=torch.uint8)
             L.check(lib.b200asr_gemm3x_tn_ws(L.ptr(a), K, L.ptr(w), L.ptr(b), L.ptr(out), M, N, K, out.stride(0),
@@ -90,7 +108,7 @@ def gemm_tn_ld(a_base, lda, M, K, w, bias=None):
     return out
 
 
-def gemm_nn(a, w, out=None, accumulate=False):
+def gemm_nn(a, w, out=None, accumulate=False, w_lo=None):
     """out[M,N] (= or +=) a[M,K] @ w[K,N]: the input gradient dY . W with W read in place (MN-major operand)."""
     lib = L.load()
     a, w = _f32c(a), _f32c(w)
@@ -101,7 +119,13 @@ def gemm_nn(a, w, out=None, accumulate=False):
         accumulate = False
     assert out.stride(1) == 1 and out.shape == (M, N)
     with L.timed("gemm3x_nn", 4 * (M * K + N * K + M * N * (2 if accumulate else 1))):
-        if M <= 256:
+        if w_lo is not None:
+            ws_bytes = lib.b200asr_gemm3x_workspace_bytes(M, N) if M <= 256 else 0
+            ws = torch.empty(max(ws_bytes, 16), device=a.device, dtype=torch.uint8)
+            L.check(lib.b200asr_gemm3x_nn_pre(L.ptr(a), K, L.ptr(w), L.ptr(w_lo), N, None, L.ptr(out), M, N, K,
+                                              out.stride(0), int(bool(accumulate)), L.ptr(ws), ws_bytes, L.stream()),
+                    "gemm3x_nn_pre")
+        elif M <= 256:
             ws_bytes = lib.b200asr_gemm3x_workspace_bytes(M, N)
             ws = torch.empty(max(ws_bytes, 16), device=a.device, dtype=torch.uint8)
             L.check(lib.b200asr_gemm3x_nn_ws(L.ptr(a), K, L.ptr(w), N, None, L.ptr(out), M, N, K, out.stride(0),
@@ -282,13 +306,15 @@ class BiLSTMFn(Function):
         umma = _use_umma(I)
         xs = None if umma else Op(x.view(B * T, I))
         gates = torch.empty((ndir, B, T, H, 4), device=dev, dtype=torch.float32)
-        w_ih_p = []
+        w_ih_p, w_ih_lo = [], []
         for d in range(ndir):
             w_ih, w_hh, b_ih, b_hh = params[4 * d:4 * d + 4]
             wp = w_ih.detach().index_select(0, perm)
             bp = (b_ih.detach() + b_hh.detach()).index_select(0, perm)
             if umma:
-                gemm_tn(x.view(B * T, I), wp, bias=bp, out=gates[d].view(B * T, 4 * H))
+                wlo = tf32_residual(wp)            # once per step: shared by the forward product and the input gradient
+                gemm_tn(x.view(B * T, I), wp, bias=bp, out=gates[d].view(B * T, 4 * H), w_lo=wlo)
+                w_ih_lo.append(wlo)
             else:
                 mm(xs, Op(wp).t(), out=gates[d].view(B * T, 4 * H), bias=bp)
             w_ih_p.append(wp)
@@ -307,7 +333,7 @@ class BiLSTMFn(Function):
         ctx.ndir = ndir
         ctx.dims = (B, T, I, H)
         ctx.consumed = False
-        ctx.save_for_backward(x, gates, cst, out, w_hh, *w_ih_p)
+        ctx.save_for_backward(x, gates, cst, out, w_hh, *w_ih_p, *w_ih_lo)
         return out
 
     @staticmethod
@@ -320,7 +346,8 @@ class BiLSTMFn(Function):
         ndir = ctx.ndir
         B, T, I, H = ctx.dims
         x, gates, cst, out, w_hh = ctx.saved_tensors[:5]
-        w_ih_p = ctx.saved_tensors[5:]
+        w_ih_p = ctx.saved_tensors[5:5 + ndir]
+        w_ih_lo = ctx.saved_tensors[5 + ndir:]
         dev = x.device
         dout = _f32c(dout)
         ws_bytes = lib.b200asr_bilstm_workspace_bytes(B, T, H, ndir)
@@ -339,7 +366,7 @@ class BiLSTMFn(Function):
             for d in range(ndir):
                 g2 = gates[d].view(B * T, 4 * H)
                 if need_dx:
-                    gemm_nn(g2, w_ih_p[d], out=dx2, accumulate=(d > 0))
+                    gemm_nn(g2, w_ih_p[d], out=dx2, accumulate=(d > 0), w_lo=w_ih_lo[d] if len(w_ih_lo) == ndir else None)
                 dw_ih = gemm_nt(g2, x, 4 * H, I, B * T, permute_rows=True)
                 hd = out[:, :, d * H:(d + 1) * H]
                 dw_hh = gemm_nt(g2, hd, 4 * H, H, T, batches=B, a_bstride=T * 4 * H, ldb=ndir * H,
@@ -641,10 +668,13 @@ class DecWeightsFn(Function):
         ctx.mem = mem
         ctx.I = w_ih.shape[1]
         token = torch.zeros(1, device=w_ih.device, dtype=torch.float32)
-        return torch.cat([w_ih, w_hh], 1).contiguous(), (b_ih + b_hh).contiguous(), token
+        wcat = torch.cat([w_ih, w_hh], 1).contiguous()
+        wlo = tf32_residual(wcat)
+        ctx.mark_non_differentiable(wlo)
+        return wcat, (b_ih + b_hh).contiguous(), token, wlo
 
     @staticmethod
-    def backward(ctx, gW, gb, _gtoken):
+    def backward(ctx, gW, gb, _gtoken, _gwlo=None):
         mem, I = ctx.mem, ctx.I
         dW = gW
         db = gb
@@ -663,25 +693,25 @@ class DecWeightsFn(Function):
 
 class DecStepFn(Function):
     @staticmethod
-    def forward(ctx, mem, token, x, h, wcat, bias):
+    def forward(ctx, mem, token, x, h, wcat, bias, wlo):
         ctx.set_materialize_grads(False)
         xcat = torch.cat([x, h], 1).contiguous()
-        pre = gemm_tn(xcat, wcat, bias=bias)
-        ctx.save_for_backward(xcat, wcat)
+        pre = gemm_tn(xcat, wcat, bias=bias, w_lo=wlo)
+        ctx.save_for_backward(xcat, wcat, wlo)
         ctx.mem = mem
         ctx.I = x.shape[1]
         return pre
 
     @staticmethod
     def backward(ctx, dpre):
-        xcat, wcat = ctx.saved_tensors
+        xcat, wcat, wlo = ctx.saved_tensors
         if dpre is None:
-            return None, None, None, None, None, None
+            return None, None, None, None, None, None, None
         dpre = _f32c(dpre)
-        dx = gemm_nn(dpre, wcat)
+        dx = gemm_nn(dpre, wcat, w_lo=wlo)
         ctx.mem.dpre.append(dpre)
         ctx.mem.x.append(xcat)
-        return None, torch.zeros(1, device=dpre.device), dx[:, :ctx.I], dx[:, ctx.I:], None, None
+        return None, torch.zeros(1, device=dpre.device), dx[:, :ctx.I], dx[:, ctx.I:], None, None, None
 
 
 def decoder_weights(w_ih, w_hh, b_ih, b_hh):
@@ -692,8 +722,8 @@ def decoder_weights(w_ih, w_hh, b_ih, b_hh):
 
 def decoder_step(dw, x, h):
     """pre-activations [B, 4H] of one decoder LSTM step from decoder_weights()' handle."""
-    mem, wcat, bias, token = dw
-    return DecStepFn.apply(mem, token, x, h, wcat, bias)
+    mem, wcat, bias, token, wlo = dw
+    return DecStepFn.apply(mem, token, x, h, wcat, bias, wlo)
 
 
 def decoder_gemm_supported(I, H):
@@ -940,12 +970,14 @@ class Linear3xFn(Function):
         Op, mm = _gemm_ops()
         shp = x.shape
         x2 = _f32c(x).reshape(-1, shp[-1])
+        wlo = None
         if _use_umma(x2.shape[1]):
-            y = gemm_tn(x2, weight.detach(), bias=bias.detach() if bias is not None else None)
+            wlo = tf32_residual(weight.detach())
+            y = gemm_tn(x2, weight.detach(), bias=bias.detach() if bias is not None else None, w_lo=wlo)
         else:
             y = mm(Op(x2), Op(weight.detach()).t(), bias=bias.detach() if bias is not None else None,
                    out=torch.empty((x2.shape[0], weight.shape[0]), device=x.device, dtype=torch.float32))
-        ctx.save_for_backward(x2, weight)
+        ctx.save_for_backward(x2, weight, *([wlo] if wlo is not None else []))
         ctx.shp = shp
         ctx.has_bias = bias is not None
         return y.view(*shp[:-1], weight.shape[0])
@@ -953,13 +985,14 @@ class Linear3xFn(Function):
     @staticmethod
     def backward(ctx, gy):
         Op, mm = _gemm_ops()
-        x2, weight = ctx.saved_tensors
+        x2, weight = ctx.saved_tensors[:2]
+        wlo = ctx.saved_tensors[2] if len(ctx.saved_tensors) > 2 else None
         gy2 = _f32c(gy).reshape(-1, weight.shape[0])
         dx = None
         umma = _use_umma(weight.shape[0]) and _use_umma(weight.shape[1])
         if ctx.needs_input_grad[0]:
             if umma:
-                dx = gemm_nn(gy2, weight.detach()).view(ctx.shp)
+                dx = gemm_nn(gy2, weight.detach(), w_lo=wlo).view(ctx.shp)
             else:
                 dx = mm(Op(gy2), Op(weight.detach())).view(ctx.shp)
         dw = None

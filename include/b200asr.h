@@ -251,6 +251,18 @@ B200ASR_API int b200asr_gemm3x_nt(const float* A, long long lda, long long a_bst
                       int ldc, int accumulate, int permute_rows, void* workspace, size_t workspace_bytes,
                       b200asr_stream stream);
 
+/* the tn / nn forms with a PRE-SPLIT B operand: B_lo = B - trunc_tf32(B) (b200asr_tf32_residual; same shape and pitch
+ * as B) is the weight matrix' residual, computed once per step instead of once per tile by every CTA: its tile arrives
+ * by TMA like B's, the in-kernel splitter pass shrinks to the A tile and 8 of the 12 tensor-core products of a K block
+ * no longer wait for it.  workspace may be NULL.                                                                    */
+B200ASR_API int b200asr_tf32_residual(const float* x, float* lo, long long n, b200asr_stream stream);
+B200ASR_API int b200asr_gemm3x_tn_pre(const float* A, int lda, const float* B, const float* B_lo, const float* bias, float* C,
+                          int M, int N, int K, int ldc, int accumulate, void* workspace, size_t workspace_bytes,
+                          b200asr_stream stream);
+B200ASR_API int b200asr_gemm3x_nn_pre(const float* A, int lda, const float* B, const float* B_lo, int ldb, const float* bias,
+                          float* C, int M, int N, int K, int ldc, int accumulate, void* workspace,
+                          size_t workspace_bytes, b200asr_stream stream);
+
 /* ---- K6 helper: split fp32 into a TF32-representable high part and the fp32 residual ---------------------------
  * hi = x rounded to TF32, lo = x - hi; used to run the input-projection (src/module.py:131, inside nn.LSTM) and the
  * weight-gradient contractions as three error-compensated TF32 tensor-core GEMMs (3xTF32) at fp32-level accuracy.  */

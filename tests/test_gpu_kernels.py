@@ -640,6 +640,13 @@ def test_gemm3x_umma_is_fp32_class(pkg, M, N, K, acc):
     e3 = scaled_err(out.cpu().numpy(), ref.cpu().numpy())
     e1 = scaled_err(sg.cpu().numpy(), ref.cpu().numpy())
     assert e3 < 3e-6 and e3 < 20 * max(e1, 1e-7), (e3, e1)
+    # pre-split form: the residual of B computed once (b200asr_tf32_residual) and loaded by TMA
+    blo = pkg.ops.tf32_residual(b)
+    assert torch.equal((b.view(torch.int32) & -8192).view(torch.float32) + blo, b)
+    out.copy_(c0)
+    pkg.ops.gemm_tn(a, b, bias=bias, out=out, accumulate=acc, w_lo=blo)
+    e3 = scaled_err(out.cpu().numpy(), ref.cpu().numpy())
+    assert e3 < 3e-6 and e3 < 20 * max(e1, 1e-7), (e3, e1)
     if acc:
         assert torch.equal(buf[:, N:], buf[:, N:])                              # padding columns untouched (no NaN)
 
@@ -721,6 +728,10 @@ def test_gemm3x_nn_is_fp32_class(pkg, M, N, K, acc):
     sg = a @ b + (c0 if acc else 0)
     e3 = scaled_err(out.cpu().numpy(), ref.cpu().numpy())
     e1 = scaled_err(sg.cpu().numpy(), ref.cpu().numpy())
+    assert e3 < 3e-6 and e3 < 20 * max(e1, 1e-7), (e3, e1)
+    out.copy_(c0)
+    pkg.ops.gemm_nn(a, b, out=out, accumulate=acc, w_lo=pkg.ops.tf32_residual(b))          # pre-split form
+    e3 = scaled_err(out.cpu().numpy(), ref.cpu().numpy())
     assert e3 < 3e-6 and e3 < 20 * max(e1, 1e-7), (e3, e1)
 
 

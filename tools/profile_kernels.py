@@ -20,11 +20,13 @@ ce_logits = torch.randn(B * 40, V, generator=g).to(dev).requires_grad_(True)
 ce_tgt = torch.randint(0, V, (B * 40,), generator=g).to(dev)
 for it in range(2):
     tr.batch(wave, [N] * B)
-    lp, _ = pkg.ops.log_softmax(logits)
-    loss = pkg.CTCLoss(blank=0)(lp.transpose(0, 1), txt, il, tld)
+    head = pkg.ops.ctc_head(logits)                      # the train step's fused CTC head (row lse + arg-max only)
+    loss = pkg.CTCLoss(blank=0)(head.transpose(0, 1), txt, il, tld)
     loss.backward()
-    c, a = pkg.ops.loc_attention_step(q, key, val, prev, ln, cw, pw, ew, eb, 0.5)
-    (c.sum() + (a * a).sum()).backward()
+    mem, mk, mv, mcw, mpw, mew, meb, token = pkg.ops.attention_memory(key, val, cw, pw, ew, eb)   # decode-loop form
+    c, a = pkg.ops.loc_attention_mem_step(mem, token, q, mk, mv, prev, ln, mcw, mpw, mew, meb, 0.5)
+    c2, a2 = pkg.ops.loc_attention_mem_step(mem, token, q, mk, mv, a, ln, mcw, mpw, mew, meb, 0.5)
+    (c.sum() + c2.sum() + (a2 * a2).sum()).backward()
     pkg.ops.cross_entropy(ce_logits, ce_tgt).backward()
     torch.cuda.synchronize()
 print("done")

@@ -41,6 +41,11 @@ for M, N, K in shapes:
     dy = torch.randn(M, N, device=dev)
     fl = 2.0 * M * N * K / 1e9
     t = timeit(lambda: ops.gemm_tn(x, w))
+    wlo = ops.tf32_residual(w)
+    tp = timeit(lambda: ops.gemm_tn(x, w, w_lo=wlo))
+    print("tn  pre-split W                              own %7.3f ms (%6.1f TF)" % (tp, fl / tp), flush=True)
+    tp = timeit(lambda: ops.gemm_nn(dy, w, w_lo=wlo))
+    print("nn  pre-split W                              own %7.3f ms (%6.1f TF)" % (tp, fl / tp), flush=True)
     t2 = timeit(lambda: lib3(x, w.t()))
     t3 = timeit(lambda: tf32(x, w.t()))
     print("tn  y=x.W^T   M=%6d N=%5d K=%5d  own %7.3f ms (%6.1f TF)  cublas3x %7.3f ms  cublas-tf32x1 %7.3f ms" % (M, N, K, t, fl / t, t2, t3), flush=True)
