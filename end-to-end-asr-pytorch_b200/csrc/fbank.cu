@@ -203,6 +203,7 @@ constexpr int DC_MAX_ORDER = 2;
 constexpr int DC_MAX_TAPS = 33;
 constexpr int DC_COLS = 128;   // n_mel*(order+1) padded column count handled per CTA pass
 constexpr int DC_ROWS = 2;     // row phases (blockDim = DC_COLS*DC_ROWS)
+constexpr int DC_TCHUNK = 64;  // frames per CTA
 
 struct DeltaParams {
     const float* fb;
@@ -224,20 +225,51 @@ __device__ __forceinline__ float delta_value(const DeltaParams& p, const float* 
     return acc;
 }
 
+// The chunk's fbank rows [t0 - pad, t0 + DC_TCHUNK + pad) are staged ONCE in shared memory (zeros outside [0, m): the
+// zero padding of src/audio.py:57-77) together with the tap weights; the taps then read shared memory.  Same tap order
+// and the same fmaf chain as delta_value() above (a zero tap or a zero-padded row adds exactly 0), so the values are
+// bit-identical to the round-1 kernels that re-read global memory per tap (measured 0.05 of HBM: ~25 instructions per
+// tap, branchy).
+__device__ __forceinline__ void delta_stage(const DeltaParams& p, const float* fb, int m, int t0, float* s_fb,
+                                            float* s_filt) {
+    const int rows = DC_TCHUNK + p.taps - 1;
+    for (int i = threadIdx.x; i < rows * p.n_mel; i += blockDim.x) {
+        const int rl = i / p.n_mel, bin = i - rl * p.n_mel;
+        const int t = t0 - p.pad + rl;
+        s_fb[i] = (t >= 0 && t < m) ? fb[(long long)t * p.n_mel + bin] : 0.f;
+    }
+    for (int i = threadIdx.x; i < (DC_MAX_ORDER + 1) * DC_MAX_TAPS; i += blockDim.x)
+        s_filt[i] = p.filt[i / DC_MAX_TAPS][i % DC_MAX_TAPS];
+    __syncthreads();
+}
+__device__ __forceinline__ float delta_smem(const float* s_fb, const float* s_filt, int n_mel, int taps, int tl, int o,
+                                            int bin) {
+    float acc = 0.f;
+    const float* w = s_filt + o * DC_MAX_TAPS;
+    const float* x = s_fb + tl * n_mel + bin;          // row tl of the tile = frame t0 + tl - pad
+    for (int tap = 0; tap < taps; ++tap) acc = fmaf(w[tap], x[tap * n_mel], acc);
+    return acc;
+}
+
 // Pass 1: per (utterance, time chunk) partial sums of x and x^2 (fp64) for every output column.
 // Pass 2: every CTA re-reduces the chunk partials of its utterance in a fixed order (deterministic), then
 // normalises and writes its own time chunk.  Both passes recompute the (cheap) delta taps from the L2-resident fbank.
-constexpr int DC_TCHUNK = 64;
 
 __global__ void __launch_bounds__(DC_COLS* DC_ROWS) delta_stats_kernel(DeltaParams p, double* __restrict__ partial,
                                                                       int nchunk) {
     __shared__ double s_red[2][DC_ROWS][DC_COLS];
+    __shared__ float s_filt[(DC_MAX_ORDER + 1) * DC_MAX_TAPS];
+    extern __shared__ float s_fb[];
     const int b = blockIdx.y, ch = blockIdx.x;
     const int D = p.n_mel * (p.order + 1);
     const int m = p.n_frames[b];
     const float* fb = p.fb + (long long)b * p.t_max * p.n_mel;
     const int r = threadIdx.x / DC_COLS, cl = threadIdx.x % DC_COLS;
     const int t0 = ch * DC_TCHUNK, t1 = min(m, t0 + DC_TCHUNK);
+    if (t0 >= m) {                                      // chunk entirely in the padding: its partials are never read
+        return;
+    }
+    delta_stage(p, fb, m, t0, s_fb, s_filt);
     for (int c0 = 0; c0 < D; c0 += DC_COLS) {
         const int col = c0 + cl;
         const bool act = col < D;
@@ -246,7 +278,7 @@ __global__ void __launch_bounds__(DC_COLS* DC_ROWS) delta_stats_kernel(DeltaPara
         double s = 0.0, ss = 0.0;
         if (act)
             for (int t = t0 + r; t < t1; t += DC_ROWS) {
-                const double v = (double)delta_value(p, fb, m, t, o, bin);
+                const double v = (double)delta_smem(s_fb, s_filt, p.n_mel, p.taps, t - t0, o, bin);
                 s += v;
                 ss += v * v;
             }
@@ -267,6 +299,8 @@ __global__ void __launch_bounds__(DC_COLS* DC_ROWS) delta_stats_kernel(DeltaPara
 __global__ void __launch_bounds__(DC_COLS* DC_ROWS) delta_norm_kernel(DeltaParams p, const double* __restrict__ partial,
                                                                      int nchunk) {
     __shared__ float s_mean[DC_COLS], s_den[DC_COLS];
+    __shared__ float s_filt[(DC_MAX_ORDER + 1) * DC_MAX_TAPS];
+    extern __shared__ float s_fb[];
     const int b = blockIdx.y, ch = blockIdx.x;
     const int D = p.n_mel * (p.order + 1);
     const int m = p.n_frames[b];
@@ -275,6 +309,7 @@ __global__ void __launch_bounds__(DC_COLS* DC_ROWS) delta_norm_kernel(DeltaParam
     const int r = threadIdx.x / DC_COLS, cl = threadIdx.x % DC_COLS;
     const int t0 = ch * DC_TCHUNK, t1 = min(p.t_max, t0 + DC_TCHUNK);
     const int mchunks = (m + DC_TCHUNK - 1) / DC_TCHUNK;
+    delta_stage(p, fb, m, t0, s_fb, s_filt);
     for (int c0 = 0; c0 < D; c0 += DC_COLS) {
         const int col = c0 + cl;
         const bool act = col < D;
@@ -300,7 +335,7 @@ __global__ void __launch_bounds__(DC_COLS* DC_ROWS) delta_norm_kernel(DeltaParam
             for (int t = t0 + r; t < t1; t += DC_ROWS) {
                 float v = 0.f;
                 if (t < m) {
-                    v = delta_value(p, fb, m, t, o, bin);
+                    v = delta_smem(s_fb, s_filt, p.n_mel, p.taps, t - t0, o, bin);
                     if (p.apply_cmvn) v = (v - mean) / den;
                 }
                 out[(long long)t * D + col] = v;
@@ -421,13 +456,15 @@ extern "C" int b200asr_delta_cmvn_fwd(const float* fbank, const int* n_frames, i
     if (t_max == 0) return B200_OK;
     const int nchunk = (t_max + DC_TCHUNK - 1) / DC_TCHUNK;
     double* partial = reinterpret_cast<double*>(workspace);
+    const size_t smem = (size_t)(DC_TCHUNK + taps - 1) * n_mel * sizeof(float);
+    B200_REQUIRE(smem <= 40 * 1024, "delta_cmvn: %d mel bins x %d taps do not fit the shared-memory tile", n_mel, taps);
     if (apply_cmvn) {
         B200_REQUIRE(workspace && workspace_bytes >= b200asr_delta_cmvn_workspace_bytes(B, t_max, n_mel, delta_order),
                      "delta_cmvn: workspace too small");
-        delta_stats_kernel<<<dim3(nchunk, B), DC_COLS * DC_ROWS, 0, (cudaStream_t)stream>>>(p, partial, nchunk);
+        delta_stats_kernel<<<dim3(nchunk, B), DC_COLS * DC_ROWS, smem, (cudaStream_t)stream>>>(p, partial, nchunk);
         B200_LAUNCH_CHECK("delta_stats_kernel");
     }
-    delta_norm_kernel<<<dim3(nchunk, B), DC_COLS * DC_ROWS, 0, (cudaStream_t)stream>>>(p, partial, nchunk);
+    delta_norm_kernel<<<dim3(nchunk, B), DC_COLS * DC_ROWS, smem, (cudaStream_t)stream>>>(p, partial, nchunk);
     B200_LAUNCH_CHECK("delta_norm_kernel");
     return B200_OK;
 }
