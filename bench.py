@@ -404,8 +404,8 @@ def main():
               "parallelism": "dp%d (utterance shards; per-layer NCCL grad all-reduce buckets overlapped with backward)" % world,
               "l2": "inputs+activations per step (>1 GB) exceed the 126 MB L2; no explicit flush",
               "gemm": "own tcgen05 3xTF32 kernel in three operand forms (x.W^T, dY.W, dY^T.X incl. shifted h_prev reads, split-K, "
-                      "gate permutation in the epilogue), two-level accumulation (TMEM chunks of 128 k summed in fp32 "
-                      "registers); B200ASR_GEMM=tf32x3 selects the cuBLAS 3xTF32 composition; fp32-accurate",
+                      "gate permutation in the epilogue), weight residuals pre-split once per step, two-level accumulation (TMEM "
+                      "chunks of 128 k summed in fp32 registers); B200ASR_GEMM=tf32x3 selects the cuBLAS 3xTF32 composition; fp32-accurate",
               "lstm": "tcgen05 fp16 hi/lo 2x2-block split product, forward and backward (H = 256 ... 768; backward exchange: data-is-the-flag polling)"}
 
     # ------------------------------------------------------------------------------- reference (CPU) arm

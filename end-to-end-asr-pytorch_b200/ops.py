@@ -75,7 +75,7 @@ def gemm_tn(a, w, bias=None, out=None, accumulate=False, w_lo=None):
     # algorithmic bytes: both operands and the result once; flops 2*M*N*K (x3 tensor-core products)
     with L.timed("gemm3x_tn", 4 * (M * K + N * K + M * N * (2 if accumulate else 1))):
         if w_lo is not None:
-            ws_bytes = lib.b200asr_gemm3x_workspace_bytes(M, N) if M <= 256 else 0
+            ws_bytes = lib.b200asr_gemm3x_workspace_bytes(M, N)
             ws = torch.empty(max(ws_bytes, 16), device=a.device, dtype=torch.uint8)
             L.check(lib.b200asr_gemm3x_tn_pre(L.ptr(a), K, L.ptr(w), L.ptr(w_lo), L.ptr(b), L.ptr(out), M, N, K,
                                               out.stride(0), int(bool(accumulate)), L.ptr(ws), ws_bytes, L.stream()),
@@ -120,7 +120,7 @@ def gemm_nn(a, w, out=None, accumulate=False, w_lo=None):
     assert out.stride(1) == 1 and out.shape == (M, N)
     with L.timed("gemm3x_nn", 4 * (M * K + N * K + M * N * (2 if accumulate else 1))):
         if w_lo is not None:
-            ws_bytes = lib.b200asr_gemm3x_workspace_bytes(M, N) if M <= 256 else 0
+            ws_bytes = lib.b200asr_gemm3x_workspace_bytes(M, N)
             ws = torch.empty(max(ws_bytes, 16), device=a.device, dtype=torch.uint8)
             L.check(lib.b200asr_gemm3x_nn_pre(L.ptr(a), K, L.ptr(w), L.ptr(w_lo), N, None, L.ptr(out), M, N, K,
                                               out.stride(0), int(bool(accumulate)), L.ptr(ws), ws_bytes, L.stream()),
