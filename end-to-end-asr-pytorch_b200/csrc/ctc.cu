@@ -158,6 +158,17 @@ __device__ __forceinline__ float lse3(float a, float b, float c) {
     return logf(expf(a - m) + expf(b - m) + expf(c - m)) + m;
 }
 
+// 4-byte asynchronous global -> shared copies, tracked by commit groups (cp.async.wait_group) instead of register scoreboards
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+constexpr int CTC_PD = 8;                    // frames of emission look-ahead in the warp kernel
+
 __global__ void __launch_bounds__(1024) ctc_alpha_beta_kernel(CtcParams p) {
     extern __shared__ float s_dyn[];
     const int S_max = p.S_max;
@@ -238,19 +249,25 @@ __global__ void __launch_bounds__(1024) ctc_alpha_beta_kernel(CtcParams p) {
     }
     if (S_max <= (int)blockDim.x) {
         // one lattice position per thread (every target shorter than 512 labels): the emission gathers run PD frames
-        // ahead in a register ring, off the T-long dependency chain
+        // ahead in a register ring, off the T-long dependency chain.  The ring holds the RAW loads (logit and row lse);
+        // the subtraction happens at the consumer - an FADD next to the load makes the warp wait for the gather right
+        // there.  (The cp.async ring of the warp kernel was measured here too: 25 % slower with a barrier per frame.)
         constexpr int PD = 4;
         const int s = threadIdx.x;
         const bool act = s < Sb;
         const int l = act ? lab[s] : 0;
         const int sk = (s < S_max) ? skip[s] : 0;
         const float* lseb = p.lse ? p.lse + (long long)b * p.T : nullptr;
-        float eq[PD];
+        float eq[PD], lq[PD];
 #pragma unroll
         for (int d = 0; d < PD; ++d) {
             const int st = 1 + d;
             eq[d] = 0.f;
-            if (st < Tb && act) eq[d] = lpb[(long long)(t0 + dt * st) * p.st + l] - (lseb ? lseb[t0 + dt * st] : 0.f);
+            lq[d] = 0.f;
+            if (st < Tb && act) {
+                eq[d] = lpb[(long long)(t0 + dt * st) * p.st + l];
+                if (lseb) lq[d] = lseb[t0 + dt * st];
+            }
         }
         for (int base = 1; base < Tb; base += PD) {
 #pragma unroll
@@ -258,9 +275,11 @@ __global__ void __launch_bounds__(1024) ctc_alpha_beta_kernel(CtcParams p) {
                 const int step = base + d;
                 if (step >= Tb) break;                       // block-uniform
                 const int t = t0 + dt * step;
-                const float e = eq[d];
-                if (step + PD < Tb && act)
-                    eq[d] = lpb[(long long)(t + dt * PD) * p.st + l] - (lseb ? lseb[t + dt * PD] : 0.f);
+                const float e = eq[d] - lq[d];
+                if (step + PD < Tb && act) {
+                    eq[d] = lpb[(long long)(t + dt * PD) * p.st + l];
+                    if (lseb) lq[d] = lseb[t + dt * PD];
+                }
                 __syncthreads();  // prev fully written
                 if (s < S_max) {
                     float v = NEG_INF;
@@ -336,6 +355,8 @@ __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_alpha_beta_warp_kernel(Ctc
     const int S_max = p.S_max;
     int* lab_s = reinterpret_cast<int*>(s_dyn) + (size_t)warp * 2 * S_max;
     float* row_s = reinterpret_cast<float*>(lab_s + S_max);
+    constexpr int SLOT = (R + 1) * 32;                   // one frame of the look-ahead ring: [r][lane] logits + [lane] row lse
+    float* ring = s_dyn + (size_t)CTC_WARPS * 2 * S_max + (size_t)warp * CTC_PD * SLOT;
 
     long long Tb64 = p.in_len[b];
     long long Lb64 = p.tgt_len[b];
@@ -385,12 +406,24 @@ __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_alpha_beta_warp_kernel(Ctc
     }
     const int t0 = is_beta ? Tb - 1 : 0;
     const int dt = is_beta ? -1 : 1;
-    // The emission gathers x[t, label] are independent of the recursion: they are kept PD frames ahead in a register
-    // ring, so the T-long chain never waits for the ~1000-cycle gather latency (measured: the one-frame look-ahead of
-    // round 1 left the kernel latency-bound at ~1300 cycles per frame).
-    constexpr int PD = 4;
-    float a[R], eq[PD][R];
+    // The emission gathers x[t, label] are independent of the recursion: they run CTC_PD frames ahead as cp.async copies
+    // into a per-warp shared-memory ring, one commit group per frame; every lane reads back only what it copied itself.
+    // Measured at V = 5000 (1000 utterances, L2 flushed): register ring with the "- lse" next to the load 2.31 ms (the
+    // FADD stalls on the load it follows), register ring of raw loads 1.49 ms, this ring 1.30 ms.  What is left is the
+    // DRAM traffic of the gathers themselves: 2 directions x T' x S positions x one 32-byte sector each is about half of
+    // the logits tensor, fetched at sector granularity.
+    float a[R];
     const float* lseb = p.lse ? p.lse + (long long)b * p.T : nullptr;
+    auto prefetch = [&](int st) {                        // frame t0 + dt * st -> ring slot st % CTC_PD
+        if (st < Tb) {
+            const float* lpn = lpb + (long long)(t0 + dt * st) * p.st;
+            float* sl = ring + (st % CTC_PD) * SLOT;
+#pragma unroll
+            for (int r = 0; r < R; ++r) cp_async4(sl + r * 32 + lane, lpn + lab[r]);
+            if (lseb) cp_async4(sl + R * 32 + lane, lseb + t0 + dt * st);
+        }
+        cp_async_commit();                               // (possibly empty) group: the group count stays one per frame
+    };
     {   // boundary row
         const float* lpt = lpb + (long long)t0 * p.st;
         const float ls = lseb ? lseb[t0] : 0.f;
@@ -408,32 +441,20 @@ __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_alpha_beta_warp_kernel(Ctc
             a[r] = v;
             if (s < S_max) lat[(long long)t0 * S_max + s] = v;
         }
-#pragma unroll
-        for (int d = 0; d < PD; ++d) {
-            const int st = 1 + d;
-            if (st < Tb) {
-                const float* lpn = lpb + (long long)(t0 + dt * st) * p.st;
-                const float lsn = lseb ? lseb[t0 + dt * st] : 0.f;
-#pragma unroll
-                for (int r = 0; r < R; ++r) eq[d][r] = lpn[lab[r]] - lsn;
-            }
-        }
+        for (int st = 1; st <= CTC_PD; ++st) prefetch(st);
     }
-    for (int base = 1; base < Tb; base += PD) {
-#pragma unroll
-        for (int d = 0; d < PD; ++d) {
-            const int step = base + d;
-            if (step >= Tb) break;                       // warp-uniform
+    for (int step = 1; step < Tb; ++step) {
+        {
             const int t = t0 + dt * step;
+            cp_async_wait<CTC_PD - 1>();                 // groups 1 .. step have landed
             float e[R];
+            {
+                const float* sl = ring + (step % CTC_PD) * SLOT;
+                const float ls = lseb ? sl[R * 32 + lane] : 0.f;
 #pragma unroll
-            for (int r = 0; r < R; ++r) e[r] = eq[d][r];
-            if (step + PD < Tb) {                        // refill this ring slot for frame step + PD
-                const float* lpn = lpb + (long long)(t + dt * PD) * p.st;
-                const float lsn = lseb ? lseb[t + dt * PD] : 0.f;
-#pragma unroll
-                for (int r = 0; r < R; ++r) eq[d][r] = lpn[lab[r]] - lsn;
+                for (int r = 0; r < R; ++r) e[r] = sl[r * 32 + lane] - ls;
             }
+            prefetch(step + CTC_PD);                     // refill the slot just read
             // neighbours across the lane boundary
             float n1, n2;
             if (!is_beta) {
@@ -491,7 +512,7 @@ __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_alpha_beta_warp_kernel(Ctc
 template <int R>
 static int launch_ctc_warp(const CtcParams& p, cudaStream_t stream) {
     const int items = 2 * p.B;
-    const size_t smem = (size_t)CTC_WARPS * 2 * p.S_max * sizeof(float);
+    const size_t smem = (size_t)CTC_WARPS * (2 * p.S_max + CTC_PD * (R + 1) * 32) * sizeof(float);
     ctc_alpha_beta_warp_kernel<R><<<(items + CTC_WARPS - 1) / CTC_WARPS, CTC_WARPS * 32, smem, stream>>>(p);
     return 0;
 }
@@ -499,15 +520,14 @@ static int launch_ctc_warp(const CtcParams& p, cudaStream_t stream) {
 constexpr int CTC_GRAD_THREADS = 256;
 constexpr int CTC_GRAD_TCHUNK = 8;
 
-__global__ void __launch_bounds__(CTC_GRAD_THREADS) ctc_grad_kernel(CtcParams p) {
+__global__ void __launch_bounds__(CTC_GRAD_THREADS, 8) ctc_grad_kernel(CtcParams p) {
     // grid (T chunks, B).  Phase 1 streams the dense part  g = exp(lp) * scale  of every row of the chunk (pure
     // 128-bit streaming, no barrier); phase 2 subtracts the label-occupancy term at the <= L+1 distinct classes of the
     // utterance (deterministic occurrence-chain sums, one owner thread per class, no atomics).
     extern __shared__ __align__(16) float s_dyn[];
-    __shared__ float s_scratch[32];
     const int S_max = p.S_max, V = p.V;
-    float* e = s_dyn;               // [S_max]
-    int* lab = reinterpret_cast<int*>(e + S_max);
+    float* e = s_dyn;               // [warps][S_max]
+    int* lab = reinterpret_cast<int*>(e + (size_t)(CTC_GRAD_THREADS / 32) * S_max);
     int* prev_same = lab + S_max;
     int* is_last = prev_same + S_max;
 
@@ -535,64 +555,80 @@ __global__ void __launch_bounds__(CTC_GRAD_THREADS) ctc_grad_kernel(CtcParams p)
 
     const int t_begin = blockIdx.x * CTC_GRAD_TCHUNK;
     const int t_end = min(p.T, t_begin + CTC_GRAD_TCHUNK);
-    // ---- phase 1: dense stream
-    for (int t = t_begin; t < t_end; ++t) {
-        float* gt = p.grad + (long long)b * p.sb + (long long)t * p.st;
-        const float* lpt = p.lp + (long long)b * p.sb + (long long)t * p.st;
-        const bool live = t < Tb;
-        const float ls = (p.lse && live) ? p.lse[(long long)b * p.T + t] : 0.f;
-        if (vec4) {
-            const float4* l4 = reinterpret_cast<const float4*>(lpt);
-            float4* g4 = reinterpret_cast<float4*>(gt);
-            for (int c = threadIdx.x; c < (V >> 2); c += blockDim.x) {
-                float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (live) {
-                    const float4 l = l4[c];
-                    o = make_float4(expf(l.x - ls) * scale, expf(l.y - ls) * scale, expf(l.z - ls) * scale,
-                                    expf(l.w - ls) * scale);
-                }
-                g4[c] = o;
-            }
-        } else {
+    // ---- phase 1: dense stream.  The chunk's rows are one flat index space, two 128-bit loads in flight per thread
+    // at 8 resident blocks per SM (the register budget of __launch_bounds__(256, 8): occupancy is what hides phase 2)
+    if (vec4) {
+        const int n4 = V >> 2, total = (t_end - t_begin) * n4;
+        const float* lp0 = p.lp + (long long)b * p.sb;
+        float* g0 = p.grad + (long long)b * p.sb;
+        const float* lse0 = p.lse ? p.lse + (long long)b * p.T : nullptr;
+        for (int i0 = threadIdx.x; i0 < total; i0 += 2 * CTC_GRAD_THREADS) {
+            const int i1 = i0 + CTC_GRAD_THREADS;
+            const int r0 = i0 / n4, r1 = i1 / n4;
+            const long long o0 = (long long)(t_begin + r0) * p.st + 4 * (i0 - r0 * n4);
+            const long long o1 = (long long)(t_begin + r1) * p.st + 4 * (i1 - r1 * n4);
+            const bool live0 = t_begin + r0 < Tb, live1 = i1 < total && t_begin + r1 < Tb;
+            float4 l0 = make_float4(0.f, 0.f, 0.f, 0.f), l1 = l0;
+            float ls0 = 0.f, ls1 = 0.f;
+            if (live0) l0 = __ldcs(reinterpret_cast<const float4*>(lp0 + o0));
+            if (live1) l1 = __ldcs(reinterpret_cast<const float4*>(lp0 + o1));
+            if (lse0 && live0) ls0 = lse0[t_begin + r0];
+            if (lse0 && live1) ls1 = lse0[t_begin + r1];
+            const float s0 = live0 ? scale : 0.f, s1 = live1 ? scale : 0.f;
+            *reinterpret_cast<float4*>(g0 + o0) =
+                make_float4(expf(l0.x - ls0) * s0, expf(l0.y - ls0) * s0, expf(l0.z - ls0) * s0, expf(l0.w - ls0) * s0);
+            if (i1 < total)
+                *reinterpret_cast<float4*>(g0 + o1) =
+                    make_float4(expf(l1.x - ls1) * s1, expf(l1.y - ls1) * s1, expf(l1.z - ls1) * s1, expf(l1.w - ls1) * s1);
+        }
+    } else {
+        for (int t = t_begin; t < t_end; ++t) {
+            float* gt = p.grad + (long long)b * p.sb + (long long)t * p.st;
+            const float* lpt = p.lp + (long long)b * p.sb + (long long)t * p.st;
+            const bool live = t < Tb;
+            const float ls = (p.lse && live) ? p.lse[(long long)b * p.T + t] : 0.f;
             for (int c = threadIdx.x; c < V; c += blockDim.x) gt[c] = live ? expf(lpt[c] - ls) * scale : 0.f;
         }
     }
     __syncthreads();
-    // ---- phase 2: occupancy of the utterance's own classes
-    for (int t = t_begin; t < t_end && t < Tb; ++t) {
+    // ---- phase 2: occupancy of the utterance's own classes.  One WARP per frame of the chunk (warp-synchronous: the
+    // block-wide version spent its time in ~10 barriers per frame, which the other resident blocks had to cover)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* ew = e + (size_t)warp * S_max;
+    for (int t = t_begin + warp; t < t_end && t < Tb; t += CTC_GRAD_THREADS / 32) {
         float* gt = p.grad + (long long)b * p.sb + (long long)t * p.st;
         const float* lpt = p.lp + (long long)b * p.sb + (long long)t * p.st;
         const float* al = p.alpha + ((long long)b * p.T + t) * S_max;
         const float* be = p.beta + ((long long)b * p.T + t) * S_max;
         const float ls = p.lse ? p.lse[(long long)b * p.T + t] : 0.f;
         float mx = NEG_INF;
-        for (int s = threadIdx.x; s < Sb; s += blockDim.x) {
+        for (int s = lane; s < Sb; s += 32) {
             const float v = al[s] + be[s];
-            e[s] = v;
+            ew[s] = v;
             mx = fmaxf(mx, v);
         }
-        const float m = block_max(mx, s_scratch);  // includes __syncthreads
-        for (int s = threadIdx.x; s < Sb; s += blockDim.x) {
-            const float v = e[s];
-            e[s] = (v == NEG_INF) ? 0.f : expf(v - m);
+        const float m = warp_max(mx);
+        for (int s = lane; s < Sb; s += 32) {
+            const float v = ew[s];
+            ew[s] = (v == NEG_INF) ? 0.f : expf(v - m);
         }
-        __syncthreads();
-        // blank (even s): fixed-order per-thread partials + fixed tree
+        __syncwarp();
+        // blank (even s): fixed-order per-lane partials + fixed shuffle tree
         float part = 0.f;
-        for (int s = 2 * threadIdx.x; s < Sb; s += 2 * blockDim.x) part += e[s];
-        const float tot_blank = block_sum(part, s_scratch);
-        if (threadIdx.x == 0 && tot_blank > 0.f)
+        for (int s = 2 * lane; s < Sb; s += 64) part += ew[s];
+        const float tot_blank = warp_sum(part);
+        if (lane == 0 && tot_blank > 0.f)
             gt[p.blank] -= expf(logf(tot_blank) + m + nll - (lpt[p.blank] - ls)) * scale;
-        // labels (odd s): the thread owning the last occurrence walks the chain backwards
-        for (int s = 2 * threadIdx.x + 1; s < Sb; s += 2 * blockDim.x) {
+        // labels (odd s): the lane owning the last occurrence walks the chain backwards
+        for (int s = 2 * lane + 1; s < Sb; s += 64) {
             if (is_last[s]) {
                 float tot = 0.f;
-                for (int q = s; q >= 0; q = prev_same[q]) tot += e[q];
+                for (int q = s; q >= 0; q = prev_same[q]) tot += ew[q];
                 const int l = lab[s];
                 if (l >= 0 && l != p.blank && tot > 0.f) gt[l] -= expf(logf(tot) + m + nll - (lpt[l] - ls)) * scale;
             }
         }
-        __syncthreads();
+        __syncwarp();
     }
 }
 
@@ -653,7 +689,7 @@ static int ctc_setup(CtcParams& p, const float* log_probs, const float* row_lse,
 
 static int ctc_launch_grad(const CtcParams& p, cudaStream_t stream) {
     const size_t S = (size_t)p.S_max;
-    const size_t smem_g = S * (sizeof(float) + 3 * sizeof(int));
+    const size_t smem_g = S * ((CTC_GRAD_THREADS / 32) * sizeof(float) + 3 * sizeof(int));
     B200_REQUIRE(smem_g <= (size_t)max_optin_smem(), "ctc: target too long for shared memory (L=%d)", p.L_max);
     if (smem_g > 48 * 1024)
         B200_CUDA(cudaFuncSetAttribute(ctc_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
