@@ -107,10 +107,17 @@ __device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t smem_addr) {
 // B_PRE: the residual tile of B comes from a pre-computed residual matrix (same shape / layout as B: the weights, split
 // once per step by b200asr_tf32_residual) through its own tensor map, so the splitters only pass over the A tile and the
 // issuer can run  A.B  and  A.B_lo  (8 of the 12 MMAs of a K block) as soon as the TMA has landed.
-template <bool A_MN, bool B_MN, bool B_PRE>
+// A_PRE: the same for A (an activation / gradient matrix whose residual the caller made once and uses in several
+// products).  With both, the splitters have nothing to split: all 12 MMAs of a K block are issued when the TMA has
+// landed and shared memory sees 240 KB of traffic per K block instead of 288.  Measured SLOWER than B_PRE alone
+// (tn 248 -> 232, nn 233 -> 208 TFLOP/s, nt unchanged at 180): per K block the SM then takes in 96 KB through TMA
+// instead of 80 (64 without any pre-split), and the L2 -> SM path (measured ceiling ~45-50 B/clk/SM,
+// tools/micro/xfer_probe.cu; 33 B/clk/SM at 248 TFLOP/s) is the tighter resource.  Kept as a tested option; the step
+// uses B_PRE (weights) only.  What would lift this bound is a CTA pair sharing the B tile (cta_group::2).
+template <bool A_MN, bool B_MN, bool B_PRE, bool A_PRE>
 __global__ void __launch_bounds__(G_THREADS, 1)
 gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-              const __grid_constant__ CUtensorMap map_blo, const GemmArgs g) {
+              const __grid_constant__ CUtensorMap map_blo, const __grid_constant__ CUtensorMap map_alo, const GemmArgs g) {
     extern __shared__ __align__(1024) uint8_t smem[];
     // stage s: [A raw | B raw | A lo | B lo]
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + G_STAGES * G_STAGE_BYTES);   // TMA landed
@@ -159,7 +166,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                 const int s = i % G_STAGES;
                 if (i >= G_STAGES) mbar_wait(&empty[s], (uint32_t)(((i / G_STAGES) - 1) & 1));
                 uint8_t* st = smem + s * G_STAGE_BYTES;
-                mbar_expect_tx(&full[s], a_bytes + (B_PRE ? 2 * b_bytes : b_bytes));
+                mbar_expect_tx(&full[s], (A_PRE ? 2 * a_bytes : a_bytes) + (B_PRE ? 2 * b_bytes : b_bytes));
                 const int bt = kb / g.kbt, t0 = (kb - bt * g.kbt) * G_BK;
                 if (A_MN) {
                     for (int j = 0; j < a_boxes; ++j)
@@ -172,6 +179,15 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                         tma_load_3d(st + G_A_BYTES + j * G_BOX, &map_b, n0 + 32 * j, t0 + g.b_shift, bt, &full[s]);
                 } else {
                     tma_load_2d(st + G_A_BYTES, &map_b, kb * G_BK, n0, &full[s]);
+                }
+                if (A_PRE) {                                   // residual of A -> the "A lo" slot of the stage
+                    uint8_t* lo = st + G_A_BYTES + G_B_BYTES;
+                    if (A_MN) {
+                        for (int j = 0; j < a_boxes; ++j)
+                            tma_load_3d(lo + j * G_BOX, &map_alo, m0 + 32 * j, t0 + g.a_shift, bt, &full[s]);
+                    } else {
+                        tma_load_2d(lo, &map_alo, kb * G_BK, m0, &full[s]);
+                    }
                 }
                 if (B_PRE) {                                   // residual of B -> the "B lo" slot of the stage
                     uint8_t* lo = st + G_A_BYTES + G_B_BYTES + G_A_BYTES;
@@ -198,7 +214,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                 const uint32_t d = tmem + 256u * buf;
                 const uint32_t a = smem_u32(smem + s * G_STAGE_BYTES), b = a + G_A_BYTES;
                 const uint32_t alo = b + G_B_BYTES, blo = alo + G_A_BYTES;
-                if (HH_FIRST || B_PRE) {
+                if (HH_FIRST || B_PRE || A_PRE) {
                     // the hi.hi products need the raw tiles only (and A.B_lo too when B's residual came by TMA): issue
                     // them when the TMA has landed, so that the splitters' pass overlaps tensor-core work
                     mbar_wait(&full[s], (uint32_t)((i / G_STAGES) & 1));
@@ -212,19 +228,25 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                             const uint64_t dbl = B_MN ? desc_mn_sw128(blo + k4 * 1024) : umma::desc_k_sw128(blo + k4 * 32);
                             umma::mma_ss<umma::FMT_TF32>(d, da, dbl, idesc, 1);
                         }
+                        if (A_PRE) {
+                            const uint64_t dal = A_MN ? desc_mn_sw128(alo + k4 * 1024) : umma::desc_k_sw128(alo + k4 * 32);
+                            umma::mma_ss<umma::FMT_TF32>(d, dal, db, idesc, 1);
+                        }
                     }
                 }
-                mbar_wait(&split[s], (uint32_t)((i / G_STAGES) & 1));
-                umma::fence_after_sync();
+                if (!(A_PRE && B_PRE)) {
+                    mbar_wait(&split[s], (uint32_t)((i / G_STAGES) & 1));
+                    umma::fence_after_sync();
 #pragma unroll
-                for (int k4 = 0; k4 < G_BK / 8; ++k4) {
-                    const uint64_t da = A_MN ? desc_mn_sw128(a + k4 * 1024) : umma::desc_k_sw128(a + k4 * 32);
-                    const uint64_t db = B_MN ? desc_mn_sw128(b + k4 * 1024) : umma::desc_k_sw128(b + k4 * 32);
-                    const uint64_t dal = A_MN ? desc_mn_sw128(alo + k4 * 1024) : umma::desc_k_sw128(alo + k4 * 32);
-                    const uint64_t dbl = B_MN ? desc_mn_sw128(blo + k4 * 1024) : umma::desc_k_sw128(blo + k4 * 32);
-                    if (!HH_FIRST && !B_PRE) umma::mma_ss<umma::FMT_TF32>(d, da, db, idesc, (j | k4) != 0);
-                    umma::mma_ss<umma::FMT_TF32>(d, dal, db, idesc, 1);
-                    if (!B_PRE) umma::mma_ss<umma::FMT_TF32>(d, da, dbl, idesc, 1);
+                    for (int k4 = 0; k4 < G_BK / 8; ++k4) {
+                        const uint64_t da = A_MN ? desc_mn_sw128(a + k4 * 1024) : umma::desc_k_sw128(a + k4 * 32);
+                        const uint64_t db = B_MN ? desc_mn_sw128(b + k4 * 1024) : umma::desc_k_sw128(b + k4 * 32);
+                        const uint64_t dal = A_MN ? desc_mn_sw128(alo + k4 * 1024) : umma::desc_k_sw128(alo + k4 * 32);
+                        const uint64_t dbl = B_MN ? desc_mn_sw128(blo + k4 * 1024) : umma::desc_k_sw128(blo + k4 * 32);
+                        if (!HH_FIRST && !B_PRE && !A_PRE) umma::mma_ss<umma::FMT_TF32>(d, da, db, idesc, (j | k4) != 0);
+                        if (!A_PRE) umma::mma_ss<umma::FMT_TF32>(d, dal, db, idesc, 1);
+                        if (!B_PRE) umma::mma_ss<umma::FMT_TF32>(d, da, dbl, idesc, 1);
+                    }
                 }
                 umma::commit(&empty[s]);
                 if (j == G_CH - 1 || i == nkb - 1) umma::commit(&acc_full[buf]);
@@ -260,7 +282,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             if (lane == 0) g_arrive(&acc_free[buf]);
         };
         // only the bytes that were loaded: A tile (or its valid boxes) and B tile (or its valid boxes)
-        const int a_vec = (int)(a_bytes / 16), b_vec = B_PRE ? 0 : (int)(b_bytes / 16);
+        const int a_vec = A_PRE ? 0 : (int)(a_bytes / 16), b_vec = B_PRE ? 0 : (int)(b_bytes / 16);
         for (int i = 0; i < nkb; ++i) {
             const int s = i % G_STAGES;
             mbar_wait(&full[s], (uint32_t)((i / G_STAGES) & 1));
@@ -276,9 +298,11 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                 const float4 v = src[j];
                 dst[j] = make_float4(tf32_residual(v.x), tf32_residual(v.y), tf32_residual(v.z), tf32_residual(v.w));
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) g_arrive(&split[s]);
+            if (!(A_PRE && B_PRE)) {                      // (nothing was written and nobody waits otherwise)
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) g_arrive(&split[s]);
+            }
             // chunk i/G_CH - 1 retired at the latest when K block i-2 left the 2-stage ring: drain it now
             if (i >= G_CH && (i % G_CH) == 1) drain(next_drain++);
         }
@@ -435,19 +459,19 @@ int pick_split(int M, int N, int KB) {
     return s;
 }
 
-template <bool A_MN, bool B_MN, bool B_PRE = false>
+template <bool A_MN, bool B_MN, bool B_PRE = false, bool A_PRE = false>
 int launch(const CUtensorMap& ma, const CUtensorMap& mb, GemmArgs g, void* ws, size_t ws_bytes, cudaStream_t stream,
-           const CUtensorMap* mblo = nullptr) {
+           const CUtensorMap* mblo = nullptr, const CUtensorMap* malo = nullptr) {
     int nsplit = pick_split(g.M, g.N, g.KB);
     if (nsplit > 1 && (ws == nullptr || ws_bytes < (size_t)nsplit * g.M * g.N * sizeof(float))) nsplit = 1;
     g.kb_per_split = (g.KB + nsplit - 1) / nsplit;
     nsplit = (g.KB + g.kb_per_split - 1) / g.kb_per_split;       // no empty slices
     g.partial = reinterpret_cast<float*>(ws);
     const size_t smem = (size_t)G_STAGES * G_STAGE_BYTES + 256;
-    auto fn = gemm3x_kernel<A_MN, B_MN, B_PRE>;
+    auto fn = gemm3x_kernel<A_MN, B_MN, B_PRE, A_PRE>;
     B200_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((g.N + G_BN - 1) / G_BN, (g.M + G_BM - 1) / G_BM, nsplit);
-    fn<<<grid, G_THREADS, smem, stream>>>(ma, mb, mblo ? *mblo : mb, g);
+    fn<<<grid, G_THREADS, smem, stream>>>(ma, mb, mblo ? *mblo : mb, malo ? *malo : ma, g);
     B200_LAUNCH_CHECK("gemm3x_kernel");
     if (nsplit > 1) {
         const long long total = (long long)g.M * g.N;
@@ -487,8 +511,9 @@ extern "C" int b200asr_gemm3x_tn(const float* A, const float* B, const float* bi
 
 static int gemm3x_tn_impl(const float* A, int lda, const float* B, const float* bias, float* C, int M, int N, int K,
                           int ldc, int accumulate, void* ws, size_t ws_bytes, b200asr_stream stream,
-                          const float* B_lo = nullptr) {
+                          const float* B_lo = nullptr, const float* A_lo = nullptr) {
     B200_REQUIRE(A && B && C, "gemm3x_tn: null pointer");
+    B200_REQUIRE(!A_lo || B_lo, "gemm3x_tn: a residual of A needs the residual of B as well");
     B200_REQUIRE(lda > 0 && (lda % 4) == 0, "gemm3x_tn: lda %d must be a positive multiple of 4", lda);
     B200_REQUIRE(b200asr_gemm3x_supported(M, N, K), "gemm3x_tn: unsupported sizes M=%d N=%d K=%d (K %% 4 must be 0)", M,
                  N, K);
@@ -507,6 +532,13 @@ static int gemm3x_tn_impl(const float* A, int lda, const float* B, const float* 
         CUtensorMap mlo;
         rc = make_map_k(&mlo, B_lo, N, K, K, G_BN);
         if (rc != B200_OK) return rc;
+        if (A_lo) {
+            B200_REQUIRE(aligned16(A_lo), "gemm3x_tn: operands must be 16-byte aligned");
+            CUtensorMap malo;
+            rc = make_map_k(&malo, A_lo, M, K, lda, G_BM);
+            if (rc != B200_OK) return rc;
+            return launch<false, false, true, true>(ma, mb, g, ws, ws_bytes, (cudaStream_t)stream, &mlo, &malo);
+        }
         return launch<false, false, true>(ma, mb, g, ws, ws_bytes, (cudaStream_t)stream, &mlo);
     }
     return launch<false, false>(ma, mb, g, ws, ws_bytes, (cudaStream_t)stream);
@@ -525,8 +557,9 @@ extern "C" int b200asr_gemm3x_tn_ws(const float* A, int lda, const float* B, con
 
 static int gemm3x_nn_impl(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int M, int N,
                           int K, int ldc, int accumulate, void* ws, size_t ws_bytes, b200asr_stream stream,
-                          const float* B_lo = nullptr) {
+                          const float* B_lo = nullptr, const float* A_lo = nullptr) {
     B200_REQUIRE(A && B && C, "gemm3x_nn: null pointer");
+    B200_REQUIRE(!A_lo || B_lo, "gemm3x_nn: a residual of A needs the residual of B as well");
     B200_REQUIRE(M > 0 && N > 0 && K > 0, "gemm3x_nn: bad sizes M=%d N=%d K=%d", M, N, K);
     B200_REQUIRE(lda >= K && (lda % 4) == 0 && ldb >= N && (ldb % 4) == 0 && ldc >= N,
                  "gemm3x_nn: row pitches must be multiples of 4 floats (lda %d ldb %d ldc %d)", lda, ldb, ldc);
@@ -544,6 +577,13 @@ static int gemm3x_nn_impl(const float* A, int lda, const float* B, int ldb, cons
         CUtensorMap mlo;
         rc = make_map_mn(&mlo, B_lo, N, K, 1, ldb, 0);
         if (rc != B200_OK) return rc;
+        if (A_lo) {
+            B200_REQUIRE(aligned16(A_lo), "gemm3x_nn: operands must be 16-byte aligned");
+            CUtensorMap malo;
+            rc = make_map_k(&malo, A_lo, M, K, lda, G_BM);
+            if (rc != B200_OK) return rc;
+            return launch<false, true, true, true>(ma, mb, g, ws, ws_bytes, (cudaStream_t)stream, &mlo, &malo);
+        }
         return launch<false, true, true>(ma, mb, g, ws, ws_bytes, (cudaStream_t)stream, &mlo);
     }
     return launch<false, true>(ma, mb, g, ws, ws_bytes, (cudaStream_t)stream);
@@ -560,11 +600,12 @@ extern "C" int b200asr_gemm3x_nn_ws(const float* A, int lda, const float* B, int
     return gemm3x_nn_impl(A, lda, B, ldb, bias, C, M, N, K, ldc, accumulate, workspace, workspace_bytes, stream);
 }
 
-extern "C" int b200asr_gemm3x_nt(const float* A, long long lda, long long a_bstride, int a_shift, const float* B,
-                                 long long ldb, long long b_bstride, int b_shift, float* C, int M, int N, int T,
-                                 int batches, int ldc, int accumulate, int permute_rows, void* workspace,
-                                 size_t workspace_bytes, b200asr_stream stream) {
+static int gemm3x_nt_impl(const float* A, const float* A_lo, long long lda, long long a_bstride, int a_shift,
+                          const float* B, const float* B_lo, long long ldb, long long b_bstride, int b_shift, float* C,
+                          int M, int N, int T, int batches, int ldc, int accumulate, int permute_rows, void* workspace,
+                          size_t workspace_bytes, b200asr_stream stream) {
     B200_REQUIRE(A && B && C, "gemm3x_nt: null pointer");
+    B200_REQUIRE((A_lo != nullptr) == (B_lo != nullptr), "gemm3x_nt: residuals are given for both operands or for none");
     B200_REQUIRE(M > 0 && N > 0 && T > 0 && batches > 0, "gemm3x_nt: bad sizes M=%d N=%d T=%d batches=%d", M, N, T,
                  batches);
     // (a pitch smaller than the row length = overlapping rows: the in-place im2col view of a strided convolution)
@@ -583,7 +624,33 @@ extern "C" int b200asr_gemm3x_nt(const float* A, long long lda, long long a_bstr
     g.C = C; g.M = M; g.N = N; g.ldc = ldc; g.accumulate = accumulate; g.perm = permute_rows;
     g.kbt = (T + G_BK - 1) / G_BK; g.KB = g.kbt * batches;
     g.a_shift = a_shift; g.b_shift = b_shift;
+    if (A_lo) {
+        B200_REQUIRE(aligned16(A_lo) && aligned16(B_lo), "gemm3x_nt: operands must be 16-byte aligned");
+        CUtensorMap malo, mblo;
+        rc = make_map_mn(&malo, A_lo, M, T, batches, lda, a_bstride);
+        if (rc != B200_OK) return rc;
+        rc = make_map_mn(&mblo, B_lo, N, T, batches, ldb, b_bstride);
+        if (rc != B200_OK) return rc;
+        return launch<true, true, true, true>(ma, mb, g, workspace, workspace_bytes, (cudaStream_t)stream, &mblo, &malo);
+    }
     return launch<true, true>(ma, mb, g, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int b200asr_gemm3x_nt(const float* A, long long lda, long long a_bstride, int a_shift, const float* B,
+                                 long long ldb, long long b_bstride, int b_shift, float* C, int M, int N, int T,
+                                 int batches, int ldc, int accumulate, int permute_rows, void* workspace,
+                                 size_t workspace_bytes, b200asr_stream stream) {
+    return gemm3x_nt_impl(A, nullptr, lda, a_bstride, a_shift, B, nullptr, ldb, b_bstride, b_shift, C, M, N, T, batches, ldc,
+                          accumulate, permute_rows, workspace, workspace_bytes, stream);
+}
+
+extern "C" int b200asr_gemm3x_nt_pre(const float* A, const float* A_lo, long long lda, long long a_bstride, int a_shift,
+                                     const float* B, const float* B_lo, long long ldb, long long b_bstride, int b_shift,
+                                     float* C, int M, int N, int T, int batches, int ldc, int accumulate,
+                                     int permute_rows, void* workspace, size_t workspace_bytes, b200asr_stream stream) {
+    B200_REQUIRE(A_lo && B_lo, "gemm3x_nt_pre: null residual");
+    return gemm3x_nt_impl(A, A_lo, lda, a_bstride, a_shift, B, B_lo, ldb, b_bstride, b_shift, C, M, N, T, batches, ldc,
+                          accumulate, permute_rows, workspace, workspace_bytes, stream);
 }
 
 extern "C" int b200asr_tf32_residual(const float* x, float* lo, long long n, b200asr_stream stream) {
@@ -607,4 +674,18 @@ extern "C" int b200asr_gemm3x_nn_pre(const float* A, int lda, const float* B, co
                                      size_t workspace_bytes, b200asr_stream stream) {
     B200_REQUIRE(B_lo, "gemm3x_nn_pre: null residual");
     return gemm3x_nn_impl(A, lda, B, ldb, bias, C, M, N, K, ldc, accumulate, workspace, workspace_bytes, stream, B_lo);
+}
+
+extern "C" int b200asr_gemm3x_tn_pre2(const float* A, const float* A_lo, int lda, const float* B, const float* B_lo,
+                                      const float* bias, float* C, int M, int N, int K, int ldc, int accumulate,
+                                      void* workspace, size_t workspace_bytes, b200asr_stream stream) {
+    B200_REQUIRE(A_lo && B_lo, "gemm3x_tn_pre2: null residual");
+    return gemm3x_tn_impl(A, lda, B, bias, C, M, N, K, ldc, accumulate, workspace, workspace_bytes, stream, B_lo, A_lo);
+}
+
+extern "C" int b200asr_gemm3x_nn_pre2(const float* A, const float* A_lo, int lda, const float* B, const float* B_lo, int ldb,
+                                      const float* bias, float* C, int M, int N, int K, int ldc, int accumulate,
+                                      void* workspace, size_t workspace_bytes, b200asr_stream stream) {
+    B200_REQUIRE(A_lo && B_lo, "gemm3x_nn_pre2: null residual");
+    return gemm3x_nn_impl(A, lda, B, ldb, bias, C, M, N, K, ldc, accumulate, workspace, workspace_bytes, stream, B_lo, A_lo);
 }

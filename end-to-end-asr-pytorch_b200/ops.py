@@ -49,6 +49,12 @@ def gate_perm(H, device):
 GEMM_MODE = os.environ.get("B200ASR_GEMM", "umma")
 
 
+# Split activations / gradients once per step too (the GEMM forms without an in-kernel split pass).  OFF: measured slower
+# (cfg B 66.1 -> 68.4 ms/step; tn 248 -> 232, nn 233 -> 208 TFLOP/s): the extra residual tiles arrive through the same
+# L2 -> SM path that already runs at ~2/3 of its measured rate, which costs more than the split pass they replace.
+PRESPLIT_ACTIVATIONS = os.environ.get("B200ASR_GEMM_PRESPLIT", "0") != "0"
+
+
 def tf32_residual(w):
     """w - trunc_tf32(w): the part of a weight matrix the tensor core does not see in the raw fp32 bit pattern.  Computed
     once per step and weight (instead of once per tile by every CTA) for the `_pre` GEMM forms."""
@@ -60,9 +66,10 @@ def tf32_residual(w):
     return lo
 
 
-def gemm_tn(a, w, bias=None, out=None, accumulate=False, w_lo=None):
+def gemm_tn(a, w, bias=None, out=None, accumulate=False, w_lo=None, a_lo=None):
     """out[M,N] (= or +=) a[M,K] @ w[N,K]^T (+ bias[N]) on the tensor cores at fp32-class accuracy (csrc/gemm.cu).
-    w_lo = tf32_residual(w) selects the pre-split form."""
+    w_lo = tf32_residual(w) selects the pre-split form; a_lo = tf32_residual(a) in addition the form without any
+    in-kernel split pass."""
     lib = L.load()
     a, w = _f32c(a), _f32c(w)
     M, K = a.shape
@@ -74,7 +81,13 @@ def gemm_tn(a, w, bias=None, out=None, accumulate=False, w_lo=None):
     b = _f32c(bias) if bias is not None else None
     # algorithmic bytes: both operands and the result once; flops 2*M*N*K (x3 tensor-core products)
     with L.timed("gemm3x_tn", 4 * (M * K + N * K + M * N * (2 if accumulate else 1))):
-        if w_lo is not None:
+        if w_lo is not None and a_lo is not None:
+            ws_bytes = lib.b200asr_gemm3x_workspace_bytes(M, N)
+            ws = torch.empty(max(ws_bytes, 16), device=a.device, dtype=torch.uint8)
+            L.check(lib.b200asr_gemm3x_tn_pre2(L.ptr(a), L.ptr(a_lo), K, L.ptr(w), L.ptr(w_lo), L.ptr(b), L.ptr(out), M, N, K,
+                                               out.stride(0), int(bool(accumulate)), L.ptr(ws), ws_bytes, L.stream()),
+                    "gemm3x_tn_pre2")
+        elif w_lo is not None:
             ws_bytes = lib.b200asr_gemm3x_workspace_bytes(M, N)
             ws = torch.empty(max(ws_bytes, 16), device=a.device, dtype=torch.uint8)
             L.check(lib.b200asr_gemm3x_tn_pre(L.ptr(a), K, L.ptr(w), L.ptr(w_lo), L.ptr(b), L.ptr(out), M, N, K,
@@ -108,7 +121,7 @@ def gemm_tn_ld(a_base, lda, M, K, w, bias=None):
     return out
 
 
-def gemm_nn(a, w, out=None, accumulate=False, w_lo=None):
+def gemm_nn(a, w, out=None, accumulate=False, w_lo=None, a_lo=None):
     """out[M,N] (= or +=) a[M,K] @ w[K,N]: the input gradient dY . W with W read in place (MN-major operand)."""
     lib = L.load()
     a, w = _f32c(a), _f32c(w)
@@ -119,7 +132,13 @@ def gemm_nn(a, w, out=None, accumulate=False, w_lo=None):
         accumulate = False
     assert out.stride(1) == 1 and out.shape == (M, N)
     with L.timed("gemm3x_nn", 4 * (M * K + N * K + M * N * (2 if accumulate else 1))):
-        if w_lo is not None:
+        if w_lo is not None and a_lo is not None:
+            ws_bytes = lib.b200asr_gemm3x_workspace_bytes(M, N)
+            ws = torch.empty(max(ws_bytes, 16), device=a.device, dtype=torch.uint8)
+            L.check(lib.b200asr_gemm3x_nn_pre2(L.ptr(a), L.ptr(a_lo), K, L.ptr(w), L.ptr(w_lo), N, None, L.ptr(out), M, N, K,
+                                               out.stride(0), int(bool(accumulate)), L.ptr(ws), ws_bytes, L.stream()),
+                    "gemm3x_nn_pre2")
+        elif w_lo is not None:
             ws_bytes = lib.b200asr_gemm3x_workspace_bytes(M, N)
             ws = torch.empty(max(ws_bytes, 16), device=a.device, dtype=torch.uint8)
             L.check(lib.b200asr_gemm3x_nn_pre(L.ptr(a), K, L.ptr(w), L.ptr(w_lo), N, None, L.ptr(out), M, N, K,
@@ -136,9 +155,11 @@ def gemm_nn(a, w, out=None, accumulate=False, w_lo=None):
     return out
 
 
-def gemm_nt(a, b, M, N, T, batches=1, lda=None, a_bstride=0, ldb=None, b_bstride=0, b_shift=0, permute_rows=False):
+def gemm_nt(a, b, M, N, T, batches=1, lda=None, a_bstride=0, ldb=None, b_bstride=0, b_shift=0, permute_rows=False,
+            a_lo=None, b_lo=None):
     """out[M,N] = sum over (batch, t) of a[batch, t, :M]^T b[batch, t + b_shift, :N]: the weight gradient dY^T . X.
-    `a` / `b` are tensors whose data pointer is element (0, 0, 0); pitches are in floats (default: dense [T, M] / [T, N])."""
+    `a` / `b` are tensors whose data pointer is element (0, 0, 0); pitches are in floats (default: dense [T, M] / [T, N]).
+    a_lo / b_lo (both or none): tf32_residual of the operands, same layout - the form without an in-kernel split pass."""
     lib = L.load()
     lda = M if lda is None else lda
     ldb = N if ldb is None else ldb
@@ -146,9 +167,14 @@ def gemm_nt(a, b, M, N, T, batches=1, lda=None, a_bstride=0, ldb=None, b_bstride
     ws_bytes = lib.b200asr_gemm3x_workspace_bytes(M, N)
     ws = torch.empty(max(ws_bytes, 16), device=a.device, dtype=torch.uint8)
     with L.timed("gemm3x_nt", 4 * (batches * T * (M + N) + M * N)):
-        L.check(lib.b200asr_gemm3x_nt(L.ptr(a), lda, a_bstride, 0, L.ptr(b), ldb, b_bstride, b_shift, L.ptr(out), M, N,
-                                      T, batches, N, 0, int(bool(permute_rows)), L.ptr(ws), ws_bytes, L.stream()),
-                "gemm3x_nt")
+        if a_lo is not None and b_lo is not None:
+            L.check(lib.b200asr_gemm3x_nt_pre(L.ptr(a), L.ptr(a_lo), lda, a_bstride, 0, L.ptr(b), L.ptr(b_lo), ldb, b_bstride,
+                                              b_shift, L.ptr(out), M, N, T, batches, N, 0, int(bool(permute_rows)),
+                                              L.ptr(ws), ws_bytes, L.stream()), "gemm3x_nt_pre")
+        else:
+            L.check(lib.b200asr_gemm3x_nt(L.ptr(a), lda, a_bstride, 0, L.ptr(b), ldb, b_bstride, b_shift, L.ptr(out), M, N,
+                                          T, batches, N, 0, int(bool(permute_rows)), L.ptr(ws), ws_bytes, L.stream()),
+                    "gemm3x_nt")
     return out
 
 
@@ -307,13 +333,16 @@ class BiLSTMFn(Function):
         xs = None if umma else Op(x.view(B * T, I))
         gates = torch.empty((ndir, B, T, H, 4), device=dev, dtype=torch.float32)
         w_ih_p, w_ih_lo = [], []
+        # the layer input enters the forward projection of both directions and both dW_ih products: split it once
+        x_lo = tf32_residual(x) if (umma and PRESPLIT_ACTIVATIONS) else None
         for d in range(ndir):
             w_ih, w_hh, b_ih, b_hh = params[4 * d:4 * d + 4]
             wp = w_ih.detach().index_select(0, perm)
             bp = (b_ih.detach() + b_hh.detach()).index_select(0, perm)
             if umma:
                 wlo = tf32_residual(wp)            # once per step: shared by the forward product and the input gradient
-                gemm_tn(x.view(B * T, I), wp, bias=bp, out=gates[d].view(B * T, 4 * H), w_lo=wlo)
+                gemm_tn(x.view(B * T, I), wp, bias=bp, out=gates[d].view(B * T, 4 * H), w_lo=wlo,
+                        a_lo=x_lo.view(B * T, I) if x_lo is not None else None)
                 w_ih_lo.append(wlo)
             else:
                 mm(xs, Op(wp).t(), out=gates[d].view(B * T, 4 * H), bias=bp)
@@ -333,7 +362,8 @@ class BiLSTMFn(Function):
         ctx.ndir = ndir
         ctx.dims = (B, T, I, H)
         ctx.consumed = False
-        ctx.save_for_backward(x, gates, cst, out, w_hh, *w_ih_p, *w_ih_lo)
+        ctx.has_x_lo = x_lo is not None
+        ctx.save_for_backward(x, gates, cst, out, w_hh, *w_ih_p, *w_ih_lo, *([x_lo] if x_lo is not None else []))
         return out
 
     @staticmethod
@@ -347,7 +377,9 @@ class BiLSTMFn(Function):
         B, T, I, H = ctx.dims
         x, gates, cst, out, w_hh = ctx.saved_tensors[:5]
         w_ih_p = ctx.saved_tensors[5:5 + ndir]
-        w_ih_lo = ctx.saved_tensors[5 + ndir:]
+        rest = ctx.saved_tensors[5 + ndir:]
+        x_lo = rest[-1] if ctx.has_x_lo else None
+        w_ih_lo = rest[:-1] if ctx.has_x_lo else rest
         dev = x.device
         dout = _f32c(dout)
         ws_bytes = lib.b200asr_bilstm_workspace_bytes(B, T, H, ndir)
@@ -363,14 +395,22 @@ class BiLSTMFn(Function):
             # own tensor-core kernels throughout: dX = dG . W (W in place), dW_ih = dG^T . X, dW_hh = dG^T . h_prev with
             # h_prev read from the layer output shifted by one step (never materialised); rows written through the gate
             # permutation by the epilogue
+            # the gate gradient enters three products per direction (dX, dW_ih, dW_hh), the layer output one (dW_hh) and
+            # the layer input one more (dW_ih): with their residuals made once here, none of these kernels splits a tile
+            pre = x_lo is not None and len(w_ih_lo) == ndir
+            g_lo = tf32_residual(gates) if pre else None
+            out_lo = tf32_residual(out) if pre else None
             for d in range(ndir):
                 g2 = gates[d].view(B * T, 4 * H)
+                gl2 = g_lo[d].view(B * T, 4 * H) if pre else None
                 if need_dx:
-                    gemm_nn(g2, w_ih_p[d], out=dx2, accumulate=(d > 0), w_lo=w_ih_lo[d] if len(w_ih_lo) == ndir else None)
-                dw_ih = gemm_nt(g2, x, 4 * H, I, B * T, permute_rows=True)
+                    gemm_nn(g2, w_ih_p[d], out=dx2, accumulate=(d > 0), w_lo=w_ih_lo[d] if len(w_ih_lo) == ndir else None,
+                            a_lo=gl2)
+                dw_ih = gemm_nt(g2, x, 4 * H, I, B * T, permute_rows=True, a_lo=gl2, b_lo=x_lo)
                 hd = out[:, :, d * H:(d + 1) * H]
                 dw_hh = gemm_nt(g2, hd, 4 * H, H, T, batches=B, a_bstride=T * 4 * H, ldb=ndir * H,
-                                b_bstride=T * ndir * H, b_shift=(-1 if d == 0 else 1), permute_rows=True)
+                                b_bstride=T * ndir * H, b_shift=(-1 if d == 0 else 1), permute_rows=True,
+                                a_lo=gl2, b_lo=out_lo[:, :, d * H:(d + 1) * H] if pre else None)
                 db = torch.empty((4 * H,), device=dev, dtype=torch.float32)
                 db.index_copy_(0, perm, g2.sum(0))
                 grads += [dw_ih, dw_hh, db, db.clone()]

@@ -262,6 +262,22 @@ B200ASR_API int b200asr_gemm3x_tn_pre(const float* A, int lda, const float* B, c
 B200ASR_API int b200asr_gemm3x_nn_pre(const float* A, int lda, const float* B, const float* B_lo, int ldb, const float* bias,
                           float* C, int M, int N, int K, int ldc, int accumulate, void* workspace,
                           size_t workspace_bytes, b200asr_stream stream);
+/* all three forms with BOTH operands pre-split: A_lo = A - trunc_tf32(A) has the shape and pitches of A (an activation
+ * or gradient matrix that enters several products of the step - the layer input x: forward projection and dW_ih; the
+ * gate gradient dG: dX, dW_ih and dW_hh - so one elementwise pass replaces the per-tile split in each of them).  The
+ * kernel then has no splitter pass at all: the 12 products of a K block are issued as soon as the four tiles have
+ * landed.  Same residuals and the same 12 products per K block as the other entry points (the issue order of the
+ * products differs, so results agree to fp32 rounding, not bit for bit).                                            */
+B200ASR_API int b200asr_gemm3x_tn_pre2(const float* A, const float* A_lo, int lda, const float* B, const float* B_lo,
+                           const float* bias, float* C, int M, int N, int K, int ldc, int accumulate, void* workspace,
+                           size_t workspace_bytes, b200asr_stream stream);
+B200ASR_API int b200asr_gemm3x_nn_pre2(const float* A, const float* A_lo, int lda, const float* B, const float* B_lo, int ldb,
+                           const float* bias, float* C, int M, int N, int K, int ldc, int accumulate, void* workspace,
+                           size_t workspace_bytes, b200asr_stream stream);
+B200ASR_API int b200asr_gemm3x_nt_pre(const float* A, const float* A_lo, long long lda, long long a_bstride, int a_shift,
+                          const float* B, const float* B_lo, long long ldb, long long b_bstride, int b_shift, float* C,
+                          int M, int N, int T, int batches, int ldc, int accumulate, int permute_rows, void* workspace,
+                          size_t workspace_bytes, b200asr_stream stream);
 
 /* ---- K6 helper: split fp32 into a TF32-representable high part and the fp32 residual ---------------------------
  * hi = x rounded to TF32, lo = x - hi; used to run the input-projection (src/module.py:131, inside nn.LSTM) and the

@@ -647,6 +647,11 @@ def test_gemm3x_umma_is_fp32_class(pkg, M, N, K, acc):
     pkg.ops.gemm_tn(a, b, bias=bias, out=out, accumulate=acc, w_lo=blo)
     e3 = scaled_err(out.cpu().numpy(), ref.cpu().numpy())
     assert e3 < 3e-6 and e3 < 20 * max(e1, 1e-7), (e3, e1)
+    # both operands pre-split: no in-kernel split pass at all
+    out.copy_(c0)
+    pkg.ops.gemm_tn(a, b, bias=bias, out=out, accumulate=acc, w_lo=blo, a_lo=pkg.ops.tf32_residual(a))
+    e3 = scaled_err(out.cpu().numpy(), ref.cpu().numpy())
+    assert e3 < 3e-6 and e3 < 20 * max(e1, 1e-7), (e3, e1)
     if acc:
         assert torch.equal(buf[:, N:], buf[:, N:])                              # padding columns untouched (no NaN)
 
@@ -733,6 +738,10 @@ def test_gemm3x_nn_is_fp32_class(pkg, M, N, K, acc):
     pkg.ops.gemm_nn(a, b, out=out, accumulate=acc, w_lo=pkg.ops.tf32_residual(b))          # pre-split form
     e3 = scaled_err(out.cpu().numpy(), ref.cpu().numpy())
     assert e3 < 3e-6 and e3 < 20 * max(e1, 1e-7), (e3, e1)
+    out.copy_(c0)
+    pkg.ops.gemm_nn(a, b, out=out, accumulate=acc, w_lo=pkg.ops.tf32_residual(b), a_lo=pkg.ops.tf32_residual(a))
+    e3 = scaled_err(out.cpu().numpy(), ref.cpu().numpy())
+    assert e3 < 3e-6 and e3 < 20 * max(e1, 1e-7), (e3, e1)
 
 
 @pytest.mark.parametrize("M,N,T,batches,shift,perm", [
@@ -772,4 +781,10 @@ def test_gemm3x_nt_is_fp32_class(pkg, M, N, T, batches, shift, perm):
     assert torch.equal(out, out2)                                               # deterministic (split-K in fixed order)
     e3 = scaled_err(out.cpu().numpy(), ref.cpu().numpy())
     e1 = scaled_err(sg.cpu().numpy(), ref.cpu().numpy())
+    assert e3 < 3e-6 and e3 < 20 * max(e1, 1e-7), (e3, e1)
+    # both operands pre-split (the residual of the padded buffer has the operand's pitch)
+    out3 = pkg.ops.gemm_nt(a, bfull, M, N, T, batches=batches, a_bstride=T * M, ldb=ldb, b_bstride=T * ldb,
+                           b_shift=shift, permute_rows=perm, a_lo=pkg.ops.tf32_residual(a),
+                           b_lo=pkg.ops.tf32_residual(bfull))
+    e3 = scaled_err(out3.cpu().numpy(), ref.cpu().numpy())
     assert e3 < 3e-6 and e3 < 20 * max(e1, 1e-7), (e3, e1)

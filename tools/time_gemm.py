@@ -46,6 +46,16 @@ for M, N, K in shapes:
     print("tn  pre-split W                              own %7.3f ms (%6.1f TF)" % (tp, fl / tp), flush=True)
     tp = timeit(lambda: ops.gemm_nn(dy, w, w_lo=wlo))
     print("nn  pre-split W                              own %7.3f ms (%6.1f TF)" % (tp, fl / tp), flush=True)
+    xlo, dylo = ops.tf32_residual(x), ops.tf32_residual(dy)
+    tp = timeit(lambda: ops.gemm_tn(x, w, w_lo=wlo, a_lo=xlo))
+    print("tn  both operands pre-split                  own %7.3f ms (%6.1f TF)" % (tp, fl / tp), flush=True)
+    tp = timeit(lambda: ops.gemm_nn(dy, w, w_lo=wlo, a_lo=dylo))
+    print("nn  both operands pre-split                  own %7.3f ms (%6.1f TF)" % (tp, fl / tp), flush=True)
+    tp = timeit(lambda: ops.gemm_nt(dy, x, N, K, M, a_lo=dylo, b_lo=xlo))
+    print("nt  both operands pre-split                  own %7.3f ms (%6.1f TF)" % (tp, fl / tp), flush=True)
+    tp = timeit(lambda: ops.tf32_residual(dy))
+    print("    residual pass over dy [%d x %d]          %7.3f ms" % (M, N, tp), flush=True)
+    del xlo, dylo
     t2 = timeit(lambda: lib3(x, w.t()))
     t3 = timeit(lambda: tf32(x, w.t()))
     print("tn  y=x.W^T   M=%6d N=%5d K=%5d  own %7.3f ms (%6.1f TF)  cublas3x %7.3f ms  cublas-tf32x1 %7.3f ms" % (M, N, K, t, fl / t, t2, t3), flush=True)
