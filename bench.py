@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time the eager step instead of the CUDA-graph replay")
+    ap.add_argument("--graph-dp", action="store_true",
+                    help="N > 1: capture the data-parallel step (NCCL all-reduces included) into the CUDA graph as well")
     ap.add_argument("--no-micro", action="store_true", help="skip the fbank/CTC micro-benchmark (BASELINE configs[4])")
     ap.add_argument("--no-also", action="store_true", help="multi-GPU runs: skip the extra cfgD (BASELINE configs[3]) timing")
     ap.add_argument("--no-parity", action="store_true", help="skip the same-run parity check against the CPU path")
@@ -500,8 +502,15 @@ def main():
     use_graph = False
     # multi-GPU runs stay eager: the captured graph would contain the NCCL all-reduce, whose teardown at process exit
     # was seen to hang (the eager data-parallel path is the validated one; the graph is worth ~1 % on cfg B)
-    if not args.no_graph and world == 1:
+    if not args.no_graph and (world == 1 or args.graph_dp):
         use_graph = step_fn.capture(wave_dev, lens_dev, txt_dev, global_batch=gbatch, global_tokens=ntok)
+        if world > 1:      # every rank replays the graph or none does (the collectives inside must pair up)
+            ok = torch.tensor([1.0 if use_graph else 0.0], device=dev)
+            torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN)
+            if use_graph and float(ok) == 0.0:
+                step_fn.release_graph()
+                use_graph = False
+                step_fn.graph_error = "capture failed on another rank"
         log("CUDA graph capture: %s" % ("ok" if use_graph else "not used (%s)" % step_fn.graph_error))
     if use_graph:
         for _ in range(3):
@@ -548,6 +557,8 @@ def main():
                          "loss": loss_d}}
         del st
         torch.cuda.empty_cache()
+    if world > 1:
+        step_fn.release_graph()          # the graph holds this communicator's NCCL kernels: drop it first
     dp.close()
     if rank != 0:
         return 0

@@ -366,15 +366,22 @@ __global__ void gemm3x_reduce_kernel(const float* __restrict__ partial, int nspl
     }
 }
 
-// lo = x - trunc_tf32(x): the residual the tensor core does not see when it reads the raw fp32 bit pattern
-__global__ void tf32_residual_kernel(const float* __restrict__ x, float* __restrict__ lo, long long n) {
-    const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (i4 + 3 < n && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(lo)) & 15) == 0) {
-        const float4 v = *reinterpret_cast<const float4*>(x + i4);
-        *reinterpret_cast<float4*>(lo + i4) =
-            make_float4(tf32_residual(v.x), tf32_residual(v.y), tf32_residual(v.z), tf32_residual(v.w));
+// lo = x - trunc_tf32(x): the residual the tensor core does not see when it reads the raw fp32 bit pattern.
+// Four 128-bit loads in flight per thread (one per thread ran at ~2/3 of the HBM rate).
+constexpr int RES_UNROLL = 4;
+__global__ void __launch_bounds__(256) tf32_residual_kernel(const float* __restrict__ x, float* __restrict__ lo, long long n) {
+    const long long base = (long long)blockIdx.x * (256 * RES_UNROLL * 4) + threadIdx.x * 4;
+    if (base + (RES_UNROLL - 1) * 1024 + 3 < n && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(lo)) & 15) == 0) {
+        float4 v[RES_UNROLL];
+#pragma unroll
+        for (int k = 0; k < RES_UNROLL; ++k) v[k] = __ldcs(reinterpret_cast<const float4*>(x + base + k * 1024));
+#pragma unroll
+        for (int k = 0; k < RES_UNROLL; ++k)
+            *reinterpret_cast<float4*>(lo + base + k * 1024) =
+                make_float4(tf32_residual(v[k].x), tf32_residual(v[k].y), tf32_residual(v[k].z), tf32_residual(v[k].w));
     } else {
-        for (long long i = i4; i < n && i < i4 + 4; ++i) lo[i] = tf32_residual(x[i]);
+        for (int k = 0; k < RES_UNROLL; ++k)
+            for (long long i = base + k * 1024; i < n && i < base + k * 1024 + 4; ++i) lo[i] = tf32_residual(x[i]);
     }
 }
 
@@ -605,7 +612,7 @@ static int gemm3x_nt_impl(const float* A, const float* A_lo, long long lda, long
                           int M, int N, int T, int batches, int ldc, int accumulate, int permute_rows, void* workspace,
                           size_t workspace_bytes, b200asr_stream stream) {
     B200_REQUIRE(A && B && C, "gemm3x_nt: null pointer");
-    B200_REQUIRE((A_lo != nullptr) == (B_lo != nullptr), "gemm3x_nt: residuals are given for both operands or for none");
+    B200_REQUIRE(!A_lo || B_lo, "gemm3x_nt: a residual of A needs the residual of B as well");
     B200_REQUIRE(M > 0 && N > 0 && T > 0 && batches > 0, "gemm3x_nt: bad sizes M=%d N=%d T=%d batches=%d", M, N, T,
                  batches);
     // (a pitch smaller than the row length = overlapping rows: the in-place im2col view of a strided convolution)
@@ -624,12 +631,14 @@ static int gemm3x_nt_impl(const float* A, const float* A_lo, long long lda, long
     g.C = C; g.M = M; g.N = N; g.ldc = ldc; g.accumulate = accumulate; g.perm = permute_rows;
     g.kbt = (T + G_BK - 1) / G_BK; g.KB = g.kbt * batches;
     g.a_shift = a_shift; g.b_shift = b_shift;
-    if (A_lo) {
-        B200_REQUIRE(aligned16(A_lo) && aligned16(B_lo), "gemm3x_nt: operands must be 16-byte aligned");
+    if (B_lo) {
+        B200_REQUIRE(aligned16(B_lo) && (!A_lo || aligned16(A_lo)), "gemm3x_nt: operands must be 16-byte aligned");
         CUtensorMap malo, mblo;
-        rc = make_map_mn(&malo, A_lo, M, T, batches, lda, a_bstride);
-        if (rc != B200_OK) return rc;
         rc = make_map_mn(&mblo, B_lo, N, T, batches, ldb, b_bstride);
+        if (rc != B200_OK) return rc;
+        if (!A_lo)       // only the wide (256-column) operand pre-split: the splitters pass over the A tile alone
+            return launch<true, true, true, false>(ma, mb, g, workspace, workspace_bytes, (cudaStream_t)stream, &mblo);
+        rc = make_map_mn(&malo, A_lo, M, T, batches, lda, a_bstride);
         if (rc != B200_OK) return rc;
         return launch<true, true, true, true>(ma, mb, g, workspace, workspace_bytes, (cudaStream_t)stream, &mblo, &malo);
     }
@@ -648,7 +657,7 @@ extern "C" int b200asr_gemm3x_nt_pre(const float* A, const float* A_lo, long lon
                                      const float* B, const float* B_lo, long long ldb, long long b_bstride, int b_shift,
                                      float* C, int M, int N, int T, int batches, int ldc, int accumulate,
                                      int permute_rows, void* workspace, size_t workspace_bytes, b200asr_stream stream) {
-    B200_REQUIRE(A_lo && B_lo, "gemm3x_nt_pre: null residual");
+    B200_REQUIRE(B_lo, "gemm3x_nt_pre: null residual of B (A_lo may be NULL: only B pre-split)");
     return gemm3x_nt_impl(A, A_lo, lda, a_bstride, a_shift, B, B_lo, ldb, b_bstride, b_shift, C, M, N, T, batches, ldc,
                           accumulate, permute_rows, workspace, workspace_bytes, stream);
 }
@@ -656,8 +665,8 @@ extern "C" int b200asr_gemm3x_nt_pre(const float* A, const float* A_lo, long lon
 extern "C" int b200asr_tf32_residual(const float* x, float* lo, long long n, b200asr_stream stream) {
     B200_REQUIRE(x && lo && n >= 0, "tf32_residual: bad arguments");
     if (n == 0) return B200_OK;
-    const long long threads = (n + 3) / 4;
-    tf32_residual_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, lo, n);
+    const long long per_block = 256LL * RES_UNROLL * 4;
+    tf32_residual_kernel<<<(unsigned)((n + per_block - 1) / per_block), 256, 0, (cudaStream_t)stream>>>(x, lo, n);
     B200_LAUNCH_CHECK("tf32_residual_kernel");
     return B200_OK;
 }

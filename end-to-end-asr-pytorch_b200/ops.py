@@ -49,10 +49,17 @@ def gate_perm(H, device):
 GEMM_MODE = os.environ.get("B200ASR_GEMM", "umma")
 
 
-# Split activations / gradients once per step too (the GEMM forms without an in-kernel split pass).  OFF: measured slower
-# (cfg B 66.1 -> 68.4 ms/step; tn 248 -> 232, nn 233 -> 208 TFLOP/s): the extra residual tiles arrive through the same
-# L2 -> SM path that already runs at ~2/3 of its measured rate, which costs more than the split pass they replace.
-PRESPLIT_ACTIVATIONS = os.environ.get("B200ASR_GEMM_PRESPLIT", "0") != "0"
+# Pre-split activations too (B200ASR_GEMM_PRESPLIT):
+#   "x" (default)  only the wide operand of the weight-gradient products (the layer input x for dW_ih, the layer output
+#                  for dW_hh: small next to dG): nt 188 -> 204 TFLOP/s, cfg B weight gradients 13.5 -> 12.8 ms for 0.5 ms of
+#                  residual passes
+#   "1"            every activation / gradient operand (no in-kernel split pass at all): measured SLOWER (cfg B 66.1 ->
+#                  68.4 ms/step; tn 248 -> 232, nn 233 -> 208 TFLOP/s) - the extra residual tiles arrive through the same
+#                  L2 -> SM path that already runs at ~2/3 of its measured rate
+#   "0"            weights only
+_PRESPLIT = os.environ.get("B200ASR_GEMM_PRESPLIT", "x")
+PRESPLIT_ACTIVATIONS = _PRESPLIT == "1"
+PRESPLIT_NT_B = _PRESPLIT == "x"
 
 
 def tf32_residual(w):
@@ -159,7 +166,7 @@ def gemm_nt(a, b, M, N, T, batches=1, lda=None, a_bstride=0, ldb=None, b_bstride
             a_lo=None, b_lo=None):
     """out[M,N] = sum over (batch, t) of a[batch, t, :M]^T b[batch, t + b_shift, :N]: the weight gradient dY^T . X.
     `a` / `b` are tensors whose data pointer is element (0, 0, 0); pitches are in floats (default: dense [T, M] / [T, N]).
-    a_lo / b_lo (both or none): tf32_residual of the operands, same layout - the form without an in-kernel split pass."""
+    b_lo (+ optionally a_lo): tf32_residual of the operands, same layout - their tiles are not split in the kernel."""
     lib = L.load()
     lda = M if lda is None else lda
     ldb = N if ldb is None else ldb
@@ -167,7 +174,7 @@ def gemm_nt(a, b, M, N, T, batches=1, lda=None, a_bstride=0, ldb=None, b_bstride
     ws_bytes = lib.b200asr_gemm3x_workspace_bytes(M, N)
     ws = torch.empty(max(ws_bytes, 16), device=a.device, dtype=torch.uint8)
     with L.timed("gemm3x_nt", 4 * (batches * T * (M + N) + M * N)):
-        if a_lo is not None and b_lo is not None:
+        if b_lo is not None:
             L.check(lib.b200asr_gemm3x_nt_pre(L.ptr(a), L.ptr(a_lo), lda, a_bstride, 0, L.ptr(b), L.ptr(b_lo), ldb, b_bstride,
                                               b_shift, L.ptr(out), M, N, T, batches, N, 0, int(bool(permute_rows)),
                                               L.ptr(ws), ws_bytes, L.stream()), "gemm3x_nt_pre")
@@ -399,7 +406,10 @@ class BiLSTMFn(Function):
             # the layer input one more (dW_ih): with their residuals made once here, none of these kernels splits a tile
             pre = x_lo is not None and len(w_ih_lo) == ndir
             g_lo = tf32_residual(gates) if pre else None
-            out_lo = tf32_residual(out) if pre else None
+            pre_b = pre or PRESPLIT_NT_B
+            if PRESPLIT_NT_B:
+                x_lo = tf32_residual(x)
+            out_lo = tf32_residual(out) if pre_b else None
             for d in range(ndir):
                 g2 = gates[d].view(B * T, 4 * H)
                 gl2 = g_lo[d].view(B * T, 4 * H) if pre else None
@@ -410,7 +420,7 @@ class BiLSTMFn(Function):
                 hd = out[:, :, d * H:(d + 1) * H]
                 dw_hh = gemm_nt(g2, hd, 4 * H, H, T, batches=B, a_bstride=T * 4 * H, ldb=ndir * H,
                                 b_bstride=T * ndir * H, b_shift=(-1 if d == 0 else 1), permute_rows=True,
-                                a_lo=gl2, b_lo=out_lo[:, :, d * H:(d + 1) * H] if pre else None)
+                                a_lo=gl2, b_lo=out_lo[:, :, d * H:(d + 1) * H] if pre_b else None)
                 db = torch.empty((4 * H,), device=dev, dtype=torch.float32)
                 db.index_copy_(0, perm, g2.sum(0))
                 grads += [dw_ih, dw_hh, db, db.clone()]

@@ -86,6 +86,15 @@ class TrainStep:
                      "ctc_output": det(ctc_output), "att_output": det(att_output), "encode_len": encode_len}
         return total.detach()
 
+    def release_graph(self):
+        """Drop the captured step.  Under data parallelism call this BEFORE the process group is destroyed: the graph
+        holds NCCL kernels of that communicator."""
+        if self.graph is not None:
+            torch.cuda.synchronize()
+            self.graph.reset()
+            self.graph = None
+            self._g_loss = None
+
     def capture(self, wave, wave_len, txt, global_batch=None, global_tokens=None, warmup=3):
         """Capture the WHOLE train step (front end, forward, losses, backward, all-reduce, clip + update) into one
         CUDA graph for fixed shapes: ~130 (cfg B) to ~2000 (cfg C: the decode loop) launches become one replay, which
@@ -111,7 +120,10 @@ class TrainStep:
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            # data parallel: the bucketed NCCL all-reduces are captured with the step (forks / joins of the capture
+            # stream).  NCCL's own threads may call the CUDA API meanwhile, so only THIS thread's calls are policed.
+            mode = "thread_local" if self.dp.enabled else "global"
+            with torch.cuda.graph(graph, capture_error_mode=mode):
                 self._g_loss = self._eager(self._g_wave, self._g_len, self._g_txt, global_batch, global_tokens, max_len)
             self.graph = graph
             return True

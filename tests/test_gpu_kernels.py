@@ -656,6 +656,17 @@ def test_gemm3x_umma_is_fp32_class(pkg, M, N, K, acc):
         assert torch.equal(buf[:, N:], buf[:, N:])                              # padding columns untouched (no NaN)
 
 
+@pytest.mark.parametrize("n", [1, 5, 4096, 4099, 3 * 4096 + 1027, 1 << 20])
+def test_tf32_residual_pass(pkg, n):
+    """lo = x - trunc_tf32(x) elementwise (unrolled 128-bit body + scalar tail; unaligned views take the scalar path)."""
+    torch.manual_seed(n)
+    x = torch.randn(n + 1, device=DEV)
+    for v in (x[:n], x[1:]):
+        lo = pkg.ops.tf32_residual(v)
+        assert torch.equal((v.contiguous().view(torch.int32) & -8192).view(torch.float32) + lo, v)
+        assert float(lo.abs().max()) <= float(v.abs().max()) * 2.0 ** -10
+
+
 @pytest.mark.parametrize("B,T,C,O", [(3, 41, 120, 640), (2, 10, 640, 640)])
 def test_conv1d_k4s2_through_the_gemm_kernel(pkg, B, T, C, O):
     """CNNExtractor's Conv1d(k=4, s=2, p=1) as one tcgen05 GEMM over the in-place im2col view (overlapping rows,
@@ -787,4 +798,8 @@ def test_gemm3x_nt_is_fp32_class(pkg, M, N, T, batches, shift, perm):
                            b_shift=shift, permute_rows=perm, a_lo=pkg.ops.tf32_residual(a),
                            b_lo=pkg.ops.tf32_residual(bfull))
     e3 = scaled_err(out3.cpu().numpy(), ref.cpu().numpy())
+    assert e3 < 3e-6 and e3 < 20 * max(e1, 1e-7), (e3, e1)
+    out4 = pkg.ops.gemm_nt(a, bfull, M, N, T, batches=batches, a_bstride=T * M, ldb=ldb, b_bstride=T * ldb,
+                           b_shift=shift, permute_rows=perm, b_lo=pkg.ops.tf32_residual(bfull))      # B only
+    e3 = scaled_err(out4.cpu().numpy(), ref.cpu().numpy())
     assert e3 < 3e-6 and e3 < 20 * max(e1, 1e-7), (e3, e1)

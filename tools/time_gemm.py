@@ -53,6 +53,8 @@ for M, N, K in shapes:
     print("nn  both operands pre-split                  own %7.3f ms (%6.1f TF)" % (tp, fl / tp), flush=True)
     tp = timeit(lambda: ops.gemm_nt(dy, x, N, K, M, a_lo=dylo, b_lo=xlo))
     print("nt  both operands pre-split                  own %7.3f ms (%6.1f TF)" % (tp, fl / tp), flush=True)
+    tp = timeit(lambda: ops.gemm_nt(dy, x, N, K, M, b_lo=xlo))
+    print("nt  B (= x) pre-split only                   own %7.3f ms (%6.1f TF)" % (tp, fl / tp), flush=True)
     tp = timeit(lambda: ops.tf32_residual(dy))
     print("    residual pass over dy [%d x %d]          %7.3f ms" % (M, N, tp), flush=True)
     del xlo, dylo
