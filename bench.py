@@ -49,6 +49,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time the eager step instead of the CUDA-graph replay")
+    ap.add_argument("--no-parity-fp64", action="store_true",
+                    help="parity block of the benchmarked workload: skip the extra fp64 CPU pass (both fp32 sides - the "
+                         "reference's CPU path and these kernels - against the exact gradient)")
     ap.add_argument("--graph-dp", action="store_true",
                     help="N > 1: capture the data-parallel step (NCCL all-reduces included) into the CUDA graph as well")
     ap.add_argument("--no-micro", action="store_true", help="skip the fbank/CTC micro-benchmark (BASELINE configs[4])")
@@ -188,7 +191,7 @@ def cpu_arm(cfg, vocab, n_samples, batch, steps, warmup):
             "cores": torch.get_num_threads(), "loss": loss}
 
 
-def parity_check(pkg, step_fn, cfg, waves, lens, txt, dev, n_ref=8):
+def parity_check(pkg, step_fn, cfg, waves, lens, txt, dev, n_ref=8, fp64=False):
     """Same-run, full-size parity (BASELINE metric, second half): the product path on the FULL per-GPU batch - front
     end, encoder, CTC head / decoder, both losses, backward, all through the CUDA kernels at the benchmark's shapes -
     against the reference's CPU path (oracle/ref_port.py: kaldi.fbank per utterance, ATen LSTM / CTC / CE) on the
@@ -306,6 +309,34 @@ def parity_check(pkg, step_fn, cfg, waves, lens, txt, dev, n_ref=8):
             worst, worst_key = e, k
     out.update(grad_norm_rel_err=abs(sq_g ** 0.5 - sq_r ** 0.5) / sq_r ** 0.5, grad_norm_ref=sq_r ** 0.5,
                grad_max_scaled_err=worst, grad_worst_tensor=worst_key)
+    if fp64:
+        # The same CPU path once more in fp64: how far is EACH fp32 implementation (the reference's ATen path and these
+        # kernels) from the exact gradient?  The step back-propagates through thousands of recurrent steps; the fp32
+        # reference itself only holds ~4e-5 here, which is the floor of any fp32-vs-fp32 gradient comparison.
+        P64 = {k: (v.double() if v.is_floating_point() else v).clone().requires_grad_(v.is_floating_point())
+               for k, v in P.items()}
+        r64 = ref_port.forward_losses(P64, cfg["model"], f_ref.double(), l_ref, t_ref)
+        r64["total_loss"].backward()
+        sq = {"x": 0.0, "ref": 0.0, "own": 0.0}
+        w = {"ref": (0.0, None), "own": (0.0, None)}
+        g64 = {k: v.grad for k, v in P64.items() if v.requires_grad and v.grad is not None and k in g_grads
+               and Pr[k].grad is not None}
+        gmax64 = max(float(v.abs().max()) for v in g64.values())
+        for k, x in g64.items():
+            sq["x"] += float((x ** 2).sum())
+            for name, t in (("ref", Pr[k].grad.double()), ("own", g_grads[k].double())):
+                sq[name] += float((t ** 2).sum())
+                e = float((t - x).abs().max()) / max(float(x.abs().max()), 1e-6 * gmax64)
+                if e > w[name][0]:
+                    w[name] = (e, k)
+        nx = sq["x"] ** 0.5
+        out["vs_fp64"] = {
+            "reference_fp32": {"grad_norm_rel_err": abs(sq["ref"] ** 0.5 - nx) / nx, "grad_max_scaled_err": w["ref"][0],
+                               "grad_worst_tensor": w["ref"][1],
+                               "loss_rel_err": abs(float(res["total_loss"]) - float(r64["total_loss"])) / abs(float(r64["total_loss"]))},
+            "these_kernels": {"grad_norm_rel_err": abs(sq["own"] ** 0.5 - nx) / nx, "grad_max_scaled_err": w["own"][0],
+                              "grad_worst_tensor": w["own"][1],
+                              "loss_rel_err": abs(float(total) - float(r64["total_loss"])) / abs(float(r64["total_loss"]))}}
     opt.buf.grad.zero_()
     return out
 
@@ -406,7 +437,7 @@ def main():
               "parallelism": "dp%d (utterance shards; per-layer NCCL grad all-reduce buckets overlapped with backward)" % world,
               "l2": "inputs+activations per step (>1 GB) exceed the 126 MB L2; no explicit flush",
               "gemm": "own tcgen05 3xTF32 kernel in three operand forms (x.W^T, dY.W, dY^T.X incl. shifted h_prev reads, split-K, "
-                      "gate permutation in the epilogue), weight residuals pre-split once per step, two-level accumulation (TMEM "
+                      "gate permutation in the epilogue), weight residuals (and the wide operand of the weight gradients) pre-split once per step, two-level accumulation (TMEM "
                       "chunks of 128 k summed in fp32 registers); B200ASR_GEMM=tf32x3 selects the cuBLAS 3xTF32 composition; fp32-accurate",
               "lstm": "tcgen05 fp16 hi/lo 2x2-block split product, forward and backward (H = 256 ... 768; backward exchange: data-is-the-flag polling)"}
 
@@ -575,7 +606,7 @@ def main():
         for w in names:
             log("parity check %s (full batch through the kernels vs the CPU path on 8 utterances)" % w)
             if w == args.workload:
-                parity[w] = parity_check(pkg, step_fn, cfg, waves, lens, txt, dev)
+                parity[w] = parity_check(pkg, step_fn, cfg, waves, lens, txt, dev, fp64=not args.no_parity_fp64)
             else:
                 cfg_w = pkg.synthetic.load_config(w)
                 vocab_w = cfg_w["data"]["corpus"]["vocab_size"]

@@ -37,6 +37,7 @@
 // a 32-byte base (TMA SWIZZLE_128B_ATOM_32B <-> descriptor layout SWIZZLE_128B_BASE32B), LBO = 4096 B (next 32
 // columns), SBO = 512 B (next 4 k); one MMA (8 k) advances the start by 1024 bytes.
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "umma.cuh"
 #include "../../include/b200asr.h"
@@ -57,7 +58,7 @@ constexpr int G_MAX_SPLIT = 32;
 #define B200ASR_GEMM_HH_FIRST 1     // measured +1.7 % (228 vs 224.5 TFLOP/s at M = 38k, N = K = 2048)
 #endif
 constexpr bool HH_FIRST = B200ASR_GEMM_HH_FIRST != 0;   // issue the hi.hi products before the residual tiles are ready
-constexpr int G_CH = 4;                      // K blocks per TMEM accumulation chunk (see the drain warps)
+constexpr int G_CH_DEFAULT = 4;              // K blocks per TMEM accumulation chunk (see the drain warps); 1, 2 or 4
 
 struct GemmArgs {
     const float* bias;
@@ -68,6 +69,7 @@ struct GemmArgs {
     int kb_per_split;
     int kbt;               // K blocks per batch entry (MN-major operands walk (batch, time)); KB = batches * kbt
     int a_shift, b_shift;  // time shift of the rows read from A / B (nt form)
+    int ch;                // K blocks per TMEM accumulation chunk
 };
 
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
@@ -133,6 +135,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     const int kb0 = blockIdx.z * g.kb_per_split;
     const int kb1 = min(g.KB, kb0 + g.kb_per_split);
     const int nkb = kb1 - kb0;                                   // >= 1 by construction of the grid
+    const int G_CH = g.ch;
     const int nchunks = (nkb + G_CH - 1) / G_CH;
     const int nvalid = min(G_BN, N - n0);
     const int n_instr = (nvalid + 15) & ~15;                     // MMA N (multiple of 16, <= 256)
@@ -304,7 +307,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                 if (lane == 0) g_arrive(&split[s]);
             }
             // chunk i/G_CH - 1 retired at the latest when K block i-2 left the 2-stage ring: drain it now
-            if (i >= G_CH && (i % G_CH) == 1) drain(next_drain++);
+            if (i > G_CH && ((i - 1) % G_CH) == 0) drain(next_drain++);
         }
         while (next_drain < nchunks) drain(next_drain++);
         // ---------------------------------------------------------------- epilogue: registers -> C
@@ -466,6 +469,18 @@ int pick_split(int M, int N, int KB) {
     return s;
 }
 
+// K blocks per accumulation chunk: B200ASR_GEMM_CHUNK = 1 | 2 | 4 (read once).  The tensor core truncates on every
+// accumulate (bias towards zero, growing with the chain length): shorter chunks = less bias, more drains.
+int gemm_chunk() {
+    static int ch = 0;
+    if (!ch) {
+        const char* e = getenv("B200ASR_GEMM_CHUNK");
+        const int v = e ? atoi(e) : G_CH_DEFAULT;
+        ch = (v == 1 || v == 2 || v == 4) ? v : G_CH_DEFAULT;
+    }
+    return ch;
+}
+
 template <bool A_MN, bool B_MN, bool B_PRE = false, bool A_PRE = false>
 int launch(const CUtensorMap& ma, const CUtensorMap& mb, GemmArgs g, void* ws, size_t ws_bytes, cudaStream_t stream,
            const CUtensorMap* mblo = nullptr, const CUtensorMap* malo = nullptr) {
@@ -474,6 +489,7 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, GemmArgs g, void* ws, s
     g.kb_per_split = (g.KB + nsplit - 1) / nsplit;
     nsplit = (g.KB + g.kb_per_split - 1) / g.kb_per_split;       // no empty slices
     g.partial = reinterpret_cast<float*>(ws);
+    g.ch = gemm_chunk();
     const size_t smem = (size_t)G_STAGES * G_STAGE_BYTES + 256;
     auto fn = gemm3x_kernel<A_MN, B_MN, B_PRE, A_PRE>;
     B200_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
