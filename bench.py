@@ -52,6 +52,8 @@ def parse_args():
     ap.add_argument("--no-parity-fp64", action="store_true",
                     help="parity block of the benchmarked workload: skip the extra fp64 CPU pass (both fp32 sides - the "
                          "reference's CPU path and these kernels - against the exact gradient)")
+    ap.add_argument("--parity-diagnose", action="store_true",
+                    help="parity block: also compare d(loss)/d(layer outputs, CTC logits) of both fp32 sides with fp64")
     ap.add_argument("--graph-dp", action="store_true",
                     help="N > 1: capture the data-parallel step (NCCL all-reduces included) into the CUDA graph as well")
     ap.add_argument("--no-micro", action="store_true", help="skip the fbank/CTC micro-benchmark (BASELINE configs[4])")
@@ -191,7 +193,7 @@ def cpu_arm(cfg, vocab, n_samples, batch, steps, warmup):
             "cores": torch.get_num_threads(), "loss": loss}
 
 
-def parity_check(pkg, step_fn, cfg, waves, lens, txt, dev, n_ref=8, fp64=False):
+def parity_check(pkg, step_fn, cfg, waves, lens, txt, dev, n_ref=8, fp64=False, diagnose=False):
     """Same-run, full-size parity (BASELINE metric, second half): the product path on the FULL per-GPU batch - front
     end, encoder, CTC head / decoder, both losses, backward, all through the CUDA kernels at the benchmark's shapes -
     against the reference's CPU path (oracle/ref_port.py: kaldi.fbank per utterance, ATen LSTM / CTC / CE) on the
@@ -212,7 +214,21 @@ def parity_check(pkg, step_fn, cfg, waves, lens, txt, dev, n_ref=8, fp64=False):
     wave_dev, txt_dev = waves.to(dev), txt.to(dev)
     feat, feat_len = step_fn.front_end(wave_dev, lens.to(dev))
     txt_len = (txt_dev != 0).sum(-1)
+    taps, hooks = {}, []
+    if diagnose:        # gradient of the loss with respect to every encoder layer's output (and the CTC logits below)
+        def tap(i):
+            def hook(mod, inp, outp):
+                if isinstance(outp[0], torch.Tensor) and outp[0].requires_grad:
+                    outp[0].retain_grad()
+                    taps["layer%d_out" % i] = outp[0]
+            return hook
+        hooks = [layer.register_forward_hook(tap(i)) for i, layer in enumerate(model.encoder.layers)]
     ctc_out, enc_len, att_out, _, _ = model(feat, feat_len, int(txt.shape[1]), tf_rate=1.0, teacher=txt_dev)
+    for h in hooks:
+        h.remove()
+    if diagnose and isinstance(ctc_out, pkg.ops.CTCHeadOutput):
+        ctc_out.logits.retain_grad()
+        taps["ctc_logits"] = ctc_out.logits
     total = 0
     g = {}
     if ctc_out is not None:
@@ -251,7 +267,11 @@ def parity_check(pkg, step_fn, cfg, waves, lens, txt, dev, n_ref=8, fp64=False):
     assert order == list(range(n)), "synthetic batch must already be sorted by length"
     if f_ref.shape[1] < feat.shape[1]:                 # the encoder computes through padding: share the global T_max
         f_ref = torch.nn.functional.pad(f_ref, (0, 0, 0, feat.shape[1] - f_ref.shape[1]))
-    res = ref_port.forward_losses(Pr, cfg["model"], f_ref, l_ref, t_ref)
+    col32 = [] if diagnose else None
+    res = ref_port.forward_losses(Pr, cfg["model"], f_ref, l_ref, t_ref, collect=col32)
+    if diagnose:
+        for t in col32 + [res["ctc_output"]]:
+            t.retain_grad()
     res["total_loss"].backward()
 
     def rel(a, b, floor):
@@ -315,7 +335,11 @@ def parity_check(pkg, step_fn, cfg, waves, lens, txt, dev, n_ref=8, fp64=False):
         # reference itself only holds ~4e-5 here, which is the floor of any fp32-vs-fp32 gradient comparison.
         P64 = {k: (v.double() if v.is_floating_point() else v).clone().requires_grad_(v.is_floating_point())
                for k, v in P.items()}
-        r64 = ref_port.forward_losses(P64, cfg["model"], f_ref.double(), l_ref, t_ref)
+        col64 = [] if diagnose else None
+        r64 = ref_port.forward_losses(P64, cfg["model"], f_ref.double(), l_ref, t_ref, collect=col64)
+        if diagnose:
+            for t in col64 + [r64["ctc_output"]]:
+                t.retain_grad()
         r64["total_loss"].backward()
         sq = {"x": 0.0, "ref": 0.0, "own": 0.0}
         w = {"ref": (0.0, None), "own": (0.0, None)}
@@ -337,6 +361,28 @@ def parity_check(pkg, step_fn, cfg, waves, lens, txt, dev, n_ref=8, fp64=False):
             "these_kernels": {"grad_norm_rel_err": abs(sq["own"] ** 0.5 - nx) / nx, "grad_max_scaled_err": w["own"][0],
                               "grad_worst_tensor": w["own"][1],
                               "loss_rel_err": abs(float(total) - float(r64["total_loss"])) / abs(float(r64["total_loss"]))}}
+    if fp64 and diagnose:
+        # where does the gradient noise enter?  d(loss)/d(boundary) of both fp32 sides against fp64, top of the network
+        # first (the CTC head's log-prob gradient equals the logit gradient: SURVEY F9), max error / max |exact|
+        rows = {}
+        names = ["ctc_logits"] + ["layer%d_out" % i for i in reversed(range(len(col64)))]
+        exact = [r64["ctc_output"].grad] + [t.grad for t in reversed(col64)]
+        ref32 = [res["ctc_output"].grad] + [t.grad for t in reversed(col32)]
+        for name, x, r in zip(names, exact, ref32):
+            if name not in taps or taps[name].grad is None:
+                continue
+            o = taps[name].grad[:n].detach().cpu().double()
+            if o.shape != x.shape:       # this package's encoder tensors keep the pre-subsampling time axis / full T_max
+                if o.numel() == x.numel():
+                    o = o.reshape(x.shape)
+                else:
+                    rows[name] = {"shape_own": list(o.shape), "shape_ref": list(x.shape)}
+                    continue
+            sc = float(x.abs().max())
+            rows[name] = {"own_vs_fp64": float((o - x).abs().max()) / sc, "ref32_vs_fp64": float((r.double() - x).abs().max()) / sc,
+                          "own_norm_rel_err": abs(float(o.norm()) - float(x.norm())) / float(x.norm()),
+                          "ref32_norm_rel_err": abs(float(r.double().norm()) - float(x.norm())) / float(x.norm())}
+        out["vs_fp64"]["boundaries"] = rows
     opt.buf.grad.zero_()
     return out
 
@@ -606,7 +652,8 @@ def main():
         for w in names:
             log("parity check %s (full batch through the kernels vs the CPU path on 8 utterances)" % w)
             if w == args.workload:
-                parity[w] = parity_check(pkg, step_fn, cfg, waves, lens, txt, dev, fp64=not args.no_parity_fp64)
+                parity[w] = parity_check(pkg, step_fn, cfg, waves, lens, txt, dev, fp64=not args.no_parity_fp64,
+                                         diagnose=args.parity_diagnose)
             else:
                 cfg_w = pkg.synthetic.load_config(w)
                 vocab_w = cfg_w["data"]["corpus"]["vocab_size"]

@@ -410,8 +410,8 @@ __global__ void __launch_bounds__(CTC_WARPS * 32) ctc_alpha_beta_warp_kernel(Ctc
     // into a per-warp shared-memory ring, one commit group per frame; every lane reads back only what it copied itself.
     // Measured at V = 5000 (1000 utterances, L2 flushed): register ring with the "- lse" next to the load 2.31 ms (the
     // FADD stalls on the load it follows), register ring of raw loads 1.49 ms, this ring 1.30 ms.  What is left is the
-    // DRAM traffic of the gathers themselves: 2 directions x T' x S positions x one 32-byte sector each is about half of
-    // the logits tensor, fetched at sector granularity.
+    // recursion itself: ~300 dependent instructions per frame in a single warp (ncu: top stall `wait`, long_scoreboard
+    // 0.09 warps per issue - profiles/r02_ncu_misc.txt).
     float a[R];
     const float* lseb = p.lse ? p.lse + (long long)b * p.T : nullptr;
     auto prefetch = [&](int st) {                        // frame t0 + dt * st -> ring slot st % CTC_PD

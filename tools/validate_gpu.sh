@@ -14,6 +14,7 @@ print({k:(round(v["ms_per_1000_utt"],3), round(v["frac_hbm"],4)) for k,v in d["m
 print(d["roofline"]); print(d["cpu_baseline"])
 PY
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/v_smoke.log 2>&1; tail -1 $O/v_smoke.log
+if [ -n "$QUICK" ]; then exit 0; fi        # QUICK=1: suite + the driver's default bench line + smoke only
 for w in cfgC cfgD; do
 timeout 600 python bench.py --workload $w --no-cpu-baseline --no-micro --parity-workloads $w > $O/v_bench_$w.json 2> $O/v_bench_$w.log
 done
