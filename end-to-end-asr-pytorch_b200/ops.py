@@ -401,9 +401,10 @@ class BiLSTMFn(Function):
         if _use_umma(I) and H % 4 == 0:
             # own tensor-core kernels throughout: dX = dG . W (W in place), dW_ih = dG^T . X, dW_hh = dG^T . h_prev with
             # h_prev read from the layer output shifted by one step (never materialised); rows written through the gate
-            # permutation by the epilogue
-            # the gate gradient enters three products per direction (dX, dW_ih, dW_hh), the layer output one (dW_hh) and
-            # the layer input one more (dW_ih): with their residuals made once here, none of these kernels splits a tile
+            # permutation by the epilogue.
+            # Residuals made once per step (B200ASR_GEMM_PRESPLIT): "x" = the wide operand of the two weight-gradient
+            # products (layer input for dW_ih, layer output for dW_hh); "1" = the gate gradient as well (it enters
+            # dX, dW_ih and dW_hh), so that none of these kernels splits a tile - measured slower, see the switch above
             pre = x_lo is not None and len(w_ih_lo) == ndir
             g_lo = tf32_residual(gates) if pre else None
             pre_b = pre or PRESPLIT_NT_B
